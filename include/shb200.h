@@ -1,0 +1,141 @@
+/*
+ * shb200.h -- C ABI of libshb200.so: the B200 (sm_100a) kernels behind SemanticHuman's
+ * spiral-mesh-autoencoder training step.
+ *
+ * The reference (XiaokunSun/SemanticHuman) has no FFI of its own: its operator interface for this path is the
+ * module-level Python class API of models.py, and underneath it ATen.  Each entry point below replaces one
+ * group of ATen call sites; the reference line(s) it stands in for are cited per function.  A reference
+ * maintainer would bind these with ctypes (INTEGRATION.md shows the stub) -- exactly what
+ * semantichuman_b200/_capi.py does.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; device pointers unless a parameter says HOST.
+ *   - no allocation, no global state, no synchronisation inside; every launch goes to `stream`
+ *     (a cudaStream_t passed as void*).  The caller owns every buffer, including workspaces.
+ *   - return value: 0 = ok; negative = argument error (SHB_E_*); positive = a cudaError_t from the launch.
+ *     shb_error_string() renders either.  The Python host raises RuntimeError on any non-zero code.
+ *   - activations are row-major (B, rows, C): batch-major, channel fastest -- the reference's own layout
+ *     (models.py:37,48).  `dtype` selects the storage type of activations/weights/gradients; accumulation
+ *     is always fp32.
+ *   - "table": the spiral index table restricted to the rows this call produces, int32, (rows_out, S),
+ *     values in [0, rows_in): the reference's -1 (models.py:42, Python negative index -> dummy row) is
+ *     normalised to rows_in-1 on the host (semantichuman_b200/indexing.py).
+ */
+#ifndef SHB200_H
+#define SHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHB_ABI_VERSION 1
+
+/* activation enum == the strings models.py:19-32 accepts */
+enum { SHB_ACT_IDENTITY = 0, SHB_ACT_RELU = 1, SHB_ACT_ELU = 2, SHB_ACT_LEAKY_RELU = 3, SHB_ACT_SIGMOID = 4,
+       SHB_ACT_TANH = 5 };
+/* storage dtype */
+enum { SHB_F32 = 0, SHB_BF16 = 1 };
+/* argument errors */
+enum { SHB_E_ARG = -1, SHB_E_DTYPE = -2, SHB_E_SHAPE = -3, SHB_E_WORKSPACE = -4, SHB_E_UNSUPPORTED = -5 };
+
+int shb_abi_version(void);
+const char* shb_error_string(int code);
+
+/* ------------------------------------------------------------------ host-side index construction (CPU) */
+
+/* Inverse-spiral CSR (replaces the index_put_(accumulate=True) that autograd runs for
+ * models.py:42).  For every source row u in [0, rows_in): the flat slot positions j*S+s with table[j,s]==u,
+ * ascending -- i.e. a stable counting sort of the flattened table.
+ *   HOST table (rows_out*S), HOST rowptr (rows_in+1), HOST slots (rows_out*S). */
+int shb_build_inverse_spiral_csr(const int32_t* table, int rows_out, int S, int rows_in, int32_t* rowptr,
+                                 int32_t* slots);
+
+/* Same relation keyed by (u, s): for key u*S+s the ascending list of output rows j with table[j,s]==u.
+ * This is the layout the input-gradient kernel consumes (one weight slice per key).
+ *   HOST keyptr (rows_in*S+1), HOST rows (rows_out*S). */
+int shb_build_inverse_spiral_by_slot(const int32_t* table, int rows_out, int S, int rows_in, int32_t* keyptr,
+                                     int32_t* rows);
+
+/* Dense padded sampling matrix (main.py:183-193: D/U .todense(), +1 row/col, corner 1) -> CSR, dropping exact
+ * zeros.  Call with colidx==NULL to count: *nnz_out receives the number of non-zeros.
+ *   HOST dense (rows*cols) fp32, HOST rowptr (rows+1), HOST colidx/vals (cap). */
+int shb_dense_to_csr(const float* dense, int rows, int cols, int32_t* rowptr, int32_t* colidx, float* vals,
+                     int64_t cap, int64_t* nnz_out);
+
+/* CSR (rows x cols) -> CSR of the transpose (cols x rows), entries of each output row in ascending column
+ * order: the operand of the Pool backward  dx = P^T dy  (autograd of models.py:127,148). HOST pointers. */
+int shb_csr_transpose(const int32_t* rowptr, const int32_t* colidx, const float* vals, int rows, int cols,
+                      int32_t* t_rowptr, int32_t* t_colidx, float* t_vals);
+
+/* ------------------------------------------------------------------ SpiralConv (models.py:34-53) */
+
+/* y[b,j,:] = act( W . concat_s x[b, table[j,s], :] + bias ),  and y[b,rows_out-1,:] = 0 when zero_last_row
+ * (the mask multiply of models.py:48-51).  Replaces index (models.py:42) + addmm (:45) + activation (:46)
+ * + mask (:49-51) with one fused gather-GEMM.
+ *   x (B, rows_in, Cin); w (Cout, S*Cin) -- nn.Linear's own layout, k = s*Cin + c, stored as `dtype`;
+ *   bias (Cout) ALWAYS fp32, or NULL;  y (B, rows_out, Cout).
+ *   rows_out may be smaller than rows_in (conv fused with a selection down-pool). */
+int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const void* bias, void* y, int B,
+                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row, int dtype,
+                       void* stream);
+
+/* gz = gy * act'(.) expressed through the saved OUTPUT y, zero on the dummy row when zero_last_row
+ * (ELU' = y+1 for y<=0 etc.).  Replaces EluBackward/MulBackward of models.py:46,51.  In place (gz==gy) ok.
+ *   gy, y, gz (B, rows_out, Cout). */
+int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int act,
+                           int zero_last_row, int dtype, void* stream);
+
+/* Weight/bias gradient: gw[n, s*Cin+c] = sum_{b,j} gz[b,j,n] * x[b, table[j,s], c];  gb[n] = sum gz[b,j,n].
+ * Replaces the  dZ^T . A  mm of AddmmBackward (models.py:45) without materialising A.  Split over rows with a
+ * fixed-order second-stage reduction: bit-reproducible.  gw (Cout, S*Cin) and gb (Cout) are ALWAYS fp32
+ * (master-weight gradients), whatever `dtype` x and gz are stored in.  gb may be NULL.
+ *   workspace: shb_spiralconv_wgrad_workspace() bytes. */
+size_t shb_spiralconv_wgrad_workspace(int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dtype);
+int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz, void* gw, void* gb,
+                             void* workspace, size_t workspace_bytes, int B, int rows_in, int rows_out, int S,
+                             int Cin, int Cout, int dtype, void* stream);
+
+/* Input gradient: gx[b,u,:] = sum_{(j,s): table[j,s]==u} gz[b,j,:] . W[:, s*Cin:(s+1)*Cin], evaluated as a
+ * gather-sum GEMM over the (u,s)-keyed inverse table -- no float atomics, fixed summation order.  Replaces
+ * mm (dA = dZ.W) + index_put_(accumulate=True) of the autograd of models.py:42,45.
+ *   dummy_row_grad: 0 -> gx[b, rows_in-1, :] = 0 (its producer masks it: every layer but the first decoder
+ *   conv of the plain AE); 1 -> computed by a segmented fixed-order reduction. */
+int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const void* w, void* gx,
+                             int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dummy_row_grad,
+                             int dtype, void* stream);
+
+/* ------------------------------------------------------------------ Pool (models.py:127,148,250,276) */
+
+/* y[b,r,:] = sum_e vals[e] * x[b, colidx[e], :]  for e in [rowptr[r], rowptr[r+1]).  CSR SpMM over batch-major
+ * features; replaces torch.matmul with the dense (1, rows_out, rows_in) D/U.  Use the transposed CSR for
+ * the backward.  x (B, rows_in, C); y (B, rows_out, C). */
+int shb_pool_spmm(const void* x, const int32_t* rowptr, const int32_t* colidx, const float* vals, void* y, int B,
+                  int rows_in, int rows_out, int C, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ losses (train_funcs.py:135,145-152,501) */
+
+/* loss = mean |a - b| over n elements (F.l1_loss, main.py:296,311).  Two-stage fixed-order reduction.
+ *   partials: fp32 workspace of shb_l1_loss_workspace(n) bytes; loss_out: device fp32 scalar. */
+size_t shb_l1_loss_workspace(int64_t n);
+int shb_l1_loss_fwd(const void* a, const void* b, int64_t n, void* partials, size_t partials_bytes, float* loss_out,
+                    int dtype, void* stream);
+/* ga = gscale * sign(a-b)/n, gb = -ga; either may be NULL.  gscale: device fp32 scalar (upstream grad). */
+int shb_l1_loss_bwd(const void* a, const void* b, int64_t n, const float* gscale, void* ga, void* gb, int dtype,
+                    void* stream);
+
+/* Part-measure latent loss (train_funcs.py:145-152): m[b,p] = ||z[b,p,:]||_2;
+ *   relative != 0:  loss = mean_{b,i} | m[b,P[i]] / measure[b,Q[i]] - 1 |
+ *   relative == 0:  loss = mean_{b,i} | m[b,P[i]] - measure[b,Q[i]] |
+ * Writes the loss and d loss / d z (unscaled by the upstream grad) in one pass; fp32 only.
+ *   z (B, n_parts, L); measure (B, n_measure); P,Q int32 (n_sel) device; gz (B, n_parts, L). */
+int shb_partnorm_loss_fwd_bwd(const float* z, const float* measure, const int32_t* P, const int32_t* Q, float* loss_out,
+                              float* gz, int B, int n_parts, int L, int n_measure, int n_sel, int relative,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHB200_H */

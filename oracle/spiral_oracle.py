@@ -1,0 +1,217 @@
+"""CPU oracle for the SemanticHuman spiral-autoencoder hot path.   *** TEST INFRASTRUCTURE ***
+
+This file restates, as plain functions over CPU torch tensors (any float dtype; float64 is the tie-breaker),
+the algorithm of the reference's ``models.py`` and of the loss lines of ``train_funcs.py``.  It exists so that
+the CUDA path can be checked on a box that does not have ``/root/reference``.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it;
+the product package ``semantichuman_b200`` never does (tests/test_no_oracle_in_product.py enforces that).
+
+Pinning: the reference has no tests or golden vectors of its own, so the oracle is pinned
+against outputs of the reference itself, generated in the build container by ``tests/golden/make_golden.py``
+(which imports ``/root/reference/models.py`` unmodified) and committed as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks every function below against them.
+
+The hot-path arithmetic of the reference lives in ATen (torch 1.10 pinned, README.md:23; torch 2.11 here):
+``index`` / ``addmm`` / ``elu`` / ``mul`` / ``bmm`` / ``l1_loss``.  The same ATen ops are used below, through a
+functional formulation; gradients come from autograd exactly as in the reference's ``loss.backward()``.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ACTIVATIONS = {
+    # models.py:19-32
+    "relu": torch.relu,
+    "elu": F.elu,
+    "leaky_relu": lambda v: F.leaky_relu(v, 0.02),
+    "sigmoid": torch.sigmoid,
+    "tanh": torch.tanh,
+    "identity": lambda v: v,
+}
+
+
+def spiral_conv(x, spiral_idx, weight, bias, act="elu"):
+    """models.py:34-53.  x (B, V+1, Cin); spiral_idx (V+1, S) or (1|B, V+1, S) integer with -1 == dummy row;
+    weight (Cout, S*Cin) with k = s*Cin + c; returns (B, V+1, Cout) with the last row zeroed."""
+    if act not in ACTIVATIONS:
+        raise NotImplementedError(act)  # models.py:31-32
+    idx = spiral_idx if spiral_idx.dim() == 2 else spiral_idx[0]
+    B, V1, Cin = x.shape
+    S = idx.shape[1]
+    rows = idx.long() % V1  # Python negative indexing: -1 -> V1-1  (models.py:42)
+    gathered = x[:, rows.reshape(-1), :].reshape(B * V1, S * Cin)  # models.py:42
+    out = F.linear(gathered, weight, bias)  # models.py:45
+    out = ACTIVATIONS[act](out).reshape(B, V1, -1)  # models.py:46,48
+    mask = torch.ones(1, V1, 1, dtype=x.dtype)
+    mask[0, -1, 0] = 0.0  # models.py:49-50
+    return out * mask  # models.py:51
+
+
+def pool(P, x):
+    """models.py:127 / :148 -- dense (1, Vout+1, Vin+1) sampling matrix times (B, Vin+1, C)."""
+    return torch.matmul(P.to(x.dtype), x)
+
+
+def conv_plan(filters_enc, filters_dec, n_levels):
+    """Layer list of SpiralAutoencoder.__init__ (models.py:69-113) as tuples
+    (stack, level, in_c, out_c, last_is_identity)."""
+    enc, dec = [], []
+    c = filters_enc[0][0]
+    for i in range(n_levels):
+        if filters_enc[1][i]:
+            enc.append((i, c, filters_enc[1][i], False))
+            c = filters_enc[1][i]
+        enc.append((i, c, filters_enc[0][i + 1], False))
+        c = filters_enc[0][i + 1]
+    c = filters_dec[0][0]
+    for i in range(n_levels):
+        lvl = n_levels - 1 - i  # spiral_sizes[-2-i]
+        if i != n_levels - 1:
+            dec.append((lvl, c, filters_dec[0][i + 1], False))
+            c = filters_dec[0][i + 1]
+            if filters_dec[1][i + 1]:
+                dec.append((lvl, c, filters_dec[1][i + 1], False))
+                c = filters_dec[1][i + 1]
+        else:
+            if filters_dec[1][i + 1]:
+                dec.append((lvl, c, filters_dec[0][i + 1], False))
+                c = filters_dec[0][i + 1]
+                dec.append((lvl, c, filters_dec[1][i + 1], True))
+                c = filters_dec[1][i + 1]
+            else:
+                dec.append((lvl, c, filters_dec[0][i + 1], True))
+                c = filters_dec[0][i + 1]
+    return enc, dec
+
+
+def _run_stack(params, prefix, plan, x, spirals, act, level_hook):
+    """Apply the convs of `plan` in order; `level_hook(level_index_in_stack, x)` runs between levels."""
+    j = 0
+    levels = []
+    for item in plan:
+        if item[0] not in levels:
+            levels.append(item[0])
+    for lvl in levels:
+        x = level_hook("pre", lvl, x)
+        for (l, _cin, _cout, ident) in plan:
+            if l != lvl:
+                continue
+            x = spiral_conv(x, spirals[lvl], params[f"{prefix}.{j}.conv.weight"], params[f"{prefix}.{j}.conv.bias"],
+                            "identity" if ident else act)
+            j += 1
+        x = level_hook("post", lvl, x)
+    return x
+
+
+def ae_encode_trunk(params, x, filters_enc, filters_dec, spirals, D, act="elu"):
+    """Encoder conv + down-pool stack shared by both models (models.py:121-127, 244-250)."""
+    n_levels = len(spirals) - 1
+    enc, _ = conv_plan(filters_enc, filters_dec, n_levels)
+    return _run_stack(params, "conv", enc, x, spirals, act,
+                      lambda when, lvl, v: pool(D[lvl], v) if when == "post" else v)
+
+
+def ae_decode_trunk(params, x, filters_enc, filters_dec, spirals, U, act="elu"):
+    """Decoder up-pool + conv stack shared by both models (models.py:147-153, 275-281)."""
+    n_levels = len(spirals) - 1
+    _, dec = conv_plan(filters_enc, filters_dec, n_levels)
+    return _run_stack(params, "dconv", dec, x, spirals, act,
+                      lambda when, lvl, v: pool(U[lvl], v) if when == "pre" else v)
+
+
+def autoencoder_forward(params, x, filters_enc, filters_dec, sizes, spirals, D, U, act="elu"):
+    """SpiralAutoencoder.forward (models.py:115-162), VAE_flag False.  Returns (x_hat, z)."""
+    B = x.shape[0]
+    h = ae_encode_trunk(params, x, filters_enc, filters_dec, spirals, D, act)
+    z = F.linear(h.reshape(B, -1), params["fc_latent_enc.weight"], params["fc_latent_enc.bias"])  # :129-130
+    h = F.linear(z, params["fc_latent_dec.weight"], params["fc_latent_dec.bias"])  # :144
+    h = h.reshape(B, sizes[-1] + 1, -1)  # :145
+    return ae_decode_trunk(params, h, filters_enc, filters_dec, spirals, U, act), z
+
+
+def multiz_kps_encode(params, kps, kps_index_list):
+    """models.py:233-236."""
+    B = kps.shape[0]
+    return torch.stack([F.linear(kps[:, idx, :].reshape(B, -1), params[f"kps_enc_list.{k}.weight"],
+                                 params[f"kps_enc_list.{k}.bias"]) for k, idx in enumerate(kps_index_list)], dim=1)
+
+
+def multiz_encode(params, x, kps, kps_index_list, part_index_lists, filters_enc, filters_dec, spirals, D, act="elu"):
+    """models.py:238-263.  Returns (z (B,P,L), z_kps (B,P,Lk), dummy (B,1,C))."""
+    B = x.shape[0]
+    h = ae_encode_trunk(params, x, filters_enc, filters_dec, spirals, D, act)
+    z = torch.stack([F.linear(h[:, torch.as_tensor(p), :].reshape(B, -1), params[f"fc_latent_enc_list.{k}.weight"],
+                              params[f"fc_latent_enc_list.{k}.bias"]) for k, p in enumerate(part_index_lists)], dim=1)
+    return z, multiz_kps_encode(params, kps, kps_index_list), h[:, -1:, :]
+
+
+def multiz_decode(params, z, z_kps, dummy, part_index_lists, filters_enc, filters_dec, sizes, spirals, U, act="elu"):
+    """models.py:265-282."""
+    B = z.shape[0]
+    pieces = [F.linear(torch.cat([z[:, k, :], z_kps[:, k, :]], dim=1), params[f"fc_latent_dec_list.{k}.weight"],
+                       params[f"fc_latent_dec_list.{k}.bias"]) for k in range(z.shape[1])]
+    h = torch.cat(pieces, dim=1).reshape(B, sizes[-1], -1)  # :269, rows in part-concatenated order
+    re_index = torch.as_tensor(np.concatenate([np.asarray(p) for p in part_index_lists]))
+    placed = torch.zeros_like(h).index_copy(1, re_index, h)  # :270-272  x[:, re_index] = x[:, arange]
+    h = torch.cat([placed, dummy], dim=1)  # :273
+    return ae_decode_trunk(params, h, filters_enc, filters_dec, spirals, U, act)
+
+
+def multiz_forward(params, x, kps, kps_index_list, part_index_lists, filters_enc, filters_dec, sizes, spirals, D, U,
+                   act="elu"):
+    """models.py:306-310.  Returns (x_hat, z, z_kps)."""
+    z, zk, dummy = multiz_encode(params, x, kps, kps_index_list, part_index_lists, filters_enc, filters_dec, spirals, D,
+                                 act)
+    return multiz_decode(params, z, zk, dummy, part_index_lists, filters_enc, filters_dec, sizes, spirals, U, act), z, zk
+
+
+def l1_loss(a, b):
+    """F.l1_loss as used at train_funcs.py:135,501 (mean over every element incl. the dummy row)."""
+    return (a - b).abs().mean()
+
+
+def zpart_reg(z, measure, P, Q, relative=True):
+    """train_funcs.py:145-152."""
+    m = torch.sqrt(torch.sum(z ** 2, dim=2))
+    if relative:
+        return (m[:, P] / measure[:, Q] - 1.0).abs().mean()
+    return (m[:, P] - measure[:, Q]).abs().mean()
+
+
+# ---------------------------------------------------------------------------------------------- index oracles
+def normalise_spiral(spiral_idx, rows_in=None):
+    """-1 -> rows_in-1 (models.py:42's negative index), int32, 2-D."""
+    a = np.asarray(spiral_idx)
+    if a.ndim == 3:
+        a = a[0]
+    a = a.astype(np.int64)
+    n = a.shape[0] if rows_in is None else rows_in
+    return np.where(a < 0, a + n, a).astype(np.int32)
+
+
+def inverse_spiral_csr(table, rows_in):
+    """stable argsort of the flattened normalised table."""
+    flat = np.asarray(table).reshape(-1).astype(np.int64)
+    slots = np.argsort(flat, kind="stable").astype(np.int32)
+    rowptr = np.zeros(rows_in + 1, np.int32)
+    np.add.at(rowptr, flat + 1, 1)
+    return np.cumsum(rowptr).astype(np.int32), slots
+
+
+def inverse_spiral_by_slot(table, rows_in):
+    """Key u*S+s -> ascending output rows j with table[j,s]==u."""
+    t = np.asarray(table).astype(np.int64)
+    rows_out, S = t.shape
+    key = (t * S + np.arange(S)[None, :]).reshape(-1)
+    order = np.argsort(key, kind="stable")
+    keyptr = np.zeros(rows_in * S + 1, np.int64)
+    np.add.at(keyptr, key + 1, 1)
+    return np.cumsum(keyptr).astype(np.int32), (order // S).astype(np.int32)
+
+
+def dense_to_csr(dense):
+    d = np.asarray(dense)
+    r, c = np.nonzero(d)
+    rowptr = np.zeros(d.shape[0] + 1, np.int32)
+    np.add.at(rowptr, r + 1, 1)
+    return np.cumsum(rowptr).astype(np.int32), c.astype(np.int32), d[r, c].astype(np.float32)

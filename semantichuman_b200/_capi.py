@@ -1,0 +1,60 @@
+"""ctypes binding of libshb200.so (the C ABI declared in include/shb200.h).
+
+There is deliberately no fallback: if the shared library is missing or a symbol is absent the import of the
+product fails loudly (north_star: "no CPU fallback").  Build it with ``python -m semantichuman_b200._build``
+or ``__graft_entry__.build()``.
+"""
+import ctypes
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libshb200.so")
+
+c_int, c_i64, c_size, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
+
+# name -> (restype, argtypes); one entry per declaration in include/shb200.h
+SIGNATURES = {
+    "shb_abi_version": (c_int, []),
+    "shb_error_string": (ctypes.c_char_p, [c_int]),
+    "shb_build_inverse_spiral_csr": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "shb_build_inverse_spiral_by_slot": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "shb_csr_transpose": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 9 + [c_vp]),
+    "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_spiralconv_wgrad_workspace": (c_size, [c_int] * 7),
+    "shb_spiralconv_bwd_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size] + [c_int] * 7 + [c_vp]),
+    "shb_spiralconv_bwd_dgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),
+    "shb_pool_spmm": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 5 + [c_vp]),
+    "shb_l1_loss_workspace": (c_size, [c_i64]),
+    "shb_l1_loss_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_size, c_vp, c_int, c_vp]),
+    "shb_l1_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "shb_partnorm_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+}
+
+ACT_ENUM = {"identity": 0, "relu": 1, "elu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5}
+F32, BF16 = 0, 1
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} not found: the CUDA extension has not been built "
+            "(run `python -m semantichuman_b200._build`); semantichuman_b200 has no CPU fallback")
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.shb_abi_version() != 1:
+        raise ImportError("libshb200.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+LIB_PATH = _LIB_PATH
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib.shb_error_string(int(code)).decode()
+        raise RuntimeError(f"{what} failed with code {code}: {msg}")

@@ -1,0 +1,173 @@
+// Pool (CSR SpMM over batch-major features) and the loss reductions of libshb200.  All HBM-bound:
+// coalesced 16-byte accesses along the channel axis, grids sized in multiples of the SM count,
+// fixed-order reductions (no float atomics).
+#include "shb_common.cuh"
+
+namespace shb {
+
+// ------------------------------------------------------------------------------------------------ Pool SpMM
+// One thread per (b, r, V-wide channel vector).  V = 4 (16 B fp32 / 8 B bf16) when C % 4 == 0, else 1.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) pool_spmm_kernel(const T* __restrict__ x, const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                        T* __restrict__ y, long long total, int rows_in, int rows_out, int CV) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cv = (int)(i % CV);
+    const long long br = i / CV;
+    const int r = (int)(br % rows_out);
+    const long long b = br / rows_out;
+    const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const T* xb = x + (b * rows_in) * (long long)(CV * V) + cv * V;
+    for (int e = e0; e < e1; ++e) {
+      const float a = __ldg(vals + e);
+      const T* px = xb + (long long)__ldg(colidx + e) * (CV * V);
+      float v[V];
+      if (V == 4) Io<T>::ld4(px, v); else v[0] = Io<T>::ld(px);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = fmaf(a, v[k], acc[k]);
+    }
+    T* py = y + br * (long long)(CV * V) + cv * V;
+    if (V == 4) Io<T>::st4(py, acc); else Io<T>::st(py, acc[0]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ L1 loss
+constexpr int L1_BLOCKS = 8 * kNumSMs;
+
+template <typename T>
+__global__ void __launch_bounds__(256) l1_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n,
+                                                         float* __restrict__ partials) {
+  __shared__ float red[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    s += fabsf(Io<T>::ld(a + i) - Io<T>::ld(b + i));
+  s = block_sum<256>(s, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) l1_final_kernel(const float* __restrict__ partials, int np, float inv_n,
+                                                       float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < np; i += 256) s += partials[i];
+  s = block_sum<256>(s, red);
+  if (threadIdx.x == 0) *out = s * inv_n;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n,
+                                                     const float* __restrict__ gscale, T* __restrict__ ga, T* __restrict__ gb) {
+  const float g = __ldg(gscale) / (float)n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = Io<T>::ld(a + i) - Io<T>::ld(b + i);
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    if (ga) Io<T>::st(ga + i, g * sgn);
+    if (gb) Io<T>::st(gb + i, -g * sgn);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ part-norm loss
+// One CTA: (b, i) terms strided over threads, fixed-order block reduction.  gz is zero-filled first.
+__global__ void __launch_bounds__(256) partnorm_kernel(const float* __restrict__ z, const float* __restrict__ measure,
+                                                       const int32_t* __restrict__ P, const int32_t* __restrict__ Q,
+                                                       float* __restrict__ loss_out, float* __restrict__ gz, int B, int n_parts,
+                                                       int L, int n_measure, int n_sel, int relative) {
+  __shared__ float red[8];
+  const long long nz = (long long)B * n_parts * L;
+  for (long long i = threadIdx.x; i < nz; i += 256) gz[i] = 0.f;
+  __syncthreads();
+  const int terms = B * n_sel;
+  const float inv = 1.f / (float)terms;
+  float s = 0.f;
+  for (int q = threadIdx.x; q < terms; q += 256) {
+    const int b = q / n_sel, i = q - b * n_sel;
+    const float* zp = z + ((long long)b * n_parts + P[i]) * L;
+    float ss = 0.f;
+    for (int l = 0; l < L; ++l) ss = fmaf(zp[l], zp[l], ss);
+    const float m = sqrtf(ss);
+    const float tgt = measure[(long long)b * n_measure + Q[i]];
+    const float d = relative ? (m / tgt - 1.f) : (m - tgt);
+    s += fabsf(d);
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    // d|d|/dz = sgn * (1/tgt or 1) * z/m ; sqrt'(0) -> inf in torch, guarded to 0 here
+    const float coef = (m > 0.f) ? sgn * inv * (relative ? 1.f / tgt : 1.f) / m : 0.f;
+    float* gp = gz + ((long long)b * n_parts + P[i]) * L;
+    for (int l = 0; l < L; ++l) gp[l] = coef * zp[l];  // P has distinct entries: one writer per (b, part)
+  }
+  s = block_sum<256>(s, red);
+  if (threadIdx.x == 0) *loss_out = s * inv;
+}
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+int shb_pool_spmm(const void* x, const int32_t* rowptr, const int32_t* colidx, const float* vals, void* y, int B,
+                  int rows_in, int rows_out, int C, int dtype, void* stream) {
+  if (!x || !rowptr || !colidx || !vals || !y) return SHB_E_ARG;
+  if (B <= 0 || rows_in <= 0 || rows_out <= 0 || C <= 0) return SHB_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = (C % 4) == 0;
+  const int CV = v4 ? C / 4 : C;
+  const long long total = (long long)B * rows_out * CV;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+  if (dtype == SHB_F32) {
+    if (v4) pool_spmm_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, rowptr, colidx, vals, (float*)y, total, rows_in, rows_out, CV);
+    else pool_spmm_kernel<float, 1><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, rowptr, colidx, vals, (float*)y, total, rows_in, rows_out, CV);
+  } else if (dtype == SHB_BF16) {
+    if (v4) pool_spmm_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rowptr, colidx, vals, (__nv_bfloat16*)y, total, rows_in, rows_out, CV);
+    else pool_spmm_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rowptr, colidx, vals, (__nv_bfloat16*)y, total, rows_in, rows_out, CV);
+  } else {
+    return SHB_E_DTYPE;
+  }
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t shb_l1_loss_workspace(int64_t n) { (void)n; return (size_t)L1_BLOCKS * sizeof(float); }
+
+int shb_l1_loss_fwd(const void* a, const void* b, int64_t n, void* partials, size_t partials_bytes, float* loss_out,
+                    int dtype, void* stream) {
+  if (!a || !b || !partials || !loss_out || n <= 0) return SHB_E_ARG;
+  if (partials_bytes < shb_l1_loss_workspace(n)) return SHB_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SHB_F32) l1_partial_kernel<float><<<L1_BLOCKS, 256, 0, st>>>((const float*)a, (const float*)b, n, (float*)partials);
+  else if (dtype == SHB_BF16) l1_partial_kernel<__nv_bfloat16><<<L1_BLOCKS, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, (float*)partials);
+  else return SHB_E_DTYPE;
+  SHB_LAUNCH_CHECK();
+  l1_final_kernel<<<1, 256, 0, st>>>((const float*)partials, L1_BLOCKS, 1.0f / (float)n, loss_out);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_l1_loss_bwd(const void* a, const void* b, int64_t n, const float* gscale, void* ga, void* gb, int dtype,
+                    void* stream) {
+  if (!a || !b || !gscale || n <= 0 || (!ga && !gb)) return SHB_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SHB_F32) l1_bwd_kernel<float><<<L1_BLOCKS, 256, 0, st>>>((const float*)a, (const float*)b, n, gscale, (float*)ga, (float*)gb);
+  else if (dtype == SHB_BF16) l1_bwd_kernel<__nv_bfloat16><<<L1_BLOCKS, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, gscale, (__nv_bfloat16*)ga, (__nv_bfloat16*)gb);
+  else return SHB_E_DTYPE;
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_partnorm_loss_fwd_bwd(const float* z, const float* measure, const int32_t* P, const int32_t* Q, float* loss_out,
+                              float* gz, int B, int n_parts, int L, int n_measure, int n_sel, int relative,
+                              void* stream) {
+  if (!z || !measure || !P || !Q || !loss_out || !gz) return SHB_E_ARG;
+  if (B <= 0 || n_parts <= 0 || L <= 0 || n_measure <= 0 || n_sel <= 0) return SHB_E_ARG;
+  partnorm_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(z, measure, P, Q, loss_out, gz, B, n_parts, L, n_measure, n_sel, relative);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

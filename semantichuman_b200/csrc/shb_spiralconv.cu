@@ -1,0 +1,527 @@
+// SpiralConv forward / backward for libshb200 -- exact-fp32 (CUDA-core FFMA) path.
+//
+// One tiled gather-GEMM kernel serves both directions:
+//   forward  (models.py:42-51):  y[(b,j), n]  = act( sum_{s,c} x[b, table[j,s], c] * W[n, s*Cin+c] + bias[n] )
+//   dgrad    (autograd of :42,45): gx[(b,u), c] = sum_{s,n} ( sum_{j in inv(u,s)} gz[b,j,n] ) * W[n, s*Cin+c]
+// i.e. C[M x N] = A[M x K] . Bop[K x N] where a K-slice of A for slot s is a gathered row (forward) or the
+// fixed-order sum of the gathered rows of the (u,s) inverse list (dgrad).  A is never materialised in HBM.
+// The weight gradient streams gz / gathered x once per slot s and reduces over rows in two fixed-order stages.
+#include "shb_common.cuh"
+
+namespace shb {
+
+constexpr int GG_BM = 128;  // rows of (b, vertex) per CTA
+constexpr int GG_BK = 16;   // K elements per stage
+constexpr int GG_NT = 256;
+constexpr int GG_LDA = GG_BM + 4;
+
+struct GGParams {
+  const void* src;         // (B, rows_src, Cs)
+  const int32_t* table;    // SINGLE: (rows_dst, S) rows of src.  MULTI: keyptr (rows_dst*S + 1)
+  const int32_t* list;     // MULTI: concatenated src rows per key
+  const void* w;           // nn.Linear weight (Cout, S*Cin)
+  const void* bias;        // (Cd) or null
+  void* dst;               // (B, rows_dst, Cd)
+  long long M;             // B * rows_dst
+  int rows_src, rows_dst, S, Cs, Cd, K;  // K = S*Cs
+  int act, zero_last, skip_last;
+};
+
+// T: storage type. BN x (TM x TN): CTA / thread tile along N.  MULTI: gather-sum over inverse lists + dgrad weight view.
+template <typename T, int BN, int TM, int TN, bool MULTI>
+__global__ void __launch_bounds__(GG_NT) gather_gemm_kernel(const GGParams p) {
+  constexpr int TX = BN / TN;
+  static_assert((GG_BM / TM) * TX == GG_NT, "thread tiling must cover the CTA tile");
+  constexpr int LDB = BN + 4;
+  constexpr int B_PER_T = (GG_BK * BN + GG_NT - 1) / GG_NT;
+
+  __shared__ __align__(16) float As[GG_BK][GG_LDA];
+  __shared__ __align__(16) float Bs[GG_BK][LDB];
+
+  const T* __restrict__ src = static_cast<const T*>(p.src);
+  const T* __restrict__ w = static_cast<const T*>(p.w);
+  const int t = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * GG_BM;
+  const int n0 = blockIdx.y * BN;
+
+  // ---- A loader role: row r = t/2, 8 consecutive k per thread
+  const int lr = t >> 1, lh = (t & 1) * 8;
+  const long long lm = m0 + lr;
+  const bool lvalid = lm < p.M;
+  int lj = 0;
+  const T* srcb = src;
+  if (lvalid) {
+    const long long b = lm / p.rows_dst;
+    lj = (int)(lm - b * p.rows_dst);
+    srcb = src + b * (long long)p.rows_src * p.Cs;
+  }
+  const bool lskip = !lvalid || (MULTI && p.skip_last && lj == p.rows_dst - 1);
+  const bool vec = (p.Cs % GG_BK) == 0;
+
+  float areg[8];
+  float breg[B_PER_T];
+
+  auto load_a = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) areg[i] = 0.f;
+    if (lskip) return;
+    if (vec) {
+      const int s = k0 / p.Cs;
+      const int c0 = k0 - s * p.Cs + lh;
+      if (!MULTI) {
+        const int row = __ldg(p.table + (long long)lj * p.S + s);
+        Io<T>::ld8(srcb + (long long)row * p.Cs + c0, areg);
+      } else {
+        const int e0 = __ldg(p.table + (long long)lj * p.S + s), e1 = __ldg(p.table + (long long)lj * p.S + s + 1);
+        for (int e = e0; e < e1; ++e) {
+          float v[8];
+          Io<T>::ld8(srcb + (long long)__ldg(p.list + e) * p.Cs + c0, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) areg[i] += v[i];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + lh + i;
+        if (k < p.K) {
+          const int s = k / p.Cs, c = k - s * p.Cs;
+          if (!MULTI) {
+            const int row = __ldg(p.table + (long long)lj * p.S + s);
+            areg[i] = Io<T>::ld(srcb + (long long)row * p.Cs + c);
+          } else {
+            const int e0 = __ldg(p.table + (long long)lj * p.S + s), e1 = __ldg(p.table + (long long)lj * p.S + s + 1);
+            float a = 0.f;
+            for (int e = e0; e < e1; ++e) a += Io<T>::ld(srcb + (long long)__ldg(p.list + e) * p.Cs + c);
+            areg[i] = a;
+          }
+        }
+      }
+    }
+  };
+
+  // Bop[k][n]: forward W[n*K + k]; dgrad (k = s*Cs + c', Cs = Cout, n < Cd = Cin): W[c'*(S*Cd) + s*Cd + n]
+  auto load_b = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < B_PER_T; ++i) {
+      const int e = t + i * GG_NT;
+      float v = 0.f;
+      if (e < GG_BK * BN) {
+        int kk, n;
+        if (!MULTI) { n = e / GG_BK; kk = e - n * GG_BK; } else { kk = e / BN; n = e - kk * BN; }
+        const int k = k0 + kk, ng = n0 + n;
+        if (k < p.K && ng < p.Cd) {
+          if (!MULTI) {
+            v = Io<T>::ld(w + (long long)ng * p.K + k);
+          } else {
+            const int s = k / p.Cs, c = k - s * p.Cs;
+            v = Io<T>::ld(w + (long long)c * ((long long)p.S * p.Cd) + (long long)s * p.Cd + ng);
+          }
+        }
+      }
+      breg[i] = v;
+    }
+  };
+
+  auto store_smem = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[lh + i][lr] = areg[i];
+#pragma unroll
+    for (int i = 0; i < B_PER_T; ++i) {
+      const int e = t + i * GG_NT;
+      if (e < GG_BK * BN) {
+        int kk, n;
+        if (!MULTI) { n = e / GG_BK; kk = e - n * GG_BK; } else { kk = e / BN; n = e - kk * BN; }
+        Bs[kk][n] = breg[i];
+      }
+    }
+  };
+
+  const int tx = t % TX, ty = t / TX;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_a(0);
+  load_b(0);
+  store_smem();
+  __syncthreads();
+  for (int k0 = 0; k0 < p.K; k0 += GG_BK) {
+    const bool more = k0 + GG_BK < p.K;
+    if (more) { load_a(k0 + GG_BK); load_b(k0 + GG_BK); }
+#pragma unroll
+    for (int kk = 0; kk < GG_BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (more) { store_smem(); __syncthreads(); }
+  }
+
+  // ---- epilogue: bias + activation + dummy-row mask
+  T* __restrict__ dst = static_cast<T*>(p.dst);
+  const float* __restrict__ bias = static_cast<const float*>(p.bias);  // fp32 in every mode
+  float bv[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = n0 + tx * TN + j;
+    bv[j] = (bias != nullptr && n < p.Cd) ? __ldg(bias + n) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+    const int j_row = (int)(m % p.rows_dst);
+    const bool zero = p.zero_last && (j_row == p.rows_dst - 1);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < p.Cd) {
+        const float v = zero ? 0.f : act_fwd(acc[i][j] + bv[j], p.act);
+        Io<T>::st(dst + m * p.Cd + n, v);
+      }
+    }
+  }
+}
+
+template <typename T, bool MULTI> static int launch_gather_gemm(const GGParams& p, cudaStream_t st) {
+  const unsigned gx = (unsigned)((p.M + GG_BM - 1) / GG_BM);
+  auto grid = [&](int bn) { return dim3(gx, (unsigned)((p.Cd + bn - 1) / bn), 1); };
+  if (p.Cd <= 4) gather_gemm_kernel<T, 4, 2, 1, MULTI><<<grid(4), GG_NT, 0, st>>>(p);
+  else if (p.Cd <= 16) gather_gemm_kernel<T, 16, 4, 2, MULTI><<<grid(16), GG_NT, 0, st>>>(p);
+  else if (p.Cd <= 32) gather_gemm_kernel<T, 32, 4, 4, MULTI><<<grid(32), GG_NT, 0, st>>>(p);
+  else if (p.Cd <= 64) gather_gemm_kernel<T, 64, 8, 4, MULTI><<<grid(64), GG_NT, 0, st>>>(p);
+  else gather_gemm_kernel<T, 128, 8, 8, MULTI><<<grid(128), GG_NT, 0, st>>>(p);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ act backward
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gz,
+                                                      long long n, int rows_out, int C, int act, int zero_last) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long row = i / C;
+    const bool zero = zero_last && ((int)(row % rows_out) == rows_out - 1);
+    const float g = Io<T>::ld(gy + i);
+    const float d = act_bwd_from_out(Io<T>::ld(y + i), act);
+    Io<T>::st(gz + i, zero ? 0.f : g * d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+constexpr int WG_BKM = 16;  // rows per stage
+constexpr int WG_NT = 256;
+
+struct WGParams {
+  const void* x;         // (B, rows_in, Cin)
+  const int32_t* table;  // (rows_out, S)
+  const void* gz;        // (B, rows_out, Cout)
+  float* ws;             // [splits][Cout*K + Cout] fp32 partials
+  long long M;           // B*rows_out
+  long long rows_per_split;
+  int rows_in, rows_out, S, Cin, Cout, K;
+  int tiles_b;           // number of tiles along Cin
+};
+
+// Output tile BA (Cout) x BB (Cin) for one slot s and one row split; thread tile TA x TB.
+template <typename T, int BA, int BB, int TA, int TB>
+__global__ void __launch_bounds__(WG_NT) wgrad_kernel(const WGParams p) {
+  constexpr int TXB = BB / TB;
+  static_assert((BA / TA) * TXB == WG_NT, "thread tiling must cover the tile");
+  constexpr int G_PER_T = WG_BKM * BA / WG_NT, X_PER_T = WG_BKM * BB / WG_NT;
+  static_assert(G_PER_T >= 1 && X_PER_T >= 1, "tile too small for the loader");
+  __shared__ __align__(16) float Gs[WG_BKM][BA];
+  __shared__ __align__(16) float Xs[WG_BKM][BB];
+
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const T* __restrict__ gz = static_cast<const T*>(p.gz);
+  const int t = threadIdx.x;
+  const int split = blockIdx.x, s = blockIdx.y;
+  const int tile_a = blockIdx.z / p.tiles_b, tile_b = blockIdx.z % p.tiles_b;
+  const int a0 = tile_a * BA, c0 = tile_b * BB;
+  const long long mbeg = (long long)split * p.rows_per_split;
+  const long long mend = min(p.M, mbeg + p.rows_per_split);
+
+  const int tx = t % TXB, ty = t / TXB;
+  float acc[TA][TB];
+  float bacc[TA];
+#pragma unroll
+  for (int i = 0; i < TA; ++i) {
+    bacc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TB; ++j) acc[i][j] = 0.f;
+  }
+  const bool do_bias = (s == 0) && (tile_b == 0) && (tx == 0);
+
+  float greg[G_PER_T], xreg[X_PER_T];
+  auto load = [&](long long mm) {
+#pragma unroll
+    for (int i = 0; i < G_PER_T; ++i) {
+      const int e = t + i * WG_NT;
+      const int mk = e / BA, a = e - mk * BA;
+      const long long m = mm + mk;
+      greg[i] = (m < mend && a0 + a < p.Cout) ? Io<T>::ld(gz + m * p.Cout + a0 + a) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < X_PER_T; ++i) {
+      const int e = t + i * WG_NT;
+      const int mk = e / BB, c = e - mk * BB;
+      const long long m = mm + mk;
+      float v = 0.f;
+      if (m < mend && c0 + c < p.Cin) {
+        const long long b = m / p.rows_out;
+        const int j = (int)(m - b * p.rows_out);
+        const int row = __ldg(p.table + (long long)j * p.S + s);
+        v = Io<T>::ld(x + (b * p.rows_in + row) * (long long)p.Cin + c0 + c);
+      }
+      xreg[i] = v;
+    }
+  };
+  auto store = [&]() {
+#pragma unroll
+    for (int i = 0; i < G_PER_T; ++i) { const int e = t + i * WG_NT; Gs[e / BA][e % BA] = greg[i]; }
+#pragma unroll
+    for (int i = 0; i < X_PER_T; ++i) { const int e = t + i * WG_NT; Xs[e / BB][e % BB] = xreg[i]; }
+  };
+
+  if (mbeg < mend) {
+    load(mbeg);
+    store();
+    __syncthreads();
+    for (long long mm = mbeg; mm < mend; mm += WG_BKM) {
+      const bool more = mm + WG_BKM < mend;
+      if (more) load(mm + WG_BKM);
+#pragma unroll
+      for (int mk = 0; mk < WG_BKM; ++mk) {
+        float a[TA], b[TB];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) a[i] = Gs[mk][ty * TA + i];
+#pragma unroll
+        for (int j = 0; j < TB; ++j) b[j] = Xs[mk][tx * TB + j];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          if (do_bias) bacc[i] += a[i];
+#pragma unroll
+          for (int j = 0; j < TB; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+      }
+      __syncthreads();
+      if (more) { store(); __syncthreads(); }
+    }
+  }
+  float* ws = p.ws + (long long)split * ((long long)p.Cout * p.K + p.Cout);
+#pragma unroll
+  for (int i = 0; i < TA; ++i) {
+    const int n = a0 + ty * TA + i;
+    if (n >= p.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < TB; ++j) {
+      const int c = c0 + tx * TB + j;
+      if (c < p.Cin) ws[(long long)n * p.K + (long long)s * p.Cin + c] = acc[i][j];
+    }
+    if (do_bias) ws[(long long)p.Cout * p.K + n] = bacc[i];
+  }
+}
+
+// out[i] = sum over splits (ascending) of ws[split][i]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long per_split,
+                                                           long long n_w, float* __restrict__ gw, float* __restrict__ gb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_split) return;
+  float a = 0.f;
+  for (int sp = 0; sp < splits; ++sp) a += ws[(long long)sp * per_split + i];
+  if (i < n_w) gw[i] = a;
+  else if (gb != nullptr) gb[i - n_w] = a;
+}
+
+static int wgrad_splits(long long M, int S, int tiles) {
+  // aim at ~4 CTAs per SM in flight, never fewer than 512 rows per split
+  long long want = (4LL * kNumSMs + (long long)S * tiles - 1) / ((long long)S * tiles);
+  long long cap = (M + 511) / 512;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+struct WGConfig { int ba, bb; };
+static WGConfig wgrad_config(int Cin, int Cout) {
+  const int mn = Cin < Cout ? Cin : Cout;
+  if (mn > 32) return {64, 64};
+  if (mn > 16) return {32, 32};
+  return {16, 16};
+}
+
+// ------------------------------------------------------------------------------------------------ dummy-row dgrad
+// gx[b, rows_in-1, c] = sum_s ( sum_{j in inv(dummy, s)} gz[b,j,:] ) . W[:, s*Cin + c];  one CTA per sample.
+template <typename T>
+__global__ void __launch_bounds__(256) dgrad_dummy_kernel(const T* __restrict__ gz, const int32_t* __restrict__ keyptr,
+                                                          const int32_t* __restrict__ rows, const T* __restrict__ w,
+                                                          T* __restrict__ gx, int rows_in, int rows_out, int S, int Cin,
+                                                          int Cout) {
+  extern __shared__ float sm[];  // red[256] + G[Cout] + out[Cin]
+  float* red = sm;
+  float* G = sm + 256;
+  float* out = G + Cout;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int u = rows_in - 1;
+  const T* gzb = gz + (long long)b * rows_out * Cout;
+  for (int c = t; c < Cin; c += 256) out[c] = 0.f;
+  // lanes: groups of `Cout`-wide rows; thread t handles channel n = t % npad in entry-group t / npad
+  int npad = 1;
+  while (npad < Cout && npad < 256) npad <<= 1;
+  const int groups = 256 / npad;
+  const int n = t % npad, g = t / npad;
+  const int K = S * Cin;
+  for (int s = 0; s < S; ++s) {
+    const int e0 = keyptr[(long long)u * S + s], e1 = keyptr[(long long)u * S + s + 1];
+    for (int nb = 0; nb < Cout; nb += npad) {  // only loops when Cout > 256
+      float a = 0.f;
+      if (nb + n < Cout)
+        for (int e = e0 + g; e < e1; e += groups) a += Io<T>::ld(gzb + (long long)rows[e] * Cout + nb + n);
+      __syncthreads();
+      red[t] = a;
+      __syncthreads();
+      if (g == 0 && nb + n < Cout) {
+        float r = 0.f;
+        for (int q = 0; q < groups; ++q) r += red[q * npad + n];
+        G[nb + n] = r;
+      }
+    }
+    __syncthreads();
+    for (int c = t; c < Cin; c += 256) {
+      float a = out[c];
+      for (int nn = 0; nn < Cout; ++nn) a = fmaf(G[nn], Io<T>::ld(w + (long long)nn * K + (long long)s * Cin + c), a);
+      out[c] = a;
+    }
+    __syncthreads();
+  }
+  for (int c = t; c < Cin; c += 256) Io<T>::st(gx + ((long long)b * rows_in + u) * Cin + c, out[c]);
+}
+
+template <typename T>
+static int wgrad_launch(const WGParams& p0, int splits, void* gw, void* gb, cudaStream_t st) {
+  WGParams p = p0;
+  const WGConfig c = wgrad_config(p.Cin, p.Cout);
+  const int tiles_a = ceil_div(p.Cout, c.ba);
+  p.tiles_b = ceil_div(p.Cin, c.bb);
+  dim3 grid((unsigned)splits, (unsigned)p.S, (unsigned)(tiles_a * p.tiles_b));
+  if (c.ba == 64) wgrad_kernel<T, 64, 64, 4, 4><<<grid, WG_NT, 0, st>>>(p);
+  else if (c.ba == 32) wgrad_kernel<T, 32, 32, 2, 2><<<grid, WG_NT, 0, st>>>(p);
+  else wgrad_kernel<T, 16, 16, 1, 1><<<grid, WG_NT, 0, st>>>(p);
+  SHB_LAUNCH_CHECK();
+  const long long n_w = (long long)p.Cout * p.K, per = n_w + p.Cout;
+  wgrad_reduce_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(p.ws, splits, per, n_w, (float*)gw, (float*)gb);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const void* bias, void* y, int B,
+                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row, int dtype,
+                       void* stream) {
+  if (!x || !table || !w || !y) return SHB_E_ARG;
+  if (B <= 0 || rows_in <= 0 || rows_out <= 0 || S <= 0 || Cin <= 0 || Cout <= 0) return SHB_E_ARG;
+  if (act < SHB_ACT_IDENTITY || act > SHB_ACT_TANH) return SHB_E_ARG;
+  GGParams p{};
+  p.src = x; p.table = table; p.list = nullptr; p.w = w; p.bias = bias; p.dst = y;
+  p.M = (long long)B * rows_out;
+  p.rows_src = rows_in; p.rows_dst = rows_out; p.S = S; p.Cs = Cin; p.Cd = Cout; p.K = S * Cin;
+  p.act = act; p.zero_last = zero_last_row; p.skip_last = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SHB_F32) return launch_gather_gemm<float, false>(p, st);
+  if (dtype == SHB_BF16) return launch_gather_gemm<__nv_bfloat16, false>(p, st);
+  return SHB_E_DTYPE;
+}
+
+int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int act,
+                           int zero_last_row, int dtype, void* stream) {
+  if (!gy || !y || !gz || B <= 0 || rows_out <= 0 || Cout <= 0) return SHB_E_ARG;
+  if (act < SHB_ACT_IDENTITY || act > SHB_ACT_TANH) return SHB_E_ARG;
+  const long long n = (long long)B * rows_out * Cout;
+  const int blocks = (int)((n + 255) / 256 < 8LL * kNumSMs ? (n + 255) / 256 : 8LL * kNumSMs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SHB_F32)
+    act_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, n, rows_out, Cout, act,
+                                                  zero_last_row);
+  else if (dtype == SHB_BF16)
+    act_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+                                                          (__nv_bfloat16*)gz, n, rows_out, Cout, act, zero_last_row);
+  else
+    return SHB_E_DTYPE;
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t shb_spiralconv_wgrad_workspace(int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dtype) {
+  (void)rows_in; (void)dtype;
+  const WGConfig c = wgrad_config(Cin, Cout);
+  const int tiles = ceil_div(Cout, c.ba) * ceil_div(Cin, c.bb);
+  const int splits = wgrad_splits((long long)B * rows_out, S, tiles);
+  return (size_t)splits * ((size_t)Cout * S * Cin + Cout) * sizeof(float);
+}
+
+int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz, void* gw, void* gb,
+                             void* workspace, size_t workspace_bytes, int B, int rows_in, int rows_out, int S,
+                             int Cin, int Cout, int dtype, void* stream) {
+  if (!x || !table || !gz || !gw || !workspace) return SHB_E_ARG;
+  if (B <= 0 || rows_in <= 0 || rows_out <= 0 || S <= 0 || Cin <= 0 || Cout <= 0) return SHB_E_ARG;
+  if (workspace_bytes < shb_spiralconv_wgrad_workspace(B, rows_in, rows_out, S, Cin, Cout, dtype)) return SHB_E_WORKSPACE;
+  const WGConfig c = wgrad_config(Cin, Cout);
+  const int tiles = ceil_div(Cout, c.ba) * ceil_div(Cin, c.bb);
+  WGParams p{};
+  p.x = x; p.table = table; p.gz = gz; p.ws = (float*)workspace;
+  p.M = (long long)B * rows_out;
+  const int splits = wgrad_splits(p.M, S, tiles);
+  p.rows_per_split = ((p.M + splits - 1) / splits + WG_BKM - 1) / WG_BKM * WG_BKM;
+  p.rows_in = rows_in; p.rows_out = rows_out; p.S = S; p.Cin = Cin; p.Cout = Cout; p.K = S * Cin;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SHB_F32) return wgrad_launch<float>(p, splits, gw, gb, st);
+  if (dtype == SHB_BF16) return wgrad_launch<__nv_bfloat16>(p, splits, gw, gb, st);
+  return SHB_E_DTYPE;
+}
+
+int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const void* w, void* gx,
+                             int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dummy_row_grad,
+                             int dtype, void* stream) {
+  if (!gz || !keyptr || !rows || !w || !gx) return SHB_E_ARG;
+  if (B <= 0 || rows_in <= 0 || rows_out <= 0 || S <= 0 || Cin <= 0 || Cout <= 0) return SHB_E_ARG;
+  GGParams p{};
+  p.src = gz; p.table = keyptr; p.list = rows; p.w = w; p.bias = nullptr; p.dst = gx;
+  p.M = (long long)B * rows_in;
+  p.rows_src = rows_out; p.rows_dst = rows_in; p.S = S; p.Cs = Cout; p.Cd = Cin; p.K = S * Cout;
+  p.act = SHB_ACT_IDENTITY; p.zero_last = 0; p.skip_last = 1;  // dummy row -> 0 here, filled below if wanted
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (dtype == SHB_F32) rc = launch_gather_gemm<float, true>(p, st);
+  else if (dtype == SHB_BF16) rc = launch_gather_gemm<__nv_bfloat16, true>(p, st);
+  else return SHB_E_DTYPE;
+  if (rc != 0 || !dummy_row_grad) return rc;
+  const size_t smem = (256 + (size_t)Cout + Cin) * sizeof(float);
+  if (dtype == SHB_F32)
+    dgrad_dummy_kernel<float><<<B, 256, smem, st>>>((const float*)gz, keyptr, rows, (const float*)w, (float*)gx, rows_in,
+                                                    rows_out, S, Cin, Cout);
+  else
+    dgrad_dummy_kernel<__nv_bfloat16><<<B, 256, smem, st>>>((const __nv_bfloat16*)gz, keyptr, rows,
+                                                            (const __nv_bfloat16*)w, (__nv_bfloat16*)gx, rows_in,
+                                                            rows_out, S, Cin, Cout);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+"""torch.autograd.Functions over the C ABI of libshb200 (include/shb200.h).
+
+torch is plumbing here: it owns device memory, streams and the autograd graph; every arithmetic step of the
+path is a kernel of libshb200.  Tensors must be CUDA tensors -- there is no CPU path (north_star).
+Forward runs on the calling thread, backward on the autograd engine's device thread; both take the stream from
+``torch.cuda.current_stream()`` at call time (threading).
+"""
+import torch
+
+from . import _capi
+from ._capi import ACT_ENUM, check, lib
+
+_DT = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16}
+
+# launch counter: bench.py reports how many libshb200 kernels a step launches ("gpu_launches")
+LAUNCHES = {"n": 0}
+
+
+def _count(n=1):
+    LAUNCHES["n"] += n
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"semantichuman_b200 supports float32 and bfloat16 activations, got {t.dtype}") from None
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("semantichuman_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class SpiralConvFn(torch.autograd.Function):
+    """y = mask * act(W . gather(x) + b)   (models.py:34-53) -- one fused kernel forward; backward =
+    act' kernel + weight-gradient kernel (+ fixed-order reduce) + inverse-table input-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, geom, act):
+        _cuda(x, weight, bias)
+        if x.dim() != 3:
+            raise ValueError("x must be (B, V+1, C)")
+        x = x.contiguous()
+        B, rows_in, cin = x.shape
+        cout, k = weight.shape
+        if rows_in != geom.rows_in or k != geom.S * cin:
+            raise ValueError(f"shape mismatch: x {tuple(x.shape)}, weight {tuple(weight.shape)}, "
+                             f"geometry rows_in={geom.rows_in} S={geom.S}")
+        if geom.table.device != x.device:
+            raise RuntimeError("spiral tables live on a different device than x")
+        w = weight.detach().to(x.dtype).contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty((B, geom.rows_out, cout), dtype=x.dtype, device=x.device)
+        check(lib.shb_spiralconv_fwd(_p(x), _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, geom.S,
+                                     cin, cout, act, int(geom.zero_last_row), _dt(x), _stream()), "shb_spiralconv_fwd")
+        _count()
+        ctx.save_for_backward(x, w, y)
+        ctx.geom, ctx.act, ctx.has_bias = geom, act, bias is not None
+        ctx.wdtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        geom, act = ctx.geom, ctx.act
+        B, rows_in, cin = x.shape
+        cout = w.shape[0]
+        gy = gy.contiguous()
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
+        dt, st = _dt(x), _stream()
+        gz = torch.empty_like(gy)
+        check(lib.shb_spiralconv_bwd_act(_p(gy), _p(y), _p(gz), B, geom.rows_out, cout, act, int(geom.zero_last_row), dt, st),
+              "shb_spiralconv_bwd_act")
+        _count()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            nbytes = lib.shb_spiralconv_wgrad_workspace(B, rows_in, geom.rows_out, geom.S, cin, cout, dt)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            gw = torch.empty((cout, geom.S * cin), dtype=torch.float32, device=x.device)
+            gb = torch.empty((cout,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            check(lib.shb_spiralconv_bwd_wgrad(_p(x), _p(geom.table), _p(gz), _p(gw), _p(gb), _p(ws), nbytes, B, rows_in,
+                                               geom.rows_out, geom.S, cin, cout, dt, st), "shb_spiralconv_bwd_wgrad")
+            _count(2)
+            if ctx.wdtype != torch.float32:
+                gw = gw.to(ctx.wdtype)
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            check(lib.shb_spiralconv_bwd_dgrad(_p(gz), _p(geom.keyptr), _p(geom.inv_rows), _p(w), _p(gx), B, rows_in,
+                                               geom.rows_out, geom.S, cin, cout, int(geom.dummy_row_grad), dt, st),
+                  "shb_spiralconv_bwd_dgrad")
+            _count(2 if geom.dummy_row_grad else 1)
+        return gx, gw, gb, None, None
+
+
+class PoolFn(torch.autograd.Function):
+    """y[b] = P . x[b] with P in CSR (models.py:127,148); backward uses the CSR of P^T."""
+
+    @staticmethod
+    def forward(ctx, x, pm):
+        _cuda(x)
+        x = x.contiguous()
+        B, rows_in, C = x.shape
+        if rows_in != pm.rows_in:
+            raise ValueError(f"pool expects {pm.rows_in} rows, got {rows_in}")
+        y = torch.empty((B, pm.rows_out, C), dtype=x.dtype, device=x.device)
+        check(lib.shb_pool_spmm(_p(x), _p(pm.rowptr), _p(pm.colidx), _p(pm.vals), _p(y), B, rows_in, pm.rows_out, C,
+                                _dt(x), _stream()), "shb_pool_spmm")
+        _count()
+        ctx.pm = pm
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        pm = ctx.pm
+        gy = gy.contiguous()
+        B, _, C = gy.shape
+        gx = torch.empty((B, pm.rows_in, C), dtype=gy.dtype, device=gy.device)
+        check(lib.shb_pool_spmm(_p(gy), _p(pm.t_rowptr), _p(pm.t_colidx), _p(pm.t_vals), _p(gx), B, pm.rows_out,
+                                pm.rows_in, C, _dt(gy), _stream()), "shb_pool_spmm(bwd)")
+        _count()
+        return gx, None
+
+
+class L1LossFn(torch.autograd.Function):
+    """mean |a - b|  (F.l1_loss, train_funcs.py:135,501); fixed-order two-stage reduction."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _cuda(a, b)
+        if a.shape != b.shape or a.dtype != b.dtype:
+            raise ValueError("l1_loss operands must have the same shape and dtype")
+        a, b = a.contiguous(), b.contiguous()
+        n = a.numel()
+        nbytes = lib.shb_l1_loss_workspace(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        check(lib.shb_l1_loss_fwd(_p(a), _p(b), n, _p(ws), nbytes, _p(out), _dt(a), _stream()), "shb_l1_loss_fwd")
+        _count(2)
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.detach().float().contiguous()
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        if ga is None and gb is None:
+            return None, None
+        check(lib.shb_l1_loss_bwd(_p(a), _p(b), a.numel(), _p(g), _p(ga), _p(gb), _dt(a), _stream()), "shb_l1_loss_bwd")
+        _count()
+        return ga, gb
+
+
+class PartNormLossFn(torch.autograd.Function):
+    """Part-measure latent loss (train_funcs.py:145-152); loss and d loss/d z in one launch."""
+
+    @staticmethod
+    def forward(ctx, z, measure, P, Q, relative):
+        _cuda(z, measure, P, Q)
+        z = z.float().contiguous()
+        measure = measure.float().contiguous()
+        B, n_parts, L = z.shape
+        out = torch.empty((), dtype=torch.float32, device=z.device)
+        gz = torch.empty_like(z)
+        check(lib.shb_partnorm_loss_fwd_bwd(_p(z), _p(measure), _p(P), _p(Q), _p(out), _p(gz), B, n_parts, L,
+                                            measure.shape[1], P.numel(), int(bool(relative)), _stream()),
+              "shb_partnorm_loss_fwd_bwd")
+        _count()
+        ctx.save_for_backward(gz)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (gz,) = ctx.saved_tensors
+        return gz * g, None, None, None, None
+
+
+def spiral_conv(x, weight, bias, geom, activation="elu"):
+    if activation not in ACT_ENUM:
+        raise NotImplementedError(activation)
+    return SpiralConvFn.apply(x, weight, bias, geom, ACT_ENUM[activation])
+
+
+def pool(x, pm):
+    return PoolFn.apply(x, pm)
+
+
+def l1_loss(a, b):
+    return L1LossFn.apply(a, b)
+
+
+def partnorm_loss(z, measure, P, Q, relative=True):
+    return PartNormLossFn.apply(z, measure, P, Q, relative)

@@ -1,0 +1,175 @@
+"""Host-side index layer: spiral tables, inverse-spiral tables, CSR forms of the D/U sampling matrices.
+
+Everything here runs once at model construction (setup time), through the host entry points of libshb200
+(shb_build_inverse_spiral_csr / _by_slot, shb_dense_to_csr, shb_csr_transpose), and leaves int32 tables resident on
+the device.  Reference contracts: spirals as built by utils_spiral.py:45-95 and cast at main.py:203
+((1, V+1, S) int64, -1 == dummy vertex); D/U as padded at main.py:183-205 (dense (1, Vout+1, Vin+1) fp32).
+"""
+import numpy as np
+import torch
+
+from ._capi import check, lib
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def normalise_spiral(spiral_adj, rows_in=None):
+    """(1|B, V+1, S) or (V+1, S), any integer/float dtype, -1 -> rows_in-1 (the Python negative index of
+    models.py:42).  Returns a host int32 (V+1, S) array.  Batch-replicated inputs (models.py:122 passes
+    S[i].repeat(B,1,1)) are validated once and only the first copy is kept."""
+    t = spiral_adj.detach().cpu() if isinstance(spiral_adj, torch.Tensor) else torch.as_tensor(np.asarray(spiral_adj))
+    if t.dim() == 3:
+        if t.shape[0] > 1 and not bool((t == t[:1]).all()):
+            raise ValueError("spiral_adj differs across the batch; SpiralConv expects a batch-replicated table")
+        t = t[0]
+    if t.dim() != 2:
+        raise ValueError("spiral_adj must be (B, V+1, S) or (V+1, S)")
+    a = t.numpy().astype(np.int64)
+    n = a.shape[0] if rows_in is None else int(rows_in)
+    if a.min() < -n or a.max() >= n:
+        raise ValueError("spiral index out of range")
+    return _i32(np.where(a < 0, a + n, a))
+
+
+def build_inverse_spiral_csr(table, rows_in):
+    """SURVEY 8(a-8) inverse-spiral CSR: (rowptr (rows_in+1), slots (rows_out*S)) host int32."""
+    table = _i32(table)
+    rows_out, S = table.shape
+    rowptr = np.empty(rows_in + 1, np.int32)
+    slots = np.empty(rows_out * S, np.int32)
+    check(lib.shb_build_inverse_spiral_csr(table.ctypes.data, rows_out, S, rows_in, rowptr.ctypes.data,
+                                           slots.ctypes.data), "shb_build_inverse_spiral_csr")
+    return rowptr, slots
+
+
+def build_inverse_spiral_by_slot(table, rows_in):
+    """(keyptr (rows_in*S+1), rows (rows_out*S)) host int32; key = u*S+s."""
+    table = _i32(table)
+    rows_out, S = table.shape
+    keyptr = np.empty(rows_in * S + 1, np.int32)
+    rows = np.empty(rows_out * S, np.int32)
+    check(lib.shb_build_inverse_spiral_by_slot(table.ctypes.data, rows_out, S, rows_in, keyptr.ctypes.data,
+                                               rows.ctypes.data), "shb_build_inverse_spiral_by_slot")
+    return keyptr, rows
+
+
+def dense_to_csr(dense):
+    """fp32 dense (rows, cols) -> (rowptr, colidx, vals) host arrays, exact zeros dropped."""
+    d = np.ascontiguousarray(dense, dtype=np.float32)
+    rows, cols = d.shape
+    nnz = np.zeros(1, np.int64)
+    check(lib.shb_dense_to_csr(d.ctypes.data, rows, cols, None, None, None, 0, nnz.ctypes.data), "shb_dense_to_csr")
+    rowptr = np.empty(rows + 1, np.int32)
+    colidx = np.empty(max(int(nnz[0]), 1), np.int32)
+    vals = np.empty(max(int(nnz[0]), 1), np.float32)
+    check(lib.shb_dense_to_csr(d.ctypes.data, rows, cols, rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data,
+                               int(nnz[0]), nnz.ctypes.data), "shb_dense_to_csr")
+    return rowptr, colidx[: int(nnz[0])], vals[: int(nnz[0])]
+
+
+def csr_transpose(rowptr, colidx, vals, rows, cols):
+    rowptr, colidx = _i32(rowptr), _i32(colidx)
+    vals = np.ascontiguousarray(vals, dtype=np.float32)
+    t_rowptr = np.empty(cols + 1, np.int32)
+    t_colidx = np.empty(max(len(colidx), 1), np.int32)
+    t_vals = np.empty(max(len(vals), 1), np.float32)
+    if len(colidx) == 0:
+        t_rowptr[:] = 0
+        return t_rowptr, t_colidx[:0], t_vals[:0]
+    check(lib.shb_csr_transpose(rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data, rows, cols,
+                                t_rowptr.ctypes.data, t_colidx.ctypes.data, t_vals.ctypes.data), "shb_csr_transpose")
+    return t_rowptr, t_colidx, t_vals
+
+
+class SpiralGeometry:
+    """Device-resident index tables for one SpiralConv call shape.
+
+    table    (rows_out, S) int32: source row of x for output row j, slot s (already -1 -> rows_in-1).
+    keyptr / inv_rows: the (u, s)-keyed inverse relation used by the input-gradient kernel.
+    rows_out < rows_in when the conv is fused with a selection down-pool (output rows = kept vertices + dummy).
+    """
+
+    def __init__(self, table, rows_in, device, zero_last_row=True, dummy_row_grad=True):
+        table = _i32(table)
+        self.rows_out, self.S = int(table.shape[0]), int(table.shape[1])
+        self.rows_in = int(rows_in)
+        self.zero_last_row = bool(zero_last_row)
+        self.dummy_row_grad = bool(dummy_row_grad)
+        self.table_host = table
+        keyptr, rows = build_inverse_spiral_by_slot(table, self.rows_in)
+        self.device = torch.device(device)
+        self.table = torch.from_numpy(table).to(self.device)
+        self.keyptr = torch.from_numpy(keyptr).to(self.device)
+        self.inv_rows = torch.from_numpy(rows).to(self.device)
+
+    @classmethod
+    def from_spiral(cls, spiral_adj, device, **kw):
+        table = normalise_spiral(spiral_adj)
+        return cls(table, table.shape[0], device, **kw)
+
+    def restricted(self, out_rows, **kw):
+        """Geometry that evaluates only `out_rows` (ascending source-vertex ids, dummy last)."""
+        out_rows = np.asarray(out_rows, dtype=np.int64)
+        return SpiralGeometry(self.table_host[out_rows], self.rows_in, self.device, **kw)
+
+    def with_flags(self, **kw):
+        g = object.__new__(SpiralGeometry)
+        g.__dict__.update(self.__dict__)
+        for k, v in kw.items():
+            setattr(g, k, bool(v))
+        return g
+
+
+class PoolMatrix:
+    """A D or U sampling matrix in CSR form (forward) plus the CSR of its transpose (backward), on the device."""
+
+    def __init__(self, rowptr, colidx, vals, rows, cols, device):
+        self.rows_out, self.rows_in = int(rows), int(cols)
+        rowptr, colidx = _i32(rowptr), _i32(colidx)
+        vals = np.ascontiguousarray(vals, dtype=np.float32)
+        self.nnz = int(len(colidx))
+        counts = np.diff(rowptr)
+        # structural fact the fused conv+down-pool relies on (mesh_sampling.py:214-227): one 1.0 per row
+        self.is_selection = bool(self.nnz == rows and (counts == 1).all() and (vals == 1.0).all())
+        self.selection_cols = colidx.copy() if self.is_selection else None
+        t_rowptr, t_colidx, t_vals = csr_transpose(rowptr, colidx, vals, rows, cols)
+        self.device = torch.device(device)
+        dev = self.device
+        self.rowptr = torch.from_numpy(rowptr).to(dev)
+        self.colidx = torch.from_numpy(np.ascontiguousarray(colidx)).to(dev)
+        self.vals = torch.from_numpy(vals).to(dev)
+        self.t_rowptr = torch.from_numpy(t_rowptr).to(dev)
+        self.t_colidx = torch.from_numpy(np.ascontiguousarray(t_colidx)).to(dev)
+        self.t_vals = torch.from_numpy(np.ascontiguousarray(t_vals)).to(dev)
+
+    @classmethod
+    def from_dense(cls, dense, device=None):
+        """dense: (1, rows, cols) or (rows, cols) tensor/array exactly as main.py:183-205 builds it."""
+        if isinstance(dense, torch.Tensor):
+            device = dense.device if device is None else device
+            d = dense.detach().to("cpu", torch.float32).numpy()
+        else:
+            d = np.asarray(dense, dtype=np.float32)
+        if d.ndim == 3:
+            if d.shape[0] != 1:
+                raise ValueError("sampling matrix must have a leading dimension of 1")
+            d = d[0]
+        rowptr, colidx, vals = dense_to_csr(d)
+        return cls(rowptr, colidx, vals, d.shape[0], d.shape[1], device)
+
+    @classmethod
+    def from_scipy_padded(cls, m, device):
+        """scipy sparse (Vout, Vin) un-padded matrix -> padded CSR with the dummy->dummy corner (main.py:190-191),
+        explicit zeros dropped (the dense path cannot see them either)."""
+        import scipy.sparse as sp
+
+        m = sp.csr_matrix(m).astype(np.float32)
+        m.eliminate_zeros()
+        m.sort_indices()
+        rows, cols = m.shape
+        rowptr = np.concatenate([m.indptr, [m.indptr[-1] + 1]]).astype(np.int32)
+        colidx = np.concatenate([m.indices, [cols]]).astype(np.int32)
+        vals = np.concatenate([m.data, [1.0]]).astype(np.float32)
+        return cls(rowptr, colidx, vals, rows + 1, cols + 1, device)

@@ -1,0 +1,295 @@
+"""Drop-in replacements for the reference's ``models.py`` classes, running on libshb200 kernels.
+
+Same constructor and forward signatures, same ``state_dict`` keys (``conv.{j}.conv.weight`` ...,
+``fc_latent_enc.*``, ``fc_latent_dec.*``, ``fc_latent_enc_list.{k}.*``, ``fc_latent_dec_list.{k}.*``,
+``kps_enc_list.{k}.*``; models.py:81-86,113,198-204,230), so the reference's training loop (train_funcs.py), entry
+script (main.py:241-259) and editing script (demo.py / utils_SH.py:358-376) can construct and call them unchanged
+and load the reference's checkpoints.
+
+What is different underneath
+  * SpiralConv is ONE fused gather-GEMM kernel (+bias +activation +dummy-row mask); the gathered
+    (B*(V+1), S*Cin) matrix of models.py:42 is never materialised.
+  * The dense D/U ``torch.matmul`` of models.py:127,148 becomes a CSR SpMM; D matrices that are pure row
+    selections (mesh_sampling.py:214-227) are folded into the preceding conv, which then only evaluates the kept
+    vertices (bit-identical, half the work).
+  * Index tables are built once per level at construction; ``S[i].repeat(B,1,1)`` (models.py:122) is never formed.
+  * No CPU path: CPU tensors raise.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functions as fn
+from ._capi import ACT_ENUM
+from .indexing import PoolMatrix, SpiralGeometry
+
+# models.py:169,285 read cfg.CONSTANTS.newskl_list; this is its default (configure/cfgs.py:21-23).  A caller that
+# merges a yaml with a longer list (traincfg.yaml:55) can assign `model.newskl_list`.
+DEFAULT_NEWSKL_LIST = [[0, 1], [0, 2], [0, 6], [1, 4], [2, 5], [6, 9], [4, 7], [5, 8], [9, 12], [9, 16], [9, 17],
+                       [7, 10], [8, 11], [12, 15], [16, 18], [17, 19], [18, 20], [19, 21], [20, 22], [21, 23],
+                       [20, 24], [21, 25], [20, 26], [21, 27], [15, 28], [15, 29], [15, 30]]
+
+
+class SpiralConv(nn.Module):
+    """models.py:10-53.  ``forward(x, spiral_adj)`` accepts the reference's (B, V+1, S) int64 tensor (validated
+    and cached per table) or, on the fast path, a prebuilt :class:`SpiralGeometry`."""
+
+    def __init__(self, in_c, spiral_size, out_c, activation='elu', bias=True, device=None):
+        super().__init__()
+        if activation not in ACT_ENUM:
+            raise NotImplementedError()  # models.py:31-32
+        self.in_c = in_c
+        self.out_c = out_c
+        self.spiral_size = spiral_size
+        self.device = device
+        self.activation_name = activation
+        self.conv = nn.Linear(in_c * spiral_size, out_c, bias=bias)
+        self._geom_cache = []  # [(first batch copy of the table on device, SpiralGeometry)]
+
+    def _geometry_for(self, spiral_adj):
+        first = spiral_adj[0] if spiral_adj.dim() == 3 else spiral_adj
+        for src, geom in self._geom_cache:
+            if src.shape == first.shape and src.device == first.device and torch.equal(src, first):
+                return geom
+        geom = SpiralGeometry.from_spiral(spiral_adj, spiral_adj.device)  # validates batch invariance once
+        self._geom_cache.append((first.clone(), geom))
+        return geom
+
+    def forward(self, x, spiral_adj):
+        geom = spiral_adj if isinstance(spiral_adj, SpiralGeometry) else self._geometry_for(spiral_adj)
+        return fn.spiral_conv(x, self.conv.weight, self.conv.bias, geom, self.activation_name)
+
+
+class Pool(nn.Module):
+    """The reference has no Pool class: this names the ``torch.matmul(D[i], x)`` / ``torch.matmul(U[i], x)`` call
+    sites (models.py:127,148,250,276).  Accepts the dense padded (1, Vout+1, Vin+1) tensor of main.py:183-205
+    (converted to CSR once), a scipy sparse matrix (un-padded), or a :class:`PoolMatrix`."""
+
+    def __init__(self, matrix, device=None):
+        super().__init__()
+        self.pm = as_pool_matrix(matrix, device)
+
+    def forward(self, x):
+        return fn.pool(x, self.pm)
+
+
+def as_pool_matrix(m, device=None):
+    if isinstance(m, PoolMatrix):
+        return m
+    if isinstance(m, torch.Tensor) or isinstance(m, np.ndarray):
+        return PoolMatrix.from_dense(m, device)
+    return PoolMatrix.from_scipy_padded(m, device)
+
+
+def _conv_stacks(filters_enc, filters_dec, spiral_sizes, activation, device):
+    """Layer construction order of models.py:69-113 (also :186-230).  Returns (enc_convs, enc_levels, dec_convs,
+    dec_levels, last_enc_channels)."""
+    n_levels = len(spiral_sizes) - 1
+    enc, enc_lvl, dec, dec_lvl = [], [], [], []
+    c = filters_enc[0][0]
+    for i in range(n_levels):
+        for width in ([filters_enc[1][i]] if filters_enc[1][i] else []) + [filters_enc[0][i + 1]]:
+            enc.append(SpiralConv(c, spiral_sizes[i], width, activation=activation, device=device).to(device))
+            enc_lvl.append(i)
+            c = width
+    enc_out = c
+    c = filters_dec[0][0]
+    for i in range(n_levels):
+        lvl = n_levels - 1 - i
+        widths = [filters_dec[0][i + 1]] + ([filters_dec[1][i + 1]] if filters_dec[1][i + 1] else [])
+        for q, width in enumerate(widths):
+            last = (i == n_levels - 1) and (q == len(widths) - 1)
+            dec.append(SpiralConv(c, spiral_sizes[lvl], width, activation='identity' if last else activation,
+                                  device=device).to(device))
+            dec_lvl.append(lvl)
+            c = width
+    return enc, enc_lvl, dec, dec_lvl, enc_out
+
+
+class _SpiralTrunk(nn.Module):
+    """Conv/pool stacks shared by both autoencoders (models.py:121-127,147-153 == :244-250,275-281)."""
+
+    def _init_trunk(self, filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool):
+        self.sizes = sizes
+        self.spirals = spirals
+        self.filters_enc = filters_enc
+        self.filters_dec = filters_dec
+        self.spiral_sizes = spiral_sizes
+        self.D = D
+        self.U = U
+        self.device = device
+        self.activation = activation
+        enc, self._enc_lvl, dec, self._dec_lvl, self._enc_out = _conv_stacks(filters_enc, filters_dec, spiral_sizes,
+                                                                             activation, device)
+        self.conv = nn.ModuleList(enc)
+        self.dconv = nn.ModuleList(dec)
+        n_levels = len(spiral_sizes) - 1
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("semantichuman_b200 models need a CUDA device; there is no CPU fallback")
+        # per-level tables; level n_levels has spirals but no conv (models.py:71,90 loop to len-1)
+        geoms = [SpiralGeometry.from_spiral(spirals[i], dev, dummy_row_grad=False) for i in range(n_levels)]
+        self._pD = [as_pool_matrix(D[i], dev) for i in range(n_levels)]
+        self._pU = [as_pool_matrix(U[i], dev) for i in range(n_levels)]
+        for i in range(n_levels):
+            if self._pD[i].rows_in != geoms[i].rows_in or self._pU[i].rows_out != geoms[i].rows_in:
+                raise ValueError(f"level {i}: D/U shapes do not match the spiral table")
+        # encoder plan: (conv index, geometry, pool-after or None)
+        self._enc_plan = []
+        for j, lvl in enumerate(self._enc_lvl):
+            last_at_level = (j + 1 == len(self._enc_lvl)) or (self._enc_lvl[j + 1] != lvl)
+            if not last_at_level:
+                self._enc_plan.append((j, geoms[lvl], None))
+            elif fuse_pool and self._pD[lvl].is_selection and self._pD[lvl].selection_cols[-1] == geoms[lvl].rows_in - 1:
+                # D is a row selection: evaluate the conv only at the kept vertices (+ dummy)
+                self._enc_plan.append((j, geoms[lvl].restricted(self._pD[lvl].selection_cols, dummy_row_grad=False), None))
+            else:
+                self._enc_plan.append((j, geoms[lvl], self._pD[lvl]))
+        # decoder plan: (conv index, geometry, pool-before or None); only the very first decoder conv can see a live
+        # dummy row (the FC output row carried by U[-1][-1,-1]=1) -> it alone computes that gradient
+        self._dec_plan = []
+        for j, lvl in enumerate(self._dec_lvl):
+            first_at_level = (j == 0) or (self._dec_lvl[j - 1] != lvl)
+            g = geoms[lvl].with_flags(dummy_row_grad=True) if j == 0 else geoms[lvl]
+            self._dec_plan.append((j, g, self._pU[lvl] if first_at_level else None))
+        self.compute_dtype = torch.float32
+
+    def set_compute_dtype(self, dtype):
+        """torch.float32 (default; exact-fp32 kernels, 1e-4 parity) or torch.bfloat16 (bf16 activations and
+        operands, fp32 accumulation, fp32 master weights; 2e-2 parity)."""
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("compute dtype must be float32 or bfloat16")
+        self.compute_dtype = dtype
+        return self
+
+    def _encode_trunk(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
+        x = x.to(self.compute_dtype)
+        for j, geom, pm in self._enc_plan:
+            x = self.conv[j](x, geom)
+            if pm is not None:
+                x = fn.pool(x, pm)
+        return x
+
+    def _decode_trunk(self, x):
+        x = x.to(self.compute_dtype)
+        for j, geom, pm in self._dec_plan:
+            if pm is not None:
+                x = fn.pool(x, pm)
+            x = self.dconv[j](x, geom)
+        return x.float()
+
+
+class SpiralAutoencoder(_SpiralTrunk):
+    """models.py:55-162."""
+
+    def __init__(self, filters_enc, filters_dec, latent_size, sizes, spiral_sizes, spirals, D, U, device,
+                 VAE_flag=False, activation='elu', fuse_pool=True):
+        super().__init__()
+        self.latent_size = latent_size
+        self.VAE_flag = VAE_flag
+        self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool)
+        self.fc_latent_enc = nn.Linear((sizes[-1] + 1) * self._enc_out, (2 if VAE_flag else 1) * latent_size)
+        self.fc_latent_dec = nn.Linear(latent_size, (sizes[-1] + 1) * filters_dec[0][0])
+
+    def _linear(self, layer, v):
+        if self.compute_dtype == torch.float32:
+            return layer(v)
+        return F.linear(v, layer.weight.to(self.compute_dtype), layer.bias.to(self.compute_dtype))
+
+    def encode(self, x, VAE_flag):
+        bsize = x.size(0)
+        x = self._encode_trunk(x)
+        z = self._linear(self.fc_latent_enc, x.reshape(bsize, -1)).float()
+        if VAE_flag:  # models.py:131-136
+            self.z_mu = z[..., :self.latent_size]
+            self.z_var = z[..., self.latent_size:]
+            std = torch.exp(self.z_var / 2)
+            eps = torch.randn_like(std)
+            z = eps.mul(std).add_(self.z_mu)
+        return z
+
+    def decode(self, z):
+        bsize = z.size(0)
+        x = self._linear(self.fc_latent_dec, z.to(self.compute_dtype))
+        return self._decode_trunk(x.view(bsize, self.sizes[-1] + 1, -1))
+
+    def forward(self, x):
+        z = self.encode(x, self.VAE_flag)
+        return self.decode(z), z
+
+
+class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
+    """models.py:166-310 -- bone-guided variant: per-part shape codes + per-part keypoint (bone) codes."""
+
+    def __init__(self, kps_index_list, vert_part_index_dict, filters_enc, filters_dec, latent_size, part_kps_latent_size,
+                 sizes, spiral_sizes, spirals, D, U, device, VAE_flag=False, activation='elu', fuse_pool=True):
+        super().__init__()
+        self.newskl_list = DEFAULT_NEWSKL_LIST
+        self.kps_keep = [i for i in range(len(self.newskl_list) + 4) if i not in (3, 13, 14)]
+        self.kps_index_list = kps_index_list
+        self.vert_part_index_dict = vert_part_index_dict
+        self.part_kps_latent_size = part_kps_latent_size
+        self.latent_size = latent_size
+        self.VAE_flag = VAE_flag
+        self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool)
+        parts = [np.asarray(v) for v in vert_part_index_dict.values()]
+        c_enc, c_dec = self._enc_out, filters_dec[0][0]
+        out_lat = (2 if VAE_flag else 1) * latent_size
+        self.fc_latent_enc_list = nn.ModuleList([nn.Linear(len(p) * c_enc, out_lat).to(device) for p in parts])
+        self.fc_latent_dec_list = nn.ModuleList(
+            [nn.Linear(latent_size + part_kps_latent_size, len(p) * c_dec).to(device) for p in parts])
+        self.kps_enc_list = nn.ModuleList(
+            [nn.Linear(len(k) * 3, part_kps_latent_size).to(device) for k in kps_index_list])
+        dev = torch.device(device)
+        self._part_idx = [torch.as_tensor(p, dtype=torch.long, device=dev) for p in parts]
+        self._kps_idx = [torch.as_tensor(k, dtype=torch.long, device=dev) for k in kps_index_list]
+        self._re_index = torch.as_tensor(np.concatenate(parts), dtype=torch.long, device=dev)
+
+    def kps_encode(self, kps):
+        B = kps.shape[0]
+        return torch.stack([self.kps_enc_list[k](kps[:, idx, :].reshape(B, -1)) for k, idx in enumerate(self._kps_idx)],
+                           dim=1)
+
+    def encode(self, x, kps, VAE_flag=None):
+        bsize = x.size(0)
+        x = self._encode_trunk(x).float()
+        z = torch.stack([self.fc_latent_enc_list[k](x[:, idx, :].reshape(bsize, -1))
+                         for k, idx in enumerate(self._part_idx)], dim=1)
+        return z, self.kps_encode(kps), x[:, -1:, :]
+
+    def decode(self, z, z_part_kps, dummy):
+        bsize = z.size(0)
+        zz = torch.cat([z, z_part_kps], dim=2)
+        pieces = [self.fc_latent_dec_list[k](zz[:, k, :]) for k in range(z.shape[1])]
+        x = torch.cat(pieces, dim=1).view(bsize, self.sizes[-1], -1)
+        # models.py:270-272: x[:, re_index] = x[:, arange]  (rows arrive in part-concatenated order)
+        x = torch.zeros_like(x).index_copy(1, self._re_index, x)
+        x = torch.cat([x, dummy.to(x.dtype).expand(bsize, -1, -1)], dim=1)
+        return self._decode_trunk(x)
+
+    def kps2skl(self, kps_tmp):
+        """models.py:284-304: keypoints -> (unit direction, length) per bone of ``newskl_list``."""
+        skl_list = self.newskl_list
+        if kps_tmp.shape[1] == len(skl_list) + 4:
+            kps = copy.deepcopy(kps_tmp)
+        else:
+            keep = [i for i in range(len(skl_list) + 4) if i not in (3, 13, 14)]
+            kps = torch.zeros((kps_tmp.shape[0], len(skl_list) + 4, 3), device=kps_tmp.device)
+            kps[:, keep, :] = kps_tmp
+        skl = torch.zeros((kps.shape[0], len(skl_list), 4), device=kps.device)
+        for i, bone in enumerate(skl_list):
+            tail = kps[:, bone[1], :] if len(bone) == 2 else (kps[:, bone[1], :] + kps[:, bone[2], :]) / 2
+            vec = kps[:, bone[0], :] - tail
+            length = torch.sqrt(torch.sum(vec ** 2, dim=1))
+            skl[:, i, :3] = vec / length[:, None]
+            skl[:, i, -1] = length
+        return skl
+
+    def forward(self, x, kps):
+        z, z_part_kps, dummy = self.encode(x, kps, self.VAE_flag)
+        return self.decode(z, z_part_kps, dummy), z, z_part_kps
