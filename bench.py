@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: SpiralAutoencoder training step on 6890-vertex meshes (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype fp32|bf16] [--batch B_per_gpu]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (CPU oracle port) on the box's host cores
+
+One step = forward + L1 loss + backward (+ gradient all-reduce when N>1) + Adam (main.py:262 hyper-parameters) over
+one batch of synthetic meshes; weights are deterministic random-init; per-GPU batch 256 (weak scaling: N=8 is
+BASELINE.json's global batch 2048).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FENC = [[3, 16, 32, 64, 128], [[], [], [], [], []]]  # configure/cfgs.py:11
+FDEC = [[128, 64, 32, 32, 16], [[], [], [], [], 3]]  # configure/cfgs.py:12
+NZ = 256  # traincfg.yaml:10
+METRIC = "train meshes/sec (6890-vert SpiralAE fwd+bwd)"
+N_INPUT_BATCHES = 8  # distinct resident batches rotated through the timed loop
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def base_config(args, world):
+    return {"workload": "SpiralAutoencoder training step: fwd + L1 loss + bwd + Adam, synthetic 6890-vertex "
+                        "SMPL-topology template (hier_2222), default filters, nz=256 (BASELINE.json configs[2]; "
+                        "N=8 is configs[3]'s global batch 2048)",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "params": 28559811, "optimizer": "Adam(lr=1e-3, wd=5e-5)", "parallelism": f"dp{world}",
+            "cache": f"{N_INPUT_BATCHES} distinct input batches rotated; per-step working set (activations + 114 MB "
+                     "weights + Adam state) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(steps, warmup, batch=16, threads=None):
+    """The reference algorithm (oracle port of models.py + train_funcs.py:495-510) on the host cores."""
+    from oracle import spiral_oracle as so
+    from semantichuman_b200.assets import Hierarchy
+    from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    h = Hierarchy("2222")
+    Dd, Ud = h.dense_DU()  # dense padded D/U exactly as the reference multiplies them (main.py:183-205)
+    spirals = h.spirals()
+    enc, dec = so.conv_plan(FENC, FDEC, 4)
+
+    class Lin(torch.nn.Module):
+        def __init__(self, k, n):
+            super().__init__()
+            self.conv = torch.nn.Linear(k, n)
+
+    class Params(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.ModuleList(Lin(h.spiral_sizes[l] * ci, co) for (l, ci, co, _) in enc)
+            self.fc_latent_enc = torch.nn.Linear((h.sizes[-1] + 1) * 128, NZ)
+            self.fc_latent_dec = torch.nn.Linear(NZ, (h.sizes[-1] + 1) * 128)
+            self.dconv = torch.nn.ModuleList(Lin(h.spiral_sizes[l] * ci, co) for (l, ci, co, _) in dec)
+
+    m = fill_deterministic_(Params(), seed=2)
+    params = dict(m.named_parameters())
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=5e-5)
+    xs = [synthetic_meshes(h.verts0, batch, seed=i) for i in range(2)]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        x = xs[i % 2]
+        xh, _ = so.autoencoder_forward(params, x, FENC, FDEC, h.sizes, spirals, Dd, Ud)
+        loss = so.l1_loss(x, xh)
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": threads,
+            "batch": batch, "steps": len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, batch=16)
+    world = args.gpus
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "meshes/s", "n_gpus": world,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": base_config(args, world),
+            "cpu_baseline": {"value": r["value"], "unit": "meshes/s", "cores": r["cores"], "kind": "port",
+                             "sample": f"batch 16 per step, {r['steps']} steps: oracle port of the reference's PyTorch "
+                                       "CPU path (dense D/U bmm, index gather, autograd, Adam)"},
+            "e2e": {"value": r["value"], "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def run_own(args):
+    import torch.distributed as dist
+
+    import semantichuman_b200 as shb
+    from semantichuman_b200 import functions as fn
+    from semantichuman_b200.assets import Hierarchy
+    from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+    from semantichuman_b200.train import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+
+    h = Hierarchy("2222")
+    Dsp, Usp = h.sparse_DU()
+    model = shb.SpiralAutoencoder(FENC, FDEC, latent_size=NZ, sizes=h.sizes, spiral_sizes=h.spiral_sizes,
+                                  spirals=h.spirals(dev), D=Dsp, U=Usp, device=dev)
+    fill_deterministic_(model, seed=2)
+    model = model.to(dev).set_compute_dtype(dtype)
+    step = TrainStep(model)
+    B = args.batch
+    host = [synthetic_meshes(h.verts0, B, seed=1000 * rank + i).pin_memory() for i in range(N_INPUT_BATCHES)]
+    resident = [x.to(dev) for x in host]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        step(resident[i % N_INPUT_BATCHES])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local) if rank == 0 else None
+    timer = fn.KernelTimer() if rank == 0 else None
+    fn.TIMER = timer
+    launches0 = fn.LAUNCHES["n"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(resident[i % N_INPUT_BATCHES])
+    e1.record()
+    barrier()
+    fn.TIMER = None
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = fn.LAUNCHES["n"] - launches0
+    clocks = sampler.stop() if sampler else None
+    last_loss = float(loss.item())
+
+    # ---- timed region 2: end to end from pinned host buffers, loss read back every step
+    for i in range(2):
+        step.stage(host[i % N_INPUT_BATCHES])
+        step.step_staged(loss_host[i % 2:i % 2 + 1])
+    barrier()
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    step.stage(host[0])
+    seen = 0.0
+    for i in range(args.steps):
+        step.step_staged(loss_host[i % 2:i % 2 + 1])
+        done[i % 2].record()
+        if i + 1 < args.steps:
+            step.stage(host[(i + 1) % N_INPUT_BATCHES])
+        if i > 0:  # read the previous step's loss on the host (train_funcs.py:513 reads it every step)
+            done[(i - 1) % 2].synchronize()
+            seen += float(loss_host[(i - 1) % 2])
+    done[(args.steps - 1) % 2].synchronize()
+    seen += float(loss_host[(args.steps - 1) % 2])
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    per = timer.summary()
+    top_name, top = max(per.items(), key=lambda kv: kv[1]["ms"])
+    avg_ms = top["ms"] / top["launches"]
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    if ai > ridge and args.dtype == "bf16":
+        achieved = top["flops"] / top["launches"] / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"]}
+    else:
+        achieved = top["bytes"] / top["launches"] / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"]}
+    roof.update({"traffic": None, "kernel": top_name, "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / ms,
+                 "peak_source": peaks["source"] + " (sustained figures: kernel timed inside a long step)",
+                 "arith_intensity_flop_per_byte": ai})
+    kernels = sorted(((k, v["ms"] / args.steps) for k, v in per.items()), key=lambda kv: -kv[1])
+    step_flops = sum(v["flops"] for v in per.values()) / args.steps
+    step_bytes = sum(v["bytes"] for v in per.values()) / args.steps
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=args.cpu_steps, warmup=1, batch=16)
+        cpu = {"value": r["value"], "unit": "meshes/s", "cores": r["cores"], "kind": "port",
+               "sample": f"batch 16 per step, {r['steps']} timed steps after 1 warm-up ({r['ms_per_step']:.0f} ms/step): "
+                         "oracle port of the reference's PyTorch CPU path"}
+
+    total = B * world
+    line = {"metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": "meshes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16",
+            "data": "synthetic", "config": base_config(args, world),
+            "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "meshes/s",
+                    "h2d_bytes_per_step": host[0].numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "loss": last_loss, "loss_e2e_mean": seen / args.steps,
+            "kernels_ms_per_step": {k: round(v, 4) for k, v in kernels[:12]},
+            "algorithmic_per_step": {"gflop_convs_pools": step_flops / 1e9, "gbytes": step_bytes / 1e9}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="shb200", choices=["shb200", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

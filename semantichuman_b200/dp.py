@@ -1,0 +1,87 @@
+"""Batch-sharded data parallelism for the training step (BASELINE.json config 4).
+
+The reference is single-device (main.py:197-201); this is the one thing the build ADDS around the path.  One
+process per GPU (torchrun), every rank holds a full replica, the global batch is split evenly by sample, and the
+only exchange is a gradient all-reduce (NCCL over NVLink/NVSwitch, ReduceOp.AVG == global-batch mean loss because
+shards are equal).  Gradients live in three flat fp32 buckets ordered by when backward finishes them:
+
+    decoder convs (ready first) -> the two FC layers (99 % of the bytes, ready mid-backward) -> encoder convs (last)
+
+Each bucket's all-reduce is launched from an autograd post-accumulate hook the moment its last gradient lands, so
+the 114 MB FC bucket travels while the encoder backward is still computing.  ``finish()`` joins before the optimizer.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(global_batch, rank, world):
+    """Even split by sample; raises if the global batch does not divide (equal shards keep AVG exact)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def _bucket_of(name):
+    if name.startswith("dconv."):
+        return 0
+    if name.startswith(("fc_latent", "kps_enc_list")):
+        return 1
+    return 2
+
+
+class GradSync:
+    """Flat-bucket gradient all-reduce overlapped with backward."""
+
+    def __init__(self, model, process_group=None):
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # NCCL averages inside the collective; gloo (CPU tests of this logic) has no AVG: sum, then scale in finish()
+        self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.buckets = []
+        self._handles = []
+        for b in range(3):
+            members = [(n, p) for n, p in named if _bucket_of(n) == b]
+            if not members:
+                continue
+            total = sum(p.numel() for _, p in members)
+            flat = torch.zeros(total, dtype=members[0][1].dtype, device=members[0][1].device)
+            off = 0
+            for _, p in members:
+                p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
+                off += p.numel()
+            bucket = {"flat": flat, "params": [p for _, p in members], "pending": 0, "work": None}
+            self.buckets.append(bucket)
+            for _, p in members:
+                p.register_post_accumulate_grad_hook(self._make_hook(bucket))
+        self.reset()
+
+    def _make_hook(self, bucket):
+        def hook(_param):
+            bucket["pending"] -= 1
+            if bucket["pending"] == 0 and self.world > 1:
+                op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+                bucket["work"] = dist.all_reduce(bucket["flat"], op=op, group=self.pg, async_op=True)
+        return hook
+
+    def reset(self):
+        """Call before each backward (instead of optimizer.zero_grad(set_to_none=True), which would drop the views)."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"] = len(b["params"])
+            b["work"] = None
+
+    def finish(self):
+        """Join the outstanding all-reduces (the current stream waits; the host does not block)."""
+        for b in self.buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+                b["work"] = None
+                if not self._avg_in_collective:
+                    b["flat"].div_(self.world)
+            elif self.world > 1 and b["pending"] != 0:
+                raise RuntimeError("GradSync.finish(): a bucket never completed -- was backward run, and reset() called?")
+
+    def grad_bytes(self):
+        return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)

@@ -20,6 +20,41 @@ def _count(n=1):
     LAUNCHES["n"] += n
 
 
+class KernelTimer:
+    """Optional per-entry-point CUDA-event timing (bench.py's roofline leg).  Events are recorded on the stream the
+    kernels are launched on; nothing is synchronised until summary()."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, meta, e0, e1 in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += meta.get("flops", 0.0)
+            d["bytes"] += meta.get("bytes", 0.0)
+        return out
+
+
+TIMER = None  # set to a KernelTimer to time every C-ABI call
+
+
+def _call(name, meta, fn_, *args):
+    """Invoke one C-ABI entry point, raising on a non-zero code; optionally bracketed by CUDA events."""
+    t = TIMER
+    if t is None:
+        check(fn_(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn_(*args), name)
+    e1.record()
+    t.records.append((name, meta, e0, e1))
+
+
 def _dt(t):
     try:
         return _DT[t.dtype]
@@ -39,6 +74,19 @@ def _stream():
 
 def _p(t):
     return None if t is None else t.data_ptr()
+
+
+def _conv_meta(B, rows_in, rows_out, S, cin, cout, esize):
+    """Algorithmic work of one SpiralConv pass in any direction: every activation row read once and
+    written once; indices and weights amortised over the batch."""
+    return {"flops": 2.0 * B * rows_out * S * cin * cout, "bytes": float(B) * (rows_in * cin + rows_out * cout) * esize}
+
+
+def _pool_meta(B, pm, C, esize, transposed):
+    """rows actually referenced + rows written, plus the CSR itself."""
+    rows_read = pm.rows_out if pm.is_selection else (pm.rows_out if transposed else pm.rows_in)
+    rows_written = pm.rows_in if transposed else pm.rows_out
+    return {"flops": 2.0 * B * pm.nnz * C, "bytes": float(B) * (rows_read + rows_written) * C * esize + pm.nnz * 8.0}
 
 
 class SpiralConvFn(torch.autograd.Function):
@@ -61,8 +109,10 @@ class SpiralConvFn(torch.autograd.Function):
         w = weight.detach().to(x.dtype).contiguous()
         b32 = None if bias is None else bias.detach().float().contiguous()
         y = torch.empty((B, geom.rows_out, cout), dtype=x.dtype, device=x.device)
-        check(lib.shb_spiralconv_fwd(_p(x), _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, geom.S,
-                                     cin, cout, act, int(geom.zero_last_row), _dt(x), _stream()), "shb_spiralconv_fwd")
+        meta = _conv_meta(B, rows_in, geom.rows_out, geom.S, cin, cout, x.element_size())
+        _call(f"spiralconv_fwd[{rows_in}>{geom.rows_out}x{geom.S}x{cin}>{cout}]", meta, lib.shb_spiralconv_fwd, _p(x),
+              _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, geom.S, cin, cout, act,
+              int(geom.zero_last_row), _dt(x), _stream())
         _count()
         ctx.save_for_backward(x, w, y)
         ctx.geom, ctx.act, ctx.has_bias = geom, act, bias is not None
@@ -80,8 +130,10 @@ class SpiralConvFn(torch.autograd.Function):
             gy = gy.to(x.dtype)
         dt, st = _dt(x), _stream()
         gz = torch.empty_like(gy)
-        check(lib.shb_spiralconv_bwd_act(_p(gy), _p(y), _p(gz), B, geom.rows_out, cout, act, int(geom.zero_last_row), dt, st),
-              "shb_spiralconv_bwd_act")
+        tag = f"[{rows_in}>{geom.rows_out}x{geom.S}x{cin}>{cout}]"
+        meta = _conv_meta(B, rows_in, geom.rows_out, geom.S, cin, cout, x.element_size())
+        _call("spiralconv_bwd_act" + tag, {"bytes": 3.0 * gy.numel() * gy.element_size()}, lib.shb_spiralconv_bwd_act,
+              _p(gy), _p(y), _p(gz), B, geom.rows_out, cout, act, int(geom.zero_last_row), dt, st)
         _count()
         gx = gw = gb = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
@@ -89,16 +141,16 @@ class SpiralConvFn(torch.autograd.Function):
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             gw = torch.empty((cout, geom.S * cin), dtype=torch.float32, device=x.device)
             gb = torch.empty((cout,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
-            check(lib.shb_spiralconv_bwd_wgrad(_p(x), _p(geom.table), _p(gz), _p(gw), _p(gb), _p(ws), nbytes, B, rows_in,
-                                               geom.rows_out, geom.S, cin, cout, dt, st), "shb_spiralconv_bwd_wgrad")
+            _call("spiralconv_bwd_wgrad" + tag, meta, lib.shb_spiralconv_bwd_wgrad, _p(x), _p(geom.table), _p(gz), _p(gw),
+                  _p(gb), _p(ws), nbytes, B, rows_in, geom.rows_out, geom.S, cin, cout, dt, st)
             _count(2)
             if ctx.wdtype != torch.float32:
                 gw = gw.to(ctx.wdtype)
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            check(lib.shb_spiralconv_bwd_dgrad(_p(gz), _p(geom.keyptr), _p(geom.inv_rows), _p(w), _p(gx), B, rows_in,
-                                               geom.rows_out, geom.S, cin, cout, int(geom.dummy_row_grad), dt, st),
-                  "shb_spiralconv_bwd_dgrad")
+            _call("spiralconv_bwd_dgrad" + tag, meta, lib.shb_spiralconv_bwd_dgrad, _p(gz), _p(geom.keyptr),
+                  _p(geom.inv_rows), _p(w), _p(gx), B, rows_in, geom.rows_out, geom.S, cin, cout,
+                  int(geom.dummy_row_grad), dt, st)
             _count(2 if geom.dummy_row_grad else 1)
         return gx, gw, gb, None, None
 
@@ -114,8 +166,8 @@ class PoolFn(torch.autograd.Function):
         if rows_in != pm.rows_in:
             raise ValueError(f"pool expects {pm.rows_in} rows, got {rows_in}")
         y = torch.empty((B, pm.rows_out, C), dtype=x.dtype, device=x.device)
-        check(lib.shb_pool_spmm(_p(x), _p(pm.rowptr), _p(pm.colidx), _p(pm.vals), _p(y), B, rows_in, pm.rows_out, C,
-                                _dt(x), _stream()), "shb_pool_spmm")
+        _call(f"pool_spmm[{rows_in}>{pm.rows_out}x{C}]", _pool_meta(B, pm, C, x.element_size(), False), lib.shb_pool_spmm,
+              _p(x), _p(pm.rowptr), _p(pm.colidx), _p(pm.vals), _p(y), B, rows_in, pm.rows_out, C, _dt(x), _stream())
         _count()
         ctx.pm = pm
         return y
@@ -126,8 +178,9 @@ class PoolFn(torch.autograd.Function):
         gy = gy.contiguous()
         B, _, C = gy.shape
         gx = torch.empty((B, pm.rows_in, C), dtype=gy.dtype, device=gy.device)
-        check(lib.shb_pool_spmm(_p(gy), _p(pm.t_rowptr), _p(pm.t_colidx), _p(pm.t_vals), _p(gx), B, pm.rows_out,
-                                pm.rows_in, C, _dt(gy), _stream()), "shb_pool_spmm(bwd)")
+        _call(f"pool_spmm_bwd[{pm.rows_out}>{pm.rows_in}x{C}]", _pool_meta(B, pm, C, gy.element_size(), True),
+              lib.shb_pool_spmm, _p(gy), _p(pm.t_rowptr), _p(pm.t_colidx), _p(pm.t_vals), _p(gx), B, pm.rows_out,
+              pm.rows_in, C, _dt(gy), _stream())
         _count()
         return gx, None
 
@@ -145,7 +198,8 @@ class L1LossFn(torch.autograd.Function):
         nbytes = lib.shb_l1_loss_workspace(n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
         out = torch.empty((), dtype=torch.float32, device=a.device)
-        check(lib.shb_l1_loss_fwd(_p(a), _p(b), n, _p(ws), nbytes, _p(out), _dt(a), _stream()), "shb_l1_loss_fwd")
+        _call("l1_loss_fwd", {"bytes": 2.0 * n * a.element_size()}, lib.shb_l1_loss_fwd, _p(a), _p(b), n, _p(ws), nbytes,
+              _p(out), _dt(a), _stream())
         _count(2)
         ctx.save_for_backward(a, b)
         return out
@@ -158,7 +212,9 @@ class L1LossFn(torch.autograd.Function):
         gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
         if ga is None and gb is None:
             return None, None
-        check(lib.shb_l1_loss_bwd(_p(a), _p(b), a.numel(), _p(g), _p(ga), _p(gb), _dt(a), _stream()), "shb_l1_loss_bwd")
+        nout = (ga is not None) + (gb is not None)
+        _call("l1_loss_bwd", {"bytes": (2.0 + nout) * a.numel() * a.element_size()}, lib.shb_l1_loss_bwd, _p(a), _p(b),
+              a.numel(), _p(g), _p(ga), _p(gb), _dt(a), _stream())
         _count()
         return ga, gb
 
@@ -174,9 +230,8 @@ class PartNormLossFn(torch.autograd.Function):
         B, n_parts, L = z.shape
         out = torch.empty((), dtype=torch.float32, device=z.device)
         gz = torch.empty_like(z)
-        check(lib.shb_partnorm_loss_fwd_bwd(_p(z), _p(measure), _p(P), _p(Q), _p(out), _p(gz), B, n_parts, L,
-                                            measure.shape[1], P.numel(), int(bool(relative)), _stream()),
-              "shb_partnorm_loss_fwd_bwd")
+        _call("partnorm_loss_fwd_bwd", {"bytes": 2.0 * z.numel() * 4}, lib.shb_partnorm_loss_fwd_bwd, _p(z), _p(measure),
+              _p(P), _p(Q), _p(out), _p(gz), B, n_parts, L, measure.shape[1], P.numel(), int(bool(relative)), _stream())
         _count()
         ctx.save_for_backward(gz)
         return out

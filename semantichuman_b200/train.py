@@ -1,0 +1,53 @@
+"""Training-step driver for the plain SpiralAutoencoder (train_funcs.py:495-513 as one callable).
+
+    step = TrainStep(model, lr=1e-3, weight_decay=5e-5)     # Adam as main.py:262
+    loss = step(x_device)                                    # fwd + l1 + bwd (+ grad all-reduce) + Adam; 0-d tensor
+
+The reference loop calls optim.zero_grad / model / loss_fn / backward / optim.step itself and can keep doing so
+with the drop-in model; this class is the same sequence packaged for the benchmark and for data-parallel runs
+(gradient buckets + overlapped all-reduce from dp.GradSync), with pinned-host staging for the end-to-end path.
+"""
+import torch
+
+from . import functions as fn
+from .dp import GradSync
+
+
+class TrainStep:
+    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True):
+        self.model = model
+        self.sync = GradSync(model)
+        self.optim = (torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True)
+                      if optimizer else None)
+        self._copy_stream = None
+        self._staged = None
+
+    def __call__(self, x):
+        self.sync.reset()
+        xh, _z = self.model(x)
+        loss = fn.l1_loss(x, xh)  # train_funcs.py:501  loss_fn(tx, tx_hat)
+        loss.backward()
+        self.sync.finish()
+        if self.optim is not None:
+            self.optim.step()
+        return loss
+
+    # ---- end-to-end path: inputs start in pinned host memory, the loss ends in host memory
+    def stage(self, x_host_pinned):
+        """Start the H2D copy of the next batch on a side stream (overlaps the current step)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._copy_stream):
+            xd = x_host_pinned.to(next(self.model.parameters()).device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (xd, ev)
+
+    def step_staged(self, loss_host_pinned):
+        """Run one step on the staged batch; the loss is copied to pinned host memory asynchronously."""
+        xd, ev = self._staged
+        torch.cuda.current_stream().wait_event(ev)
+        xd.record_stream(torch.cuda.current_stream())
+        loss = self(xd)
+        loss_host_pinned.copy_(loss.detach(), non_blocking=True)
+        return loss

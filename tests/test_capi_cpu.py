@@ -1,0 +1,115 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/shb200.h declares, and
+its host entry points (index construction) agree with the numpy oracle bit for bit.  No kernel is launched."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import spiral_oracle as so
+from semantichuman_b200 import _capi, indexing
+from semantichuman_b200.assets import Hierarchy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "shb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(shb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 16
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/shb200.h but not exported by libshb200.so"
+        assert n in _capi.SIGNATURES, f"{n} has no ctypes signature in _capi.py"
+    assert sorted(_capi.SIGNATURES) == names
+    assert _capi.lib.shb_abi_version() == 1
+    assert b"invalid argument" in _capi.lib.shb_error_string(-1)
+
+
+def test_argument_errors_are_reported_not_crashed():
+    # null pointers are rejected before any launch (no GPU needed)
+    assert _capi.lib.shb_spiralconv_fwd(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 0, 1, 0, None) == -1
+    assert _capi.lib.shb_pool_spmm(None, None, None, None, None, 1, 1, 1, 1, 0, None) == -1
+    with pytest.raises(RuntimeError):
+        _capi.check(-3, "x")
+
+
+@pytest.mark.parametrize("tag,cfg", [("small", "A"), ("open", "A"), ("2222", "A"), ("4444", "B")])
+def test_inverse_spiral_tables_bit_exact(tag, cfg):
+    h = Hierarchy(tag, cfg)
+    for l, s in enumerate(h.spirals()):
+        t = indexing.normalise_spiral(s.repeat(2, 1, 1))  # batch-replicated as models.py:122 passes it
+        assert (t == so.normalise_spiral(s.numpy())).all()
+        n = t.shape[0]
+        assert t.min() >= 0 and t.max() == n - 1 and (t[-1] == n - 1).all()
+        rp, sl = indexing.build_inverse_spiral_csr(t, n)
+        rp2, sl2 = so.inverse_spiral_csr(t, n)
+        assert rp.dtype == np.int32 and (rp == rp2).all() and (sl == sl2).all()
+        kp, rows = indexing.build_inverse_spiral_by_slot(t, n)
+        kp2, rows2 = so.inverse_spiral_by_slot(t, n)
+        assert (kp == kp2).all() and (rows == rows2).all()
+        # every slot appears exactly once, and the relation inverts the table
+        assert sorted(sl.tolist()) == list(range(t.size))
+        u = np.repeat(np.arange(n), np.diff(rp))
+        assert (t.reshape(-1)[sl] == u).all()
+
+
+def test_inverse_tables_for_restricted_rows():
+    h = Hierarchy("small")
+    t = indexing.normalise_spiral(h.spirals()[0])
+    keep = np.concatenate([h.raw["D0_col"], [t.shape[0] - 1]])
+    sub = t[keep]
+    kp, rows = indexing.build_inverse_spiral_by_slot(sub, t.shape[0])
+    kp2, rows2 = so.inverse_spiral_by_slot(sub, t.shape[0])
+    assert (kp == kp2).all() and (rows == rows2).all()
+
+
+def test_batch_varying_spiral_rejected():
+    import torch
+
+    h = Hierarchy("small")
+    s = h.spirals()[0].repeat(2, 1, 1)
+    s[1, 0, 1] = 5
+    with pytest.raises(ValueError):
+        indexing.normalise_spiral(s)
+    with pytest.raises(ValueError):
+        indexing.normalise_spiral(torch.full((1, 4, 2), 9))
+
+
+@pytest.mark.parametrize("tag", ["small", "2222"])
+def test_dense_to_csr_and_transpose(tag):
+    h = Hierarchy(tag)
+    levels = range(h.n_levels) if tag == "small" else [2, 3]  # dense level 0 of 6890 is 95 MB; keep CPU suite light
+    D, U = h.dense_DU()
+    for l in levels:
+        for m in (D[l], U[l]):
+            d = m[0].numpy()
+            rp, ci, v = indexing.dense_to_csr(d)
+            rp2, ci2, v2 = so.dense_to_csr(d)
+            assert (rp == rp2).all() and (ci == ci2).all() and (v == v2).all()
+            trp, tci, tv = indexing.csr_transpose(rp, ci, v, d.shape[0], d.shape[1])
+            rp3, ci3, v3 = so.dense_to_csr(d.T.copy())
+            assert (trp == rp3).all() and (tci == ci3).all() and (tv == v3).all()
+    # structural facts the fused conv + down-pool relies on
+    import scipy.sparse as sp
+
+    for l in range(h.n_levels):
+        rp = h.D_sp[l].indptr
+        assert (np.diff(rp) == 1).all() and (h.D_sp[l].data == 1.0).all()
+        assert (np.diff(sp.csr_matrix(h.U_sp[l]).indptr) == 3).all()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "semantichuman_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("numpy oracle", ""), f"{f} mentions the oracle"
+                assert "/root/reference" not in txt, f
