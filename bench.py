@@ -13,9 +13,7 @@ BASELINE.json's global batch 2048).  Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,45 +39,53 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md recipe:
+    clocks.sm, clocks.max.sm, clocks_event_reasons.*), every 50 ms on a host thread."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+
+        self.samples, self.reasons, self.err = [], set(), None
+        self.stop_flag = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
-                                         stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err, self.max_mhz = None, repr(e), None
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except AttributeError:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+            self.stop_flag.wait(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.tmp.flush()
-        rows = [r.strip().split(", ") for r in open(self.tmp.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.tmp.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [], "error": self.err}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "reasons": sorted(self.reasons)}
 
 
 def base_config(args, world):
@@ -304,7 +310,7 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="shb200", choices=["shb200", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])

@@ -1,0 +1,6 @@
+#!/bin/bash
+# Rebuild libshb200.so, then run a command on the B200 box:  scripts/gpu.sh [--timeout S] [--gpus N] -- '<cmd>'
+set -e
+cd "$(dirname "$0")/.."
+python -m semantichuman_b200._build >/dev/null
+exec /usr/local/graft/bin/gpurun "$@"

@@ -112,7 +112,11 @@ def _conv_stacks(filters_enc, filters_dec, spiral_sizes, activation, device):
 class _SpiralTrunk(nn.Module):
     """Conv/pool stacks shared by both autoencoders (models.py:121-127,147-153 == :244-250,275-281)."""
 
-    def _init_trunk(self, filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool):
+    def _init_trunk(self, filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool,
+                    make_heads):
+        """`make_heads(enc_out_channels)` registers the latent layers; it runs between the registration of
+        ``conv`` and ``dconv`` so that parameter order (hence optimizer-state order in the reference's checkpoints,
+        main.py:288) is the reference's: conv, fc..., dconv (models.py:81-86,113)."""
         self.sizes = sizes
         self.spirals = spirals
         self.filters_enc = filters_enc
@@ -125,6 +129,7 @@ class _SpiralTrunk(nn.Module):
         enc, self._enc_lvl, dec, self._dec_lvl, self._enc_out = _conv_stacks(filters_enc, filters_dec, spiral_sizes,
                                                                              activation, device)
         self.conv = nn.ModuleList(enc)
+        make_heads(self._enc_out)
         self.dconv = nn.ModuleList(dec)
         n_levels = len(spiral_sizes) - 1
         dev = torch.device(device)
@@ -192,9 +197,13 @@ class SpiralAutoencoder(_SpiralTrunk):
         super().__init__()
         self.latent_size = latent_size
         self.VAE_flag = VAE_flag
-        self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool)
-        self.fc_latent_enc = nn.Linear((sizes[-1] + 1) * self._enc_out, (2 if VAE_flag else 1) * latent_size)
-        self.fc_latent_dec = nn.Linear(latent_size, (sizes[-1] + 1) * filters_dec[0][0])
+
+        def heads(enc_out):
+            self.fc_latent_enc = nn.Linear((sizes[-1] + 1) * enc_out, (2 if VAE_flag else 1) * latent_size)
+            self.fc_latent_dec = nn.Linear(latent_size, (sizes[-1] + 1) * filters_dec[0][0])
+
+        self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool,
+                         heads)
 
     def _linear(self, layer, v):
         if self.compute_dtype == torch.float32:
@@ -236,15 +245,19 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
         self.part_kps_latent_size = part_kps_latent_size
         self.latent_size = latent_size
         self.VAE_flag = VAE_flag
-        self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool)
         parts = [np.asarray(v) for v in vert_part_index_dict.values()]
-        c_enc, c_dec = self._enc_out, filters_dec[0][0]
+        c_dec = filters_dec[0][0]
         out_lat = (2 if VAE_flag else 1) * latent_size
-        self.fc_latent_enc_list = nn.ModuleList([nn.Linear(len(p) * c_enc, out_lat).to(device) for p in parts])
-        self.fc_latent_dec_list = nn.ModuleList(
-            [nn.Linear(latent_size + part_kps_latent_size, len(p) * c_dec).to(device) for p in parts])
-        self.kps_enc_list = nn.ModuleList(
-            [nn.Linear(len(k) * 3, part_kps_latent_size).to(device) for k in kps_index_list])
+
+        def heads(c_enc):  # models.py:199-204
+            self.fc_latent_enc_list = nn.ModuleList([nn.Linear(len(p) * c_enc, out_lat).to(device) for p in parts])
+            self.fc_latent_dec_list = nn.ModuleList(
+                [nn.Linear(latent_size + part_kps_latent_size, len(p) * c_dec).to(device) for p in parts])
+            self.kps_enc_list = nn.ModuleList(
+                [nn.Linear(len(k) * 3, part_kps_latent_size).to(device) for k in kps_index_list])
+
+        self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool,
+                         heads)
         dev = torch.device(device)
         self._part_idx = [torch.as_tensor(p, dtype=torch.long, device=dev) for p in parts]
         self._kps_idx = [torch.as_tensor(k, dtype=torch.long, device=dev) for k in kps_index_list]

@@ -113,3 +113,26 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("numpy oracle", ""), f"{f} mentions the oracle"
                 assert "/root/reference" not in txt, f
+
+
+def test_parameter_order_matches_reference_state_dict():
+    """Optimizer state in the reference's checkpoints is indexed by parameter order (main.py:288): the drop-in must
+    register conv, fc_latent_*, dconv in the reference's order (models.py:81-86,113).  Checked against the key order
+    of the golden state_dicts, which were dumped from the reference modules."""
+    import inspect
+
+    from semantichuman_b200 import models
+    from tests.helpers import golden
+
+    for name, cls in (("golden_ae_small", "SpiralAutoencoder"), ("golden_multiz_small", "SpiralAutoencoder_multiz_partkps")):
+        keys = [k[2:] for k in golden(name).files if k.startswith("p_")]
+        groups = []
+        for k in keys:
+            g = k.split(".")[0]
+            if not groups or groups[-1] != g:
+                groups.append(g)
+        src = inspect.getsource(getattr(models, cls)) + inspect.getsource(models._SpiralTrunk._init_trunk)
+        pos = [src.index("self." + g + " =") if g not in ("conv", "dconv") else None for g in groups]
+        assert groups[0] == "conv" and groups[-1] == "dconv", groups
+        inner = [p for p in pos if p is not None]
+        assert inner == sorted(inner), groups
