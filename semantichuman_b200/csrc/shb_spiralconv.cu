@@ -6,7 +6,10 @@
 // i.e. C[M x N] = A[M x K] . Bop[K x N] where a K-slice of A for slot s is a gathered row (forward) or the
 // fixed-order sum of the gathered rows of the (u,s) inverse list (dgrad).  A is never materialised in HBM.
 // The weight gradient streams gz / gathered x once per slot s and reduces over rows in two fixed-order stages.
+#include <stdlib.h>
+
 #include "shb_common.cuh"
+#include "shb_internal.h"
 
 namespace shb {
 
@@ -426,6 +429,14 @@ static int wgrad_launch(const WGParams& p0, int splits, void* gw, void* gb, cuda
   return 0;
 }
 
+bool umma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SHB_DISABLE_UMMA");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 }  // namespace shb
 
 using namespace shb;
@@ -445,7 +456,12 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
   p.act = act; p.zero_last = zero_last_row; p.skip_last = 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SHB_F32) return launch_gather_gemm<float, false>(p, st);
-  if (dtype == SHB_BF16) return launch_gather_gemm<__nv_bfloat16, false>(p, st);
+  if (dtype == SHB_BF16) {
+    if (umma_enabled() && umma_gather_gemm_supported(Cin, Cout, S))  // tensor-core path (tcgen05 + TMEM)
+      return umma_gather_gemm(x, table, nullptr, w, (const float*)bias, y, B, rows_in, rows_out, S, Cin, Cout, act,
+                              zero_last_row, 0, false, st);
+    return launch_gather_gemm<__nv_bfloat16, false>(p, st);
+  }
   return SHB_E_DTYPE;
 }
 
@@ -509,8 +525,13 @@ int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (dtype == SHB_F32) rc = launch_gather_gemm<float, true>(p, st);
-  else if (dtype == SHB_BF16) rc = launch_gather_gemm<__nv_bfloat16, true>(p, st);
-  else return SHB_E_DTYPE;
+  else if (dtype == SHB_BF16) {
+    if (umma_enabled() && umma_gather_gemm_supported(Cout, Cin, S))
+      rc = umma_gather_gemm(gz, keyptr, rows, w, nullptr, gx, B, rows_out, rows_in, S, Cout, Cin, SHB_ACT_IDENTITY, 0, 1,
+                            true, st);
+    else
+      rc = launch_gather_gemm<__nv_bfloat16, true>(p, st);
+  } else return SHB_E_DTYPE;
   if (rc != 0 || !dummy_row_grad) return rc;
   const size_t smem = (256 + (size_t)Cout + Cin) * sizeof(float);
   if (dtype == SHB_F32)
