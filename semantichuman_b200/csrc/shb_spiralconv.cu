@@ -443,6 +443,9 @@ using namespace shb;
 
 extern "C" {
 
+// not part of the public ABI (not declared in include/shb200.h): perf-debug hook used by scripts/trace_umma.py
+void shbdbg_set_trace(void* buf) { umma_set_trace((long long*)buf); }
+
 int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const void* bias, void* y, int B,
                        int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row, int dtype,
                        void* stream) {
@@ -485,7 +488,9 @@ int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int r
 }
 
 size_t shb_spiralconv_wgrad_workspace(int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dtype) {
-  (void)rows_in; (void)dtype;
+  (void)rows_in;
+  if (dtype == SHB_BF16 && umma_enabled() && umma_wgrad_supported(Cin, Cout, S))
+    return umma_wgrad_workspace(B, rows_out, S, Cin, Cout);
   const WGConfig c = wgrad_config(Cin, Cout);
   const int tiles = ceil_div(Cout, c.ba) * ceil_div(Cin, c.bb);
   const int splits = wgrad_splits((long long)B * rows_out, S, tiles);
@@ -498,6 +503,9 @@ int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz
   if (!x || !table || !gz || !gw || !workspace) return SHB_E_ARG;
   if (B <= 0 || rows_in <= 0 || rows_out <= 0 || S <= 0 || Cin <= 0 || Cout <= 0) return SHB_E_ARG;
   if (workspace_bytes < shb_spiralconv_wgrad_workspace(B, rows_in, rows_out, S, Cin, Cout, dtype)) return SHB_E_WORKSPACE;
+  if (dtype == SHB_BF16 && umma_enabled() && umma_wgrad_supported(Cin, Cout, S))
+    return umma_wgrad(x, table, gz, (float*)gw, (float*)gb, workspace, B, rows_in, rows_out, S, Cin, Cout,
+                      (cudaStream_t)stream);
   const WGConfig c = wgrad_config(Cin, Cout);
   const int tiles = ceil_div(Cout, c.ba) * ceil_div(Cin, c.bb);
   WGParams p{};

@@ -13,6 +13,8 @@
 //     releases A stages / publishes accumulators with tcgen05.commit -> mbarrier;
 //   * 4 epilogue warps read the accumulator with tcgen05.ld, apply bias + activation + dummy-row mask, and store bf16.
 // The gathered (M x K) matrix never exists in HBM: activations are read once from HBM (re-reads hit L2).
+#include <stdlib.h>
+
 #include "shb_common.cuh"
 #include "shb_internal.h"
 #include "shb_umma.cuh"
@@ -28,6 +30,11 @@ constexpr int UG_EPI_WARPS = 4, UG_PROD_WARPS = 8;
 constexpr int UG_PROD_THREADS = UG_PROD_WARPS * 32;
 constexpr int UG_THREADS = (UG_EPI_WARPS + 1 + UG_PROD_WARPS) * 32;
 constexpr int UG_MAX_STAGES = 8;
+// A producer thread keeps this many cp.async groups (stages) in flight behind the one it is issuing; a stage is
+// published (one mbarrier arrival per WARP -- per-thread arrivals serialise on the barrier at ~16 cycles each) once
+// cp.async.wait_group says it has landed.  Must be < ring depth.
+constexpr int UG_LAG = 2;
+constexpr int UG_IDX_PER_THREAD = 8;  // per-tile index block: 128 rows x (S or S+1) entries <= 8 * 256
 
 struct UGParams {
   const __nv_bfloat16* src;  // (B, rows_src, CS)
@@ -43,6 +50,9 @@ struct UGParams {
   int nstage;   // depth of the A ring
   int num_tiles;
   int act, zero_last, skip_last;
+  long long* trace;  // debug timeline (CTA 0): [role 0..2][event 0..3][512] clock64 stamps, or null
+  int dbg;      // SHB_UMMA_DEBUG bitmask (perf bisection only): 1 skip copies, 2 skip MMAs, 4 skip epilogue stores
+  int noinc;    // 1: per-thread cp.async.mbarrier.arrive.noinc (no fence); 0: wait_group + proxy fence + per-warp arrive
   uint32_t tmem_cols;
 };
 
@@ -51,8 +61,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+#define UG_TRACE(role, ev, idx)                                                              \
+  do {                                                                                     \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[((role) * 4 + (ev)) * 512 + (idx)] = clock64(); \
+  } while (0)
+
 template <int CS, bool SUM>
-__global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const UGParams p) {
+__global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const UGParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[UG_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UG_MAX_STAGES];
@@ -92,7 +107,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const U
   }
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) {
-      mbar_init(&full_bar[i], UG_PROD_THREADS);
+      mbar_init(&full_bar[i], (!SUM && p.noinc) ? UG_PROD_THREADS : UG_PROD_WARPS);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -112,7 +127,9 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const U
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
-      mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1);
+      if (warp == 0 && lane == 0) UG_TRACE(2, 0, tcount);
+      mbar_wait_backoff(&tfull_bar[buf], (tcount >> 1) & 1, 200);
+      if (warp == 0 && lane == 0) UG_TRACE(2, 1, tcount);
       tc_fence_after();
       const long long m = (long long)tile * UG_BM + warp * 32 + lane;
       const bool valid = m < p.M;
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const U
           const float b = (p.bias != nullptr && n < p.Cd) ? __ldg(p.bias + n) : 0.f;
           v[t] = zero ? 0.f : act_fwd(__uint_as_float(r[t]) + b, p.act);
         }
-        if (!valid) continue;
+        if (!valid || (p.dbg & 4)) continue;
         if ((p.Cd & 7) == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -163,21 +180,24 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const U
       int tcount = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
-        mbar_wait(&tempty_bar[buf], ((tcount >> 1) & 1) ^ 1);
+        mbar_wait_backoff(&tempty_bar[buf], ((tcount >> 1) & 1) ^ 1, 40);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.NPAD);
         for (int st = 0; st < p.NS; ++st, ++it) {
           const uint32_t slot = it % p.nstage, ph = (it / p.nstage) & 1;
-          mbar_wait(&full_bar[slot], ph);
+          UG_TRACE(1, 0, it);
+          mbar_wait_backoff(&full_bar[slot], ph, 20);
+          UG_TRACE(1, 1, it);
           tc_fence_after();
           const int chunks = min(UG_KC, p.Q - st * UG_KC);
           const uint32_t a_st = a_base + slot * UG_STAGE_BYTES;
           for (int kk = 0; kk < chunks / 2; ++kk) {
             const uint64_t da = smem_desc(a_st + kk * 256, 128, UG_KC * 128);
             const uint64_t db = smem_desc(w_base + (uint32_t)(st * UG_KC + 2 * kk) * 128, 128, sbo_b);
-            mma_bf16(tmem_d, da, db, idesc, (st | kk) != 0);
+            if (!(p.dbg & 2)) mma_bf16(tmem_d, da, db, idesc, (st | kk) != 0);
           }
           mma_commit(&empty_bar[slot]);  // A stage reusable once these MMAs have read it
+          UG_TRACE(1, 2, it);
         }
         mma_commit(&tfull_bar[buf]);     // accumulator complete
       }
@@ -185,62 +205,175 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const U
     __syncwarp();
   } else {
     // ================================================================ producers: gather rows into the A ring
+    // Lane mapping: 8 consecutive lanes fetch the 8 consecutive 16-byte chunks (128 B of K) of ONE row, so that a
+    // gathered neighbour row costs one L1TEX wavefront instead of one per chunk; a warp instruction covers 4 rows,
+    // a thread owns chunk column kc of rows  i*32 + pw*4 + rr,  i = 0..3.
+    // The tile's block of the index table (128 rows x SP entries) is staged in shared memory, double-buffered, with
+    // the NEXT tile's block prefetched into registers while the current tile is gathered: a stage can then be issued
+    // without any dependent global load, so the cp.async ring really fills (the loop was index-latency bound before).
     const int pt = tid - (UG_EPI_WARPS + 1) * 32;  // 0..255
-    const int r = pt & (UG_BM - 1), half = pt >> 7;
+    const int pw = pt >> 5, kc = pt & 7, rr = (pt >> 3) & 3;
     const uint32_t a_base = smem_u32(a_ring);
-    const uint32_t row_off = (uint32_t)(r >> 3) * (UG_KC * 128) + (uint32_t)(r & 7) * 16;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long m = (long long)tile * UG_BM + r;
-      bool valid = m < p.M;
-      int j = 0;
-      const __nv_bfloat16* srcb = p.src;
-      if (valid) {
-        const long long b = m / p.rows_dst;
-        j = (int)(m - b * p.rows_dst);
-        srcb = p.src + b * (long long)p.rows_src * CS;
+    const int SP = SUM ? p.S + 1 : p.S;            // dgrad also needs the end pointer of each key
+    int32_t* idx_s = reinterpret_cast<int32_t*>(a_ring + (size_t)p.nstage * UG_STAGE_BYTES);  // [2][128*SP]
+    const int nidx = UG_BM * SP;
+    int pre[UG_IDX_PER_THREAD];
+    auto fetch_idx_block = [&](int tile) {  // global -> registers (coalesced: consecutive entries are contiguous)
+#pragma unroll
+      for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
+        const int e = pt + u * UG_PROD_THREADS;
+        pre[u] = 0;
+        if (e < nidx && tile < p.num_tiles) {
+          const unsigned r = (unsigned)e / (unsigned)SP, sl = (unsigned)e - r * (unsigned)SP;
+          const unsigned m = (unsigned)tile * UG_BM + r;
+          if ((long long)m < p.M) pre[u] = __ldg(p.table + (size_t)(m % (unsigned)p.rows_dst) * p.S + sl);
+        }
       }
-      if (SUM && p.skip_last && j == p.rows_dst - 1) valid = false;
-      const int32_t* trow = p.table + (long long)j * p.S;
-      for (int st = 0; st < p.NS; ++st, ++it) {
+    };
+    auto store_idx_block = [&](int buf) {
+#pragma unroll
+      for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
+        const int e = pt + u * UG_PROD_THREADS;
+        if (e < nidx) idx_s[buf * nidx + e] = pre[u];
+      }
+    };
+    fetch_idx_block(blockIdx.x);
+    store_idx_block(0);
+    asm volatile("bar.sync 1, %0;" ::"n"(UG_PROD_THREADS) : "memory");
+    uint32_t it = 0, published = 0;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const int32_t* idx_cur = idx_s + (tcount & 1) * nidx;
+      fetch_idx_block(tile + gridDim.x);  // next tile's block: in flight during this tile's stages
+      bool valid[4];
+      const __nv_bfloat16* srcb[4];
+      uint32_t row_off[4];
+      int irow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 32 + pw * 4 + rr;
+        const long long m = (long long)tile * UG_BM + r;
+        valid[i] = m < p.M;
+        srcb[i] = p.src;
+        if (valid[i]) {
+          const unsigned b = (unsigned)m / (unsigned)p.rows_dst;
+          srcb[i] = p.src + (size_t)b * p.rows_src * CS;
+          if (SUM && p.skip_last && ((unsigned)m - b * (unsigned)p.rows_dst) == (unsigned)(p.rows_dst - 1)) valid[i] = false;
+        }
+        irow[i] = r * SP;
+        row_off[i] = (uint32_t)(r >> 3) * (UG_KC * 128) + (uint32_t)(r & 7) * 16 + (uint32_t)kc * 128;
+      }
+      int firstn[4] = {0, 0, 0, 0}, cntn[4] = {0, 0, 0, 0};
+      auto prefetch_lists = [&](int st) {  // dgrad: first list entry of each key, one stage ahead
+        const int q = st * UG_KC + kc;
+        const int s = (q < p.Q) ? (q * 8) / CS : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          firstn[i] = 0;
+          cntn[i] = 0;
+          if (valid[i] && q < p.Q) {
+            const int e0 = idx_cur[irow[i] + s];
+            cntn[i] = idx_cur[irow[i] + s + 1] - e0;
+            firstn[i] = e0;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e0 = firstn[i];
+          firstn[i] = cntn[i] > 0 ? __ldg(p.list + e0) : 0;
+          cntn[i] = cntn[i] > 1 ? (cntn[i] | (e0 << 8)) : cntn[i];  // tails (rare) re-read the list from e0
+        }
+      };
+      if (SUM) prefetch_lists(0);
+      for (int st = 0; st < p.NS; ++st) {
         const uint32_t slot = it % p.nstage, ph = (it / p.nstage) & 1;
+        const int q = st * UG_KC + kc;
+        const bool inq = q < p.Q;
+        const int k = q * 8, s = inq ? k / CS : 0, c = k - s * CS;
+        int firstc[4], cntc[4];
+        if (SUM) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            firstc[i] = firstn[i];
+            cntc[i] = cntn[i];
+          }
+          if (st + 1 < p.NS) prefetch_lists(st + 1);
+        }
+        if (pt == 0) UG_TRACE(0, 0, it);
         mbar_wait(&empty_bar[slot], ph ^ 1);
-        const uint32_t dst0 = a_base + slot * UG_STAGE_BYTES + row_off;
+        if (pt == 0) UG_TRACE(0, 1, it);
+        const uint32_t dst0 = a_base + slot * UG_STAGE_BYTES;
+        if (inq && !(p.dbg & 1)) {
+          if (!SUM) {
+            int row[4];
 #pragma unroll
-        for (int i = 0; i < UG_KC / 2; ++i) {
-          const int kc = half * (UG_KC / 2) + i;
-          const int q = st * UG_KC + kc;
-          if (q < p.Q) {
-            const int k = q * 8, s = k / CS, c = k - s * CS;
-            if (!SUM) {
-              const int row = valid ? __ldg(trow + s) : 0;
-              cp_async16(dst0 + kc * 128, srcb + (size_t)row * CS + c, valid ? 16u : 0u);
-            } else {
-              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (valid) {
-                const int e0 = __ldg(trow + s), e1 = __ldg(trow + s + 1);
-                for (int e = e0; e < e1; ++e) {
-                  float v[8];
-                  Io<__nv_bfloat16>::ld8(srcb + (size_t)__ldg(p.list + e) * CS + c, v);
+            for (int i = 0; i < 4; ++i) row[i] = idx_cur[irow[i] + s];
 #pragma unroll
-                  for (int t = 0; t < 8; ++t) acc[t] += v[t];
-                }
+            for (int i = 0; i < 4; ++i)
+              cp_async16(dst0 + row_off[i], srcb[i] + (size_t)row[i] * CS + c, valid[i] ? 16u : 0u);
+          } else {
+            // gather-sum in a fixed order: the four first entries in flight together, then the (rare) longer tails
+            float acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (cntc[i] > 0) {
+                Io<__nv_bfloat16>::ld8(srcb[i] + (size_t)firstc[i] * CS + c, acc[i]);
+              } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[i][t] = 0.f;
               }
-              const uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + kc * 128), "r"(o.x), "r"(o.y),
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int cnt = cntc[i] & 0xff, e0 = cntc[i] >> 8;
+              for (int e = 1; e < cnt; ++e) {
+                float v[8];
+                Io<__nv_bfloat16>::ld8(srcb[i] + (size_t)__ldg(p.list + e0 + e) * CS + c, v);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[i][t] += v[t];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 o = make_uint4(pack_bf16x2(acc[i][0], acc[i][1]), pack_bf16x2(acc[i][2], acc[i][3]),
+                                         pack_bf16x2(acc[i][4], acc[i][5]), pack_bf16x2(acc[i][6], acc[i][7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(o.x), "r"(o.y),
                            "r"(o.z), "r"(o.w)
                            : "memory");
             }
           }
         }
+        if (pt == 0) UG_TRACE(0, 2, it);
+        ++it;
         if (!SUM) {
-          cp_async_mbar_arrive_noinc(&full_bar[slot]);
+          if (p.noinc) {
+            cp_async_mbar_arrive_noinc(&full_bar[slot]);
+          } else {
+            cp_async_commit();
+            if (it - published > UG_LAG) {
+              cp_async_wait_group<UG_LAG>();
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&full_bar[published % p.nstage]);
+              ++published;
+            }
+          }
         } else {
           fence_proxy_async_smem();
-          mbar_arrive(&full_bar[slot]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[slot]);
         }
       }
+      // publish the next tile's index block; every producer is past its reads of that buffer (barrier of the previous tile)
+      store_idx_block((tcount + 1) & 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(UG_PROD_THREADS) : "memory");
+    }
+    if (!SUM && !p.noinc) {  // drain: publish the stages still in flight
+      cp_async_wait_group<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      for (; published < it; ++published)
+        if (lane == 0) mbar_arrive(&full_bar[published % p.nstage]);
     }
   }
 
@@ -254,8 +387,11 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gather_gemm_kernel(const U
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static size_t ug_smem_bytes(int NPAD, int Q, int nstage) {
-  return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES;
+static long long* g_trace = nullptr;
+void umma_set_trace(long long* buf) { g_trace = buf; }
+
+static size_t ug_smem_bytes(int NPAD, int Q, int nstage, int S) {
+  return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES + (size_t)2 * UG_BM * (S + 1) * 4;
 }
 constexpr size_t UG_SMEM_MAX = 227 * 1024 - 1024;  // leave room for the static barriers
 
@@ -265,7 +401,8 @@ bool umma_gather_gemm_supported(int Cs, int Cd, int S) {
   if (!(Cs == 16 || Cs == 32 || Cs == 64 || Cs == 128)) return false;
   const int NPAD = ug_npad(Cd);
   if (NPAD > 256) return false;
-  return ug_smem_bytes(NPAD, S * Cs / 8, 2) <= UG_SMEM_MAX;
+  if (UG_BM * (S + 1) > UG_IDX_PER_THREAD * UG_PROD_THREADS) return false;  // S <= 15
+  return ug_smem_bytes(NPAD, S * Cs / 8, UG_LAG + 1, S) <= UG_SMEM_MAX;
 }
 
 template <int CS, bool SUM> static int ug_launch(const UGParams& p, size_t smem, int want_per_sm, cudaStream_t st) {
@@ -276,11 +413,20 @@ template <int CS, bool SUM> static int ug_launch(const UGParams& p, size_t smem,
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  // persistent kernel with static tile striding: the grid must be fully co-resident
-  int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, umma_gather_gemm_kernel<CS, SUM>, UG_THREADS, smem);
-  if (e != cudaSuccess) return (int)e;
-  if (occ < 1) return SHB_E_SHAPE;
+  // CTAs per SM from registers and shared memory (the runtime's occupancy query is conservative about the carveout);
+  // CTAs are independent, so an over-estimate only costs a second wave, never correctness
+  static int regs = 0;
+  if (regs == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, umma_gather_gemm_kernel<CS, SUM>);
+    if (e != cudaSuccess) return (int)e;
+    regs = fa.numRegs;
+    cudaFuncSetAttribute(umma_gather_gemm_kernel<CS, SUM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  }
+  const int by_regs = 65536 / (((regs + 7) / 8 * 8) * UG_THREADS);
+  const int by_smem = (int)((228 * 1024) / (smem + 2048));
+  int occ = by_regs < by_smem ? by_regs : by_smem;
+  if (occ < 1) occ = 1;
   int grid = kNumSMs * (occ < want_per_sm ? occ : want_per_sm);
   if (grid > p.num_tiles) grid = p.num_tiles;
   umma_gather_gemm_kernel<CS, SUM><<<grid, UG_THREADS, smem, st>>>(p);
@@ -300,16 +446,23 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* list,
   p.NS = (p.Q + UG_KC - 1) / UG_KC;
   p.num_tiles = (int)((p.M + UG_BM - 1) / UG_BM);
   p.act = act; p.zero_last = zero_last; p.skip_last = skip_last;
+  {
+    static const int mode = [] { const char* e = getenv("SHB_UMMA_NOINC"); return (e && e[0] == '0') ? 0 : 1; }();
+    p.noinc = mode;
+    static const int dbg = [] { const char* e = getenv("SHB_UMMA_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
+    p.trace = g_trace;
+  }
   int nstage = 6;
-  while (nstage > 2 && ug_smem_bytes(p.NPAD, p.Q, nstage) > UG_SMEM_MAX) --nstage;
+  while (nstage > UG_LAG + 1 && ug_smem_bytes(p.NPAD, p.Q, nstage, S) > UG_SMEM_MAX) --nstage;
   // two CTAs per SM when both fit with a deep enough ring: more gathers in flight
   int ctas_per_sm = 1;
-  if (ug_smem_bytes(p.NPAD, p.Q, 4) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }
+  if (ug_smem_bytes(p.NPAD, p.Q, 4, S) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }
   p.nstage = nstage;
   uint32_t cols = 32;
   while (cols < 2u * p.NPAD) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = ug_smem_bytes(p.NPAD, p.Q, nstage);
+  const size_t smem = ug_smem_bytes(p.NPAD, p.Q, nstage, S);
 #define UG_DISPATCH(CSV)                                                                   \
   case CSV:                                                                                \
     return sum_mode ? ug_launch<CSV, true>(p, smem, ctas_per_sm, st) : ug_launch<CSV, false>(p, smem, ctas_per_sm, st);
@@ -321,6 +474,310 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* list,
     default: return SHB_E_SHAPE;
   }
 #undef UG_DISPATCH
+}
+
+}  // namespace shb
+
+// ================================================================================================ weight gradient
+//   gw[n, s*Cin + c] = sum_{m=(b,j)} gz[m, n] * x[b, table[j,s], c]
+// as  D[k, n] = sum_m At[k, m] * Bt[n, m]:  UMMA-M = 128-wide blocks of k = s*Cin+c, UMMA-N = Cout, UMMA-K = rows m.
+// Both operands are MN-major (a gathered x row holds consecutive k, a gz row holds consecutive n), so every 16-byte
+// cp.async chunk lands unchanged in the un-swizzled core-matrix layout.  The ENTIRE (K x Cout) fp32 accumulator stays
+// in TMEM (ceil(K/128)*NPAD <= 512 columns) while the CTA streams its contiguous share of the rows exactly once; each CTA
+// then writes one fp32 partial, and a fixed-order reduction over CTAs finishes gw (bit-reproducible, no atomics).
+namespace shb {
+
+constexpr int UW_MAX_STAGES = 6;
+
+struct UWParams {
+  const __nv_bfloat16* x;   // (B, rows_in, CIN)
+  const int32_t* table;     // (rows_out, S)
+  const __nv_bfloat16* gz;  // (B, rows_out, Cout)
+  float* ws;                // [grid][Cout*K] fp32 partials
+  long long M, rows_per_cta;
+  int rows_in, rows_out, S, Cout, NPAD, K, Q, KT, NQ;  // Q = K/8 chunks per x row set, NQ = NPAD/8
+  int nstage;
+  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+};
+
+template <int CIN, int BKM>
+__global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParams p) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ __align__(8) uint64_t full_bar[UW_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[UW_MAX_STAGES];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const long long mbeg = (long long)blockIdx.x * p.rows_per_cta;
+  const long long mend = min(p.M, mbeg + p.rows_per_cta);
+  const int nst = mbeg < mend ? (int)((mend - mbeg + BKM - 1) / BKM) : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nstage; ++i) {
+      mbar_init(&full_bar[i], UG_PROD_WARPS);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == UG_EPI_WARPS) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  constexpr uint32_t SBO = BKM * 16;  // MN-direction core-matrix stride; K-direction (row groups of 8) stride = 128
+
+  if (warp < UG_EPI_WARPS) {
+    // ================================================================ epilogue: TMEM -> fp32 partial in the workspace
+    float* ws = p.ws + (size_t)blockIdx.x * ((size_t)p.Cout * p.K);
+    if (nst > 0) {
+      mbar_wait_backoff(&done_bar, 0, 1000);
+      tc_fence_after();
+    }
+    for (int t = 0; t < p.KT; ++t) {
+      const int k = t * 128 + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t)(t * p.NPAD) + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < p.NPAD; c0 += 16) {
+        uint32_t r[16];
+        if (nst > 0) {
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = 0u;
+        }
+        if (k < p.K) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.Cout) ws[(size_t)(c0 + i) * p.K + k] = __uint_as_float(r[i]);
+        }
+      }
+    }
+  } else if (warp == UG_EPI_WARPS) {
+    // ================================================================ MMA issuer
+    if (lane == 0 && nst > 0) {
+      const uint32_t idesc = idesc_bf16_f32(128, p.NPAD, 1, 1);
+      const uint32_t base = smem_u32(dyn_smem);
+      for (int st = 0; st < nst; ++st) {
+        const uint32_t slot = st % p.nstage, ph = (st / p.nstage) & 1;
+        mbar_wait_backoff(&full_bar[slot], ph, 20);
+        tc_fence_after();
+        const uint32_t a_st = base + slot * stage_bytes, b_st = a_st + p.a_stage_bytes;
+#pragma unroll
+        for (int kk = 0; kk < BKM / 16; ++kk) {
+          const uint64_t db = smem_desc(b_st + kk * 256, 128, SBO);
+          for (int t = 0; t < p.KT; ++t) {
+            const uint64_t da = smem_desc(a_st + (uint32_t)(t * 16) * SBO + kk * 256, 128, SBO);
+            mma_bf16(tmem_base + (uint32_t)(t * p.NPAD), da, db, idesc, (st | kk) != 0);
+          }
+        }
+        mma_commit(&empty_bar[slot]);
+      }
+      mma_commit(&done_bar);
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ producers
+    // consecutive lanes fetch consecutive 16-byte chunks of one gathered row (one L1TEX wavefront per row per 128 B);
+    // each warp owns BKM/8 rows of the stage, a thread owns chunk lanes ql, ql+QL, ...
+    const int pt = tid - (UG_EPI_WARPS + 1) * 32;
+    const int pw = pt >> 5, l = pt & 31;
+    constexpr int RPW = BKM / 8;   // rows per warp
+    constexpr int QL = 32 / RPW;   // chunk lanes per row
+    const int mr = pw * RPW + l / QL, ql = l % QL;
+    const uint32_t base = smem_u32(dyn_smem);
+    int published = 0;
+    constexpr int NI = 16;  // index registers per stage per thread: Q / QL <= 16
+    int rowc[NI];
+    bool validc = false;
+    long long mc = 0;
+    const __nv_bfloat16* xbc = p.x;
+    auto fetch_stage_idx = [&](int st, int* rowv, bool& valid, long long& m, const __nv_bfloat16*& xb) {
+      m = mbeg + (long long)st * BKM + mr;
+      valid = st < nst && m < mend;
+      unsigned b = 0, j = 0;
+      if (valid) {
+        b = (unsigned)m / (unsigned)p.rows_out;
+        j = (unsigned)m - b * (unsigned)p.rows_out;
+      }
+      xb = p.x + (size_t)b * p.rows_in * CIN;
+      const int32_t* trow = p.table + (size_t)j * p.S;
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int q = ql + u * QL;
+        rowv[u] = (valid && q < p.Q) ? __ldg(trow + (q * 8) / CIN) : 0;
+      }
+    };
+    fetch_stage_idx(0, rowc, validc, mc, xbc);
+    for (int st = 0; st < nst; ++st) {
+      const uint32_t slot = st % p.nstage, ph = (st / p.nstage) & 1;
+      int rown[NI];
+      bool validn;
+      long long mn;
+      const __nv_bfloat16* xbn;
+      fetch_stage_idx(st + 1, rown, validn, mn, xbn);  // next stage's indices: in flight while this stage is issued
+      mbar_wait(&empty_bar[slot], ph ^ 1);
+      const uint32_t a_dst = base + slot * stage_bytes + (uint32_t)mr * 16;
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int q = ql + u * QL;
+        if (q < p.Q)
+          cp_async16(a_dst + (uint32_t)q * SBO, xbc + (size_t)rowc[u] * CIN + (q * 8) % CIN, validc ? 16u : 0u);
+      }
+      const uint32_t b_dst = a_dst + p.a_stage_bytes;
+      for (int q = ql; q < p.NQ; q += QL) {
+        const bool in = validc && (q * 8 < p.Cout);
+        cp_async16(b_dst + (uint32_t)q * SBO, p.gz + (validc ? mc : 0) * p.Cout + q * 8, in ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (st + 1 - published > UG_LAG) {
+        cp_async_wait_group<UG_LAG>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (l == 0) mbar_arrive(&full_bar[published % p.nstage]);
+        ++published;
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) rowc[u] = rown[u];
+      validc = validn;
+      mc = mn;
+      xbc = xbn;
+    }
+    cp_async_wait_group<0>();
+    fence_proxy_async_smem();
+    __syncwarp();
+    for (; published < nst; ++published)
+      if (l == 0) mbar_arrive(&full_bar[published % p.nstage]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == UG_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+__global__ void __launch_bounds__(256) uw_reduce_kernel(const float* __restrict__ ws, int parts, long long n,
+                                                        float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int c = 0; c < parts; ++c) a += ws[(size_t)c * n + i];
+  out[i] = a;
+}
+
+// column sums of gz (bias gradient): per-block partials in fixed order, then a fixed-order final pass
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ gz, long long M, int C,
+                                                             int CP /*pow2 >= C, <= 256*/, long long rows_per_block,
+                                                             float* __restrict__ part) {
+  __shared__ float red[256];
+  const int tx = threadIdx.x % CP, ty = threadIdx.x / CP, ny = 256 / CP;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float a = 0.f;
+  if (tx < C)
+    for (long long r = r0 + ty; r < r1; r += ny) a += __bfloat162float(gz[r * C + tx]);
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (ty == 0 && tx < C) {
+    float s = 0.f;
+    for (int q = 0; q < ny; ++q) s += red[q * CP + tx];
+    part[(size_t)blockIdx.x * C + tx] = s;
+  }
+}
+
+static size_t uw_stage_bytes(int KT, int NPAD, int bkm) { return (size_t)KT * 16 * bkm * 16 + (size_t)(NPAD / 8) * bkm * 16; }
+
+struct UWPlan { int bkm, nstage, KT, NPAD, grid; size_t smem; uint32_t cols; bool ok; };
+
+static UWPlan uw_plan(int Cin, int Cout, int S) {
+  UWPlan pl{};
+  pl.ok = false;
+  if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
+  if ((Cout & 7) != 0) return pl;  // gz rows must be whole 16-byte chunks for cp.async
+  pl.NPAD = ug_npad(Cout);
+  const int K = S * Cin;
+  pl.KT = (K + 127) / 128;
+  if (pl.KT * pl.NPAD > 512 || pl.NPAD > 256) return pl;
+  if (K / 8 > 16 * 8) return pl;  // producer keeps Q / QL <= 16 index registers per stage
+  pl.cols = 32;
+  while ((int)pl.cols < pl.KT * pl.NPAD) pl.cols <<= 1;
+  for (int bkm : {32, 16}) {
+    const size_t sb = uw_stage_bytes(pl.KT, pl.NPAD, bkm);
+    int ns = (int)(UG_SMEM_MAX / sb);
+    if (ns > UW_MAX_STAGES) ns = UW_MAX_STAGES;
+    if (ns >= 3) { pl.bkm = bkm; pl.nstage = ns; pl.smem = sb * ns; pl.ok = true; break; }
+  }
+  pl.grid = kNumSMs;
+  return pl;
+}
+
+bool umma_wgrad_supported(int Cin, int Cout, int S) { return uw_plan(Cin, Cout, S).ok; }
+
+size_t umma_wgrad_workspace(int B, int rows_out, int S, int Cin, int Cout) {
+  (void)B; (void)rows_out;
+  // per-CTA fp32 partials of gw, then per-block partials of the bias gradient
+  return (size_t)kNumSMs * Cout * S * Cin * sizeof(float) + (size_t)4 * kNumSMs * Cout * sizeof(float);
+}
+
+template <int CIN, int BKM> static int uw_launch(const UWParams& p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<CIN, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)UG_SMEM_MAX);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  umma_wgrad_kernel<CIN, BKM><<<grid, UG_THREADS, smem, st>>>(p);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, float* gb, void* workspace, int B,
+               int rows_in, int rows_out, int S, int Cin, int Cout, cudaStream_t st) {
+  const UWPlan pl = uw_plan(Cin, Cout, S);
+  if (!pl.ok) return SHB_E_SHAPE;
+  UWParams p{};
+  p.x = (const __nv_bfloat16*)x; p.table = table; p.gz = (const __nv_bfloat16*)gz; p.ws = (float*)workspace;
+  p.M = (long long)B * rows_out;
+  int grid = pl.grid;
+  const long long per = ((p.M + grid - 1) / grid + pl.bkm - 1) / pl.bkm * pl.bkm;
+  grid = (int)((p.M + per - 1) / per);
+  p.rows_per_cta = per;
+  p.rows_in = rows_in; p.rows_out = rows_out; p.S = S; p.Cout = Cout; p.NPAD = pl.NPAD; p.K = S * Cin; p.Q = p.K / 8;
+  p.KT = pl.KT; p.NQ = pl.NPAD / 8; p.nstage = pl.nstage;
+  p.a_stage_bytes = (uint32_t)pl.KT * 16 * pl.bkm * 16; p.b_stage_bytes = (uint32_t)(pl.NPAD / 8) * pl.bkm * 16;
+  p.tmem_cols = pl.cols;
+  int rc;
+#define UW_DISPATCH(C)                                                                                          \
+  case C:                                                                                                       \
+    rc = pl.bkm == 32 ? uw_launch<C, 32>(p, grid, pl.smem, st) : uw_launch<C, 16>(p, grid, pl.smem, st);        \
+    break;
+  switch (Cin) {
+    UW_DISPATCH(16)
+    UW_DISPATCH(32)
+    UW_DISPATCH(64)
+    UW_DISPATCH(128)
+    default: return SHB_E_SHAPE;
+  }
+#undef UW_DISPATCH
+  if (rc != 0) return rc;
+  const long long n = (long long)Cout * p.K;
+  uw_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, grid, n, gw);
+  SHB_LAUNCH_CHECK();
+  if (gb != nullptr) {
+    float* part = (float*)workspace + (size_t)kNumSMs * Cout * p.K;
+    int CP = 1;
+    while (CP < Cout) CP <<= 1;
+    if (CP > 256) return SHB_E_SHAPE;
+    const int blocks = 4 * kNumSMs;
+    const long long rpb = (p.M + blocks - 1) / blocks;
+    colsum_partial_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gz, p.M, Cout, CP, rpb, part);
+    SHB_LAUNCH_CHECK();
+    uw_reduce_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(part, blocks, Cout, gb);
+    SHB_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 }  // namespace shb

@@ -34,15 +34,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Long waits (an epilogue warp waiting a whole tile, an MMA thread waiting for a gather) must not spin flat out:
+// every poll is an MIO/shared-memory op, and a dozen idle warps polling measurably starved the producers' LDS /
+// LDGSTS / arrive traffic (ncu: 75 % of executed warp-instructions were polls; short-scoreboard + MIO stalls).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---------------------------------------------------------------------------------------------- cp.async (LDGSTS)
-// 16-byte global -> shared copy, L2-only caching; src_bytes == 0 zero-fills the destination.
+// 16-byte global -> shared copy; src_bytes == 0 zero-fills the destination.
+// .ca (through L1): lanes that touch the same 128-byte line are coalesced into ONE L1TEX wavefront -- what a row
+// gather wants.  .cg (L1 bypass) issues one 32-byte sector request per lane (measured: 1 request / 16-byte chunk,
+// ~1.8 cycles each), which made the gather L1TEX-bound.
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 // The barrier receives ONE arrival (counted in its expected count) when all prior cp.async of this thread land.
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// returns once at most N of this thread's most recent cp.async groups are still in flight
+template <int N> __device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
