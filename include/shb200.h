@@ -83,10 +83,18 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
                        void* stream);
 
 /* gz = gy * act'(.) expressed through the saved OUTPUT y, zero on the dummy row when zero_last_row
- * (ELU' = y+1 for y<=0 etc.).  Replaces EluBackward/MulBackward of models.py:46,51.  In place (gz==gy) ok.
- *   gy, y, gz (B, rows_out, Cout). */
-int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int act,
-                           int zero_last_row, int dtype, void* stream);
+ * (ELU' = y+1 for y<=0 etc.).  Replaces EluBackward/MulBackward of models.py:46,51.
+ *   gy, y (B, rows_out, Cout);  gz (B, rows_out, gz_channels), gz_channels >= Cout, extra channels zero-filled
+ *   (the host pads 3-channel gradients to 16 so that they can take the tensor-core path).
+ *   In place (gz==gy) is allowed when gz_channels == Cout. */
+int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int gz_channels,
+                           int act, int zero_last_row, int dtype, void* stream);
+
+/* dst[r, c] = c < C ? src[r, c] : 0, converting between fp32 and bf16 on the way: channel zero-padding of
+ * narrow activations (the 3-channel mesh coordinates of models.py:157) to a 16-byte-chunk multiple.
+ *   src (rows, C) as dtype_src;  dst (rows, Cp) as dtype_dst. */
+int shb_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cp, int dtype_src, int dtype_dst,
+                     void* stream);
 
 /* Weight/bias gradient: gw[n, s*Cin+c] = sum_{b,j} gz[b,j,n] * x[b, table[j,s], c];  gb[n] = sum gz[b,j,n].
  * Replaces the  dZ^T . A  mm of AddmmBackward (models.py:45) without materialising A.  Split over rows with a

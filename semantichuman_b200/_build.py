@@ -1,6 +1,7 @@
 """In-tree nvcc build of libshb200.so (sm_100a only).
 
-``python -m semantichuman_b200._build`` or ``__graft_entry__.build()``.  The shared library lands next to this
+``python semantichuman_b200/_build.py`` (run as a script: importing the package would try to load the library
+being built) or ``__graft_entry__.build()``.  The shared library lands next to this
 file so that it travels with a source snapshot to a GPU box; nothing is JIT-compiled at import time.
 """
 import os

@@ -1,7 +1,7 @@
 """ctypes binding of libshb200.so (the C ABI declared in include/shb200.h).
 
 There is deliberately no fallback: if the shared library is missing or a symbol is absent the import of the
-product fails loudly (north_star: "no CPU fallback").  Build it with ``python -m semantichuman_b200._build``
+product fails loudly (north_star: "no CPU fallback").  Build it with ``python semantichuman_b200/_build.py``
 or ``__graft_entry__.build()``.
 """
 import ctypes
@@ -20,7 +20,8 @@ SIGNATURES = {
     "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "shb_csr_transpose": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 9 + [c_vp]),
-    "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
+    "shb_pad_channels": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "shb_spiralconv_wgrad_workspace": (c_size, [c_int] * 7),
     "shb_spiralconv_bwd_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size] + [c_int] * 7 + [c_vp]),
     "shb_spiralconv_bwd_dgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),
@@ -39,7 +40,7 @@ def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
             f"{_LIB_PATH} not found: the CUDA extension has not been built "
-            "(run `python -m semantichuman_b200._build`); semantichuman_b200 has no CPU fallback")
+            "(run `python semantichuman_b200/_build.py`); semantichuman_b200 has no CPU fallback")
     lib = ctypes.CDLL(_LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly

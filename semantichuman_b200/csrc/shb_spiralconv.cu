@@ -209,16 +209,34 @@ template <typename T, bool MULTI> static int launch_gather_gemm(const GGParams& 
 }
 
 // ------------------------------------------------------------------------------------------------ act backward
+// gz[row, c] = c < C ? gy[row, c] * act'(y[row, c]) : 0  (gz has CP >= C channels; dummy rows zeroed)
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gz,
-                                                      long long n, int rows_out, int C, int act, int zero_last) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const long long row = i / C;
-    const bool zero = zero_last && ((int)(row % rows_out) == rows_out - 1);
-    const float g = Io<T>::ld(gy + i);
-    const float d = act_bwd_from_out(Io<T>::ld(y + i), act);
-    Io<T>::st(gz + i, zero ? 0.f : g * d);
+                                                      unsigned rows, unsigned rows_out, int C, int CP, int act, int zero_last) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned cp = (unsigned)CP;
+  const unsigned long long total = (unsigned long long)rows * cp;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned row = (unsigned)(i / cp), c = (unsigned)(i - (unsigned long long)row * cp);
+    float v = 0.f;
+    if ((int)c < C && !(zero_last && (row % rows_out) == rows_out - 1)) {
+      const size_t k = (size_t)row * C + c;
+      v = Io<T>::ld(gy + k) * act_bwd_from_out(Io<T>::ld(y + k), act);
+    }
+    Io<T>::st(gz + i, v);
+  }
+}
+
+// dst[row, c] = c < C ? (Tdst)src[row, c] : 0   -- channel zero-padding (+ fp32 -> bf16 cast) so that 3-channel
+// mesh coordinates can use the 16-byte-chunk tensor-core gather path
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) pad_channels_kernel(const TS* __restrict__ src, TD* __restrict__ dst,
+                                                           unsigned long long rows, int C, int CP) {
+  const unsigned long long total = rows * (unsigned)CP, stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned long long row = i / (unsigned)CP;
+    const int c = (int)(i - row * (unsigned)CP);
+    Io<TD>::st(dst + i, c < C ? Io<TS>::ld(src + row * C + c) : 0.f);
   }
 }
 
@@ -468,19 +486,42 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
   return SHB_E_DTYPE;
 }
 
-int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int act,
-                           int zero_last_row, int dtype, void* stream) {
-  if (!gy || !y || !gz || B <= 0 || rows_out <= 0 || Cout <= 0) return SHB_E_ARG;
+int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int gz_channels,
+                           int act, int zero_last_row, int dtype, void* stream) {
+  if (!gy || !y || !gz || B <= 0 || rows_out <= 0 || Cout <= 0 || gz_channels < Cout) return SHB_E_ARG;
   if (act < SHB_ACT_IDENTITY || act > SHB_ACT_TANH) return SHB_E_ARG;
-  const long long n = (long long)B * rows_out * Cout;
-  const int blocks = (int)((n + 255) / 256 < 8LL * kNumSMs ? (n + 255) / 256 : 8LL * kNumSMs);
+  const unsigned long long rows = (unsigned long long)B * rows_out;
+  if (rows >= (1ull << 32)) return SHB_E_SHAPE;
+  const unsigned long long n = rows * gz_channels;
+  const int blocks = (int)((n + 255) / 256 < 16ULL * kNumSMs ? (n + 255) / 256 : 16ULL * kNumSMs);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SHB_F32)
-    act_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, n, rows_out, Cout, act,
-                                                  zero_last_row);
+    act_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, (unsigned)rows,
+                                                  (unsigned)rows_out, Cout, gz_channels, act, zero_last_row);
   else if (dtype == SHB_BF16)
     act_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
-                                                          (__nv_bfloat16*)gz, n, rows_out, Cout, act, zero_last_row);
+                                                          (__nv_bfloat16*)gz, (unsigned)rows, (unsigned)rows_out, Cout,
+                                                          gz_channels, act, zero_last_row);
+  else
+    return SHB_E_DTYPE;
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cp, int dtype_src, int dtype_dst, void* stream) {
+  if (!src || !dst || rows <= 0 || C <= 0 || Cp < C) return SHB_E_ARG;
+  const unsigned long long n = (unsigned long long)rows * Cp;
+  const int blocks = (int)((n + 255) / 256 < 16ULL * kNumSMs ? (n + 255) / 256 : 16ULL * kNumSMs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_src == SHB_F32 && dtype_dst == SHB_F32)
+    pad_channels_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, (float*)dst, rows, C, Cp);
+  else if (dtype_src == SHB_F32 && dtype_dst == SHB_BF16)
+    pad_channels_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, rows, C, Cp);
+  else if (dtype_src == SHB_BF16 && dtype_dst == SHB_BF16)
+    pad_channels_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src,
+                                                                               (__nv_bfloat16*)dst, rows, C, Cp);
+  else if (dtype_src == SHB_BF16 && dtype_dst == SHB_F32)
+    pad_channels_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, rows, C, Cp);
   else
     return SHB_E_DTYPE;
   SHB_LAUNCH_CHECK();

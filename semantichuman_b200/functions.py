@@ -89,16 +89,37 @@ def _pool_meta(B, pm, C, esize, transposed):
     return {"flops": 2.0 * B * pm.nnz * C, "bytes": float(B) * (rows_read + rows_written) * C * esize + pm.nnz * 8.0}
 
 
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def pad_channels(x, cp, out_dtype=None):
+    """(…, C) -> (…, cp) zero-padded along the channel axis (+ optional fp32<->bf16 cast) in one kernel."""
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    x = x.contiguous()
+    C = x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (cp,), dtype=out_dtype, device=x.device)
+    rows = x.numel() // C
+    _call("pad_channels", {"bytes": float(rows) * (C * x.element_size() + cp * out.element_size())}, lib.shb_pad_channels,
+          _p(x), _p(out), rows, C, cp, _DT[x.dtype], _DT[out_dtype], _stream())
+    _count()
+    return out
+
+
 class SpiralConvFn(torch.autograd.Function):
     """y = mask * act(W . gather(x) + b)   (models.py:34-53) -- one fused kernel forward; backward =
-    act' kernel + weight-gradient kernel (+ fixed-order reduce) + inverse-table input-gradient kernel."""
+    act' kernel + weight-gradient kernel (+ fixed-order reduce) + inverse-table input-gradient kernel.
+
+    bf16 mode: operands whose channel count is not a multiple of 16 (the 3-channel mesh coordinates at both ends of
+    the autoencoder) are zero-padded to 16 so that every layer takes the tcgen05 path (16-byte gather chunks, UMMA
+    K = 16); the padding never leaves this function (gradients are sliced back)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, geom, act):
+    def forward(ctx, x, weight, bias, geom, act, compute_dtype):
         _cuda(x, weight, bias)
         if x.dim() != 3:
             raise ValueError("x must be (B, V+1, C)")
-        x = x.contiguous()
+        cdt = x.dtype if compute_dtype is None else compute_dtype
         B, rows_in, cin = x.shape
         cout, k = weight.shape
         if rows_in != geom.rows_in or k != geom.S * cin:
@@ -106,53 +127,74 @@ class SpiralConvFn(torch.autograd.Function):
                              f"geometry rows_in={geom.rows_in} S={geom.S}")
         if geom.table.device != x.device:
             raise RuntimeError("spiral tables live on a different device than x")
-        w = weight.detach().to(x.dtype).contiguous()
+        S = geom.S
+        cin_p = _pad16(cin) if (cdt == torch.bfloat16 and cin % 16) else cin
+        if cin_p != cin or x.dtype != cdt:
+            xk = pad_channels(x, cin_p, cdt)  # pad and/or cast in one pass
+        else:
+            xk = x.contiguous()
+        w = weight.detach()
+        if cin_p != cin:
+            w = torch.nn.functional.pad(w.view(cout, S, cin), (0, cin_p - cin)).reshape(cout, S * cin_p)
+        w = w.to(cdt).contiguous()
         b32 = None if bias is None else bias.detach().float().contiguous()
-        y = torch.empty((B, geom.rows_out, cout), dtype=x.dtype, device=x.device)
-        meta = _conv_meta(B, rows_in, geom.rows_out, geom.S, cin, cout, x.element_size())
-        _call(f"spiralconv_fwd[{rows_in}>{geom.rows_out}x{geom.S}x{cin}>{cout}]", meta, lib.shb_spiralconv_fwd, _p(x),
-              _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, geom.S, cin, cout, act,
-              int(geom.zero_last_row), _dt(x), _stream())
+        y = torch.empty((B, geom.rows_out, cout), dtype=cdt, device=x.device)
+        meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, xk.element_size())
+        _call(f"spiralconv_fwd[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]", meta, lib.shb_spiralconv_fwd, _p(xk),
+              _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, S, cin_p, cout, act,
+              int(geom.zero_last_row), _dt(xk), _stream())
         _count()
-        ctx.save_for_backward(x, w, y)
+        ctx.save_for_backward(xk, w, y)
         ctx.geom, ctx.act, ctx.has_bias = geom, act, bias is not None
-        ctx.wdtype = weight.dtype
+        ctx.wdtype, ctx.xdtype, ctx.cin = weight.dtype, x.dtype, cin
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        geom, act = ctx.geom, ctx.act
-        B, rows_in, cin = x.shape
-        cout = w.shape[0]
+        geom, act, cin = ctx.geom, ctx.act, ctx.cin
+        B, rows_in, cin_p = x.shape
+        cout, S = w.shape[0], geom.S
         gy = gy.contiguous()
         if gy.dtype != x.dtype:
             gy = gy.to(x.dtype)
         dt, st = _dt(x), _stream()
-        gz = torch.empty_like(gy)
-        tag = f"[{rows_in}>{geom.rows_out}x{geom.S}x{cin}>{cout}]"
-        meta = _conv_meta(B, rows_in, geom.rows_out, geom.S, cin, cout, x.element_size())
-        _call("spiralconv_bwd_act" + tag, {"bytes": 3.0 * gy.numel() * gy.element_size()}, lib.shb_spiralconv_bwd_act,
-              _p(gy), _p(y), _p(gz), B, geom.rows_out, cout, act, int(geom.zero_last_row), dt, st)
+        bf16 = x.dtype == torch.bfloat16
+        cout_p = _pad16(cout) if (bf16 and cout % 8) else cout
+        gz = torch.empty((B, geom.rows_out, cout_p), dtype=x.dtype, device=x.device)
+        tag = f"[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]"
+        meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, x.element_size())
+        _call("spiralconv_bwd_act" + tag, {"bytes": (2.0 * gy.numel() + gz.numel()) * gy.element_size()},
+              lib.shb_spiralconv_bwd_act, _p(gy), _p(y), _p(gz), B, geom.rows_out, cout, cout_p, act,
+              int(geom.zero_last_row), dt, st)
         _count()
+        if cout_p != cout:  # zero rows for the padded output channels
+            w = torch.nn.functional.pad(w, (0, 0, 0, cout_p - cout)).contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            nbytes = lib.shb_spiralconv_wgrad_workspace(B, rows_in, geom.rows_out, geom.S, cin, cout, dt)
+            nbytes = lib.shb_spiralconv_wgrad_workspace(B, rows_in, geom.rows_out, S, cin_p, cout_p, dt)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-            gw = torch.empty((cout, geom.S * cin), dtype=torch.float32, device=x.device)
-            gb = torch.empty((cout,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            gw = torch.empty((cout_p, S * cin_p), dtype=torch.float32, device=x.device)
+            gb = torch.empty((cout_p,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
             _call("spiralconv_bwd_wgrad" + tag, meta, lib.shb_spiralconv_bwd_wgrad, _p(x), _p(geom.table), _p(gz), _p(gw),
-                  _p(gb), _p(ws), nbytes, B, rows_in, geom.rows_out, geom.S, cin, cout, dt, st)
+                  _p(gb), _p(ws), nbytes, B, rows_in, geom.rows_out, S, cin_p, cout_p, dt, st)
             _count(2)
+            if cout_p != cout or cin_p != cin:
+                gw = gw.view(cout_p, S, cin_p)[:cout, :, :cin].reshape(cout, S * cin)
+                gb = None if gb is None else gb[:cout]
             if ctx.wdtype != torch.float32:
                 gw = gw.to(ctx.wdtype)
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             _call("spiralconv_bwd_dgrad" + tag, meta, lib.shb_spiralconv_bwd_dgrad, _p(gz), _p(geom.keyptr),
-                  _p(geom.inv_rows), _p(w), _p(gx), B, rows_in, geom.rows_out, geom.S, cin, cout,
+                  _p(geom.inv_rows), _p(w), _p(gx), B, rows_in, geom.rows_out, S, cin_p, cout_p,
                   int(geom.dummy_row_grad), dt, st)
             _count(2 if geom.dummy_row_grad else 1)
-        return gx, gw, gb, None, None
+            if cin_p != cin:
+                gx = gx[..., :cin]
+            if gx.dtype != ctx.xdtype:
+                gx = gx.to(ctx.xdtype)
+        return gx, gw, gb, None, None, None
 
 
 class PoolFn(torch.autograd.Function):
@@ -242,10 +284,12 @@ class PartNormLossFn(torch.autograd.Function):
         return gz * g, None, None, None, None
 
 
-def spiral_conv(x, weight, bias, geom, activation="elu"):
+def spiral_conv(x, weight, bias, geom, activation="elu", compute_dtype=None):
+    """compute_dtype: storage/operand dtype of this layer (default: x.dtype); a differing input is cast (and, in
+    bf16 mode, channel-padded) by one fused kernel."""
     if activation not in ACT_ENUM:
         raise NotImplementedError(activation)
-    return SpiralConvFn.apply(x, weight, bias, geom, ACT_ENUM[activation])
+    return SpiralConvFn.apply(x, weight, bias, geom, ACT_ENUM[activation], compute_dtype)
 
 
 def pool(x, pm):

@@ -58,9 +58,9 @@ class SpiralConv(nn.Module):
         self._geom_cache.append((first.clone(), geom))
         return geom
 
-    def forward(self, x, spiral_adj):
+    def forward(self, x, spiral_adj, compute_dtype=None):
         geom = spiral_adj if isinstance(spiral_adj, SpiralGeometry) else self._geometry_for(spiral_adj)
-        return fn.spiral_conv(x, self.conv.weight, self.conv.bias, geom, self.activation_name)
+        return fn.spiral_conv(x, self.conv.weight, self.conv.bias, geom, self.activation_name, compute_dtype)
 
 
 class Pool(nn.Module):
@@ -173,9 +173,8 @@ class _SpiralTrunk(nn.Module):
     def _encode_trunk(self, x):
         if not x.is_cuda:
             raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
-        x = x.to(self.compute_dtype)
         for j, geom, pm in self._enc_plan:
-            x = self.conv[j](x, geom)
+            x = self.conv[j](x, geom, self.compute_dtype)  # the first conv casts (and pads) its fp32 input itself
             if pm is not None:
                 x = fn.pool(x, pm)
         return x
