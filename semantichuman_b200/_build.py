@@ -68,5 +68,6 @@ def build(force=False, verbose=False, extra_flags=()):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True,
-                extra_flags=("-Xptxas", "-v") if "--ptxas-v" in sys.argv else ()))
+    extra = tuple(os.environ.get("SHB_NVCC_FLAGS", "").split())  # e.g. SHB_NVCC_FLAGS=-DSHB_UMMA_TRACE (debug timeline)
+    print(build(force="--force" in sys.argv or bool(extra), verbose=True,
+                extra_flags=extra + (("-Xptxas", "-v") if "--ptxas-v" in sys.argv else ())))

@@ -25,7 +25,13 @@ using namespace umma;
 
 constexpr int UG_BM = 128;             // rows per tile == UMMA M
 constexpr int UG_KC = 8;               // 16-byte chunks (8 bf16) per row per stage  -> BK = 64
-constexpr int UG_STAGE_BYTES = UG_BM * UG_KC * 16;
+// K-direction core-matrix stride of the A ring: 128 B of payload + 16 B of padding.  LDGSTS writes shared memory one
+// returning 32-byte SECTOR at a time; a sector holds two consecutive K chunks of a row, which an un-padded layout puts
+// 128 B apart (same banks, 2-way conflict on every sector: ncu showed 35 smem wavefronts per LDGSTS).  The UMMA
+// descriptor accepts any multiple of 16 as LBO/SBO.
+constexpr int UG_LBO = 144;
+constexpr int UG_SBO = UG_KC * UG_LBO;   // 8-row group stride
+constexpr int UG_STAGE_BYTES = (UG_BM / 8) * UG_SBO;
 constexpr int UG_EPI_WARPS = 4, UG_PROD_WARPS = 8;
 constexpr int UG_PROD_THREADS = UG_PROD_WARPS * 32;
 constexpr int UG_THREADS = (UG_EPI_WARPS + 1 + UG_PROD_WARPS) * 32;
@@ -61,11 +67,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+#ifdef SHB_UMMA_TRACE
 #define UG_TRACE(role, ev, idx)                                                              \
   do {                                                                                     \
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[((role) * 4 + (ev)) * 512 + (idx)] = clock64(); \
   } while (0)
+#else
+#define UG_TRACE(role, ev, idx) do { } while (0)
+#endif
 
+// Every role's inner loop is latency-bound on a single warp's dependent instruction stream (measured with the
+// clock64 timeline: ~6 cycles per instruction), so the loops below carry NO runtime divisions, keep ring slot/phase
+// as incremented counters, and advance precomputed UMMA descriptors by adding to their low word.
 template <int CS, bool SUM>
 __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const UGParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -74,12 +87,14 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* w_img = dyn_smem;                                   // [NPAD/8][Q][8 rows][16 B]
   const uint32_t w_bytes = (uint32_t)p.NPAD * p.Q * 16;
   uint8_t* a_ring = dyn_smem + ((w_bytes + 127) / 128) * 128;  // nstage x [16 row groups][8 chunks][8 rows][16 B]
   const int K = p.Q * 8;
+  const uint32_t nstage = (uint32_t)p.nstage;
 
   // ---------------------------------------------------------------- prologue: weights -> smem (core-matrix layout)
   {
@@ -103,11 +118,12 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
       }
       *reinterpret_cast<uint4*>(w_img + ((size_t)(n >> 3) * p.Q + q) * 128 + (n & 7) * 16) = v;
     }
+    if (tid < 256) bias_s[tid] = (p.bias != nullptr && tid < p.Cd) ? __ldg(p.bias + tid) : 0.f;
     fence_proxy_async_smem();
   }
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) {
-      mbar_init(&full_bar[i], (!SUM && p.noinc) ? UG_PROD_THREADS : UG_PROD_WARPS);
+      mbar_init(&full_bar[i], SUM ? UG_PROD_WARPS : UG_PROD_THREADS);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -125,17 +141,15 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
   if (warp < UG_EPI_WARPS) {
     // ================================================================ epilogue warps: TMEM -> bias/act/mask -> bf16 -> HBM
     int tcount = 0;
+    const unsigned rows_dst = (unsigned)p.rows_dst;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
-      if (warp == 0 && lane == 0) UG_TRACE(2, 0, tcount);
-      mbar_wait_backoff(&tfull_bar[buf], (tcount >> 1) & 1, 200);
-      if (warp == 0 && lane == 0) UG_TRACE(2, 1, tcount);
+      mbar_wait_backoff(&tfull_bar[buf], (tcount >> 1) & 1, 100);
       tc_fence_after();
-      const long long m = (long long)tile * UG_BM + warp * 32 + lane;
-      const bool valid = m < p.M;
-      const int j = valid ? (int)(m % p.rows_dst) : 0;
-      const bool zero = p.zero_last && (j == p.rows_dst - 1);
-      __nv_bfloat16* out = p.dst + (valid ? m : 0) * p.Cd;
+      const unsigned m = (unsigned)tile * UG_BM + warp * 32 + lane;
+      const bool valid = (long long)m < p.M;
+      const bool zero = p.zero_last && valid && (m % rows_dst == rows_dst - 1);
+      __nv_bfloat16* out = p.dst + (size_t)(valid ? m : 0) * p.Cd;
       const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NPAD) + ((uint32_t)(warp * 32) << 16);
       for (int c0 = 0; c0 < p.NPAD; c0 += 16) {
         uint32_t r[16];
@@ -146,14 +160,10 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
+        if (!valid || (p.dbg & 4)) continue;
         float v[16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const int n = c0 + t;
-          const float b = (p.bias != nullptr && n < p.Cd) ? __ldg(p.bias + n) : 0.f;
-          v[t] = zero ? 0.f : act_fwd(__uint_as_float(r[t]) + b, p.act);
-        }
-        if (!valid || (p.dbg & 4)) continue;
+        for (int t = 0; t < 16; ++t) v[t] = zero ? 0.f : act_fwd(__uint_as_float(r[t]) + bias_s[c0 + t], p.act);
         if ((p.Cd & 7) == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -174,30 +184,45 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
     // ================================================================ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(UG_BM, p.NPAD, 0, 0);
-      const uint32_t a_base = smem_u32(a_ring), w_base = smem_u32(w_img);
-      const uint32_t sbo_b = (uint32_t)p.Q * 128;
-      uint32_t it = 0;
+      // descriptor = hi (SBO, version) | lo (start address >> 4, LBO = 128 B); k-steps and stages only move the start address
+      const uint64_t hi_a = ((uint64_t)(UG_SBO >> 4) << 32) | ((uint64_t)1 << 46);
+      const uint64_t hi_b = ((uint64_t)(((uint32_t)p.Q * 128) >> 4) << 32) | ((uint64_t)1 << 46);
+      const uint32_t lo_a0 = (smem_u32(a_ring) >> 4) | ((uint32_t)(UG_LBO >> 4) << 16);
+      const uint32_t lo_b0 = (smem_u32(w_img) >> 4) | ((128u >> 4) << 16);
+      uint32_t slot = 0, ph = 0, lo_a = lo_a0;
       int tcount = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
         mbar_wait_backoff(&tempty_bar[buf], ((tcount >> 1) & 1) ^ 1, 40);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.NPAD);
-        for (int st = 0; st < p.NS; ++st, ++it) {
-          const uint32_t slot = it % p.nstage, ph = (it / p.nstage) & 1;
-          UG_TRACE(1, 0, it);
+        uint32_t lo_b = lo_b0, acc = 0;
+        int left = p.Q;  // chunks of this tile still to multiply
+        for (int st = 0; st < p.NS; ++st) {
+          UG_TRACE(1, 0, st);
           mbar_wait_backoff(&full_bar[slot], ph, 20);
-          UG_TRACE(1, 1, it);
+          UG_TRACE(1, 1, st);
           tc_fence_after();
-          const int chunks = min(UG_KC, p.Q - st * UG_KC);
-          const uint32_t a_st = a_base + slot * UG_STAGE_BYTES;
-          for (int kk = 0; kk < chunks / 2; ++kk) {
-            const uint64_t da = smem_desc(a_st + kk * 256, 128, UG_KC * 128);
-            const uint64_t db = smem_desc(w_base + (uint32_t)(st * UG_KC + 2 * kk) * 128, 128, sbo_b);
-            if (!(p.dbg & 2)) mma_bf16(tmem_d, da, db, idesc, (st | kk) != 0);
+          if (!(p.dbg & 2)) {
+            if (left >= UG_KC) {
+#pragma unroll
+              for (int kk = 0; kk < UG_KC / 2; ++kk) {
+                mma_bf16(tmem_d, hi_a | (lo_a + kk * (2 * UG_LBO >> 4)), hi_b | (lo_b + kk * 16), idesc, acc);
+                acc = 1;
+              }
+            } else {
+              for (int kk = 0; kk < left / 2; ++kk) {
+                mma_bf16(tmem_d, hi_a | (lo_a + kk * (2 * UG_LBO >> 4)), hi_b | (lo_b + kk * 16), idesc, acc);
+                acc = 1;
+              }
+            }
           }
           mma_commit(&empty_bar[slot]);  // A stage reusable once these MMAs have read it
-          UG_TRACE(1, 2, it);
+          UG_TRACE(1, 2, st);
+          left -= UG_KC;
+          lo_b += UG_KC * 8;             // 8 chunks x 128 B >> 4
+          lo_a += UG_STAGE_BYTES >> 4;
+          if (++slot == nstage) { slot = 0; ph ^= 1; lo_a = lo_a0; }
         }
         mma_commit(&tfull_bar[buf]);     // accumulator complete
       }
@@ -205,75 +230,92 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
     __syncwarp();
   } else {
     // ================================================================ producers: gather rows into the A ring
-    // Lane mapping: 8 consecutive lanes fetch the 8 consecutive 16-byte chunks (128 B of K) of ONE row, so that a
-    // gathered neighbour row costs one L1TEX wavefront instead of one per chunk; a warp instruction covers 4 rows,
-    // a thread owns chunk column kc of rows  i*32 + pw*4 + rr,  i = 0..3.
-    // The tile's block of the index table (128 rows x SP entries) is staged in shared memory, double-buffered, with
-    // the NEXT tile's block prefetched into registers while the current tile is gathered: a stage can then be issued
-    // without any dependent global load, so the cp.async ring really fills (the loop was index-latency bound before).
+    // Lane mapping: 8 consecutive lanes fetch the 8 consecutive 16-byte chunks (128 B of K) of ONE row; a warp instruction
+    // covers 4 rows; a thread owns chunk column kc of rows  i*32 + pw*4 + rr,  i = 0..3.  Measured with ncu: LDGSTS is
+    // cheap (~6 shared-memory wavefronts per instruction instead of 35) only when BOTH hold:
+    //   * consecutive lanes read consecutive global addresses (a returning 128-byte line is handled as one unit), and
+    //   * the chunks of that line land in different banks -- hence the 144-byte K stride (UG_LBO) of the A ring.
+    // The tile's block of the index table (128 rows x SP entries) is staged in shared memory, double-buffered, the NEXT
+    // tile's block being prefetched into registers while the current tile is gathered.
     const int pt = tid - (UG_EPI_WARPS + 1) * 32;  // 0..255
     const int pw = pt >> 5, kc = pt & 7, rr = (pt >> 3) & 3;
     const uint32_t a_base = smem_u32(a_ring);
     const int SP = SUM ? p.S + 1 : p.S;            // dgrad also needs the end pointer of each key
     int32_t* idx_s = reinterpret_cast<int32_t*>(a_ring + (size_t)p.nstage * UG_STAGE_BYTES);  // [2][128*SP]
     const int nidx = UG_BM * SP;
+    const unsigned rows_dst = (unsigned)p.rows_dst;
+    // slot/channel walk of this thread's chunk column (compile-time shape)
+    constexpr int CPS = CS / 8;                          // chunks per spiral slot
+    constexpr int SPS = CS <= 64 ? UG_KC / CPS : 1;      // slots per stage (CS = 128: one slot spans two stages)
+    const int sl0 = CS <= 64 ? kc / CPS : 0;             // slot of this chunk column within a stage
+    const int c0 = CS <= 64 ? (kc % CPS) * 8 : kc * 8;   // channel offset (+64 on odd stages when CS = 128)
+    // index-block coordinates of the entries this thread prefetches (tile independent)
     int pre[UG_IDX_PER_THREAD];
-    auto fetch_idx_block = [&](int tile) {  // global -> registers (coalesced: consecutive entries are contiguous)
+    unsigned pre_r[UG_IDX_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
+      const unsigned e = (unsigned)pt + u * UG_PROD_THREADS;
+      const unsigned r = e / (unsigned)SP;
+      pre_r[u] = (e < (unsigned)nidx) ? ((r << 8) | (e - r * (unsigned)SP)) : 0xffffffffu;  // row << 8 | slot
+    }
+    auto fetch_idx_block = [&](int tile) {  // global -> registers
+      const bool live = tile < p.num_tiles;
+      const unsigned m0 = (unsigned)tile * UG_BM;
+      const unsigned j0 = live ? m0 % rows_dst : 0;
 #pragma unroll
       for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
-        const int e = pt + u * UG_PROD_THREADS;
         pre[u] = 0;
-        if (e < nidx && tile < p.num_tiles) {
-          const unsigned r = (unsigned)e / (unsigned)SP, sl = (unsigned)e - r * (unsigned)SP;
-          const unsigned m = (unsigned)tile * UG_BM + r;
-          if ((long long)m < p.M) pre[u] = __ldg(p.table + (size_t)(m % (unsigned)p.rows_dst) * p.S + sl);
+        if (live && pre_r[u] != 0xffffffffu) {
+          const unsigned r = pre_r[u] >> 8, sl = pre_r[u] & 0xff;
+          unsigned j = j0 + r;
+          if (j >= rows_dst) j = (rows_dst >= UG_BM) ? j - rows_dst : j % rows_dst;
+          if ((long long)(m0 + r) < p.M) pre[u] = __ldg(p.table + (size_t)j * p.S + sl);
         }
       }
     };
     auto store_idx_block = [&](int buf) {
 #pragma unroll
-      for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
-        const int e = pt + u * UG_PROD_THREADS;
-        if (e < nidx) idx_s[buf * nidx + e] = pre[u];
-      }
+      for (int u = 0; u < UG_IDX_PER_THREAD; ++u)
+        if (pre_r[u] != 0xffffffffu) idx_s[buf * nidx + pt + u * UG_PROD_THREADS] = pre[u];
     };
     fetch_idx_block(blockIdx.x);
     store_idx_block(0);
     asm volatile("bar.sync 1, %0;" ::"n"(UG_PROD_THREADS) : "memory");
-    uint32_t it = 0, published = 0;
+    uint32_t slot = 0, ph = 0;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int32_t* idx_cur = idx_s + (tcount & 1) * nidx;
       fetch_idx_block(tile + gridDim.x);  // next tile's block: in flight during this tile's stages
+      const unsigned m0 = (unsigned)tile * UG_BM;
+      const unsigned b0 = m0 / rows_dst, j0 = m0 - b0 * rows_dst;
       bool valid[4];
-      const __nv_bfloat16* srcb[4];
+      const __nv_bfloat16* srcc[4];
       uint32_t row_off[4];
       int irow[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = i * 32 + pw * 4 + rr;
-        const long long m = (long long)tile * UG_BM + r;
-        valid[i] = m < p.M;
-        srcb[i] = p.src;
-        if (valid[i]) {
-          const unsigned b = (unsigned)m / (unsigned)p.rows_dst;
-          srcb[i] = p.src + (size_t)b * p.rows_src * CS;
-          if (SUM && p.skip_last && ((unsigned)m - b * (unsigned)p.rows_dst) == (unsigned)(p.rows_dst - 1)) valid[i] = false;
+        const unsigned r = i * 32 + pw * 4 + rr;
+        unsigned j = j0 + r, b = b0;
+        if (j >= rows_dst) {
+          if (rows_dst >= UG_BM) { j -= rows_dst; b += 1; } else { b += j / rows_dst; j %= rows_dst; }
         }
+        valid[i] = (long long)(m0 + r) < p.M;
+        if (SUM && p.skip_last && j == rows_dst - 1) valid[i] = false;
+        srcc[i] = p.src + (valid[i] ? (size_t)b * p.rows_src * CS : 0) + c0;
         irow[i] = r * SP;
-        row_off[i] = (uint32_t)(r >> 3) * (UG_KC * 128) + (uint32_t)(r & 7) * 16 + (uint32_t)kc * 128;
+        row_off[i] = (uint32_t)(r >> 3) * UG_SBO + (uint32_t)(r & 7) * 16 + (uint32_t)kc * UG_LBO;
       }
+      int s[2] = {sl0, sl0};  // spiral slot of this thread's chunk column in the current stage (kept as a pair: see items)
       int firstn[4] = {0, 0, 0, 0}, cntn[4] = {0, 0, 0, 0};
-      auto prefetch_lists = [&](int st) {  // dgrad: first list entry of each key, one stage ahead
-        const int q = st * UG_KC + kc;
-        const int s = (q < p.Q) ? (q * 8) / CS : 0;
+      auto prefetch_lists = [&](int sa, int sb) {  // dgrad: first list entry of each key, one stage ahead
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          const int sn = (i & 1) ? sb : sa;
           firstn[i] = 0;
           cntn[i] = 0;
-          if (valid[i] && q < p.Q) {
-            const int e0 = idx_cur[irow[i] + s];
-            cntn[i] = idx_cur[irow[i] + s + 1] - e0;
+          if (valid[i] && sn < p.S) {
+            const int e0 = idx_cur[irow[i] + sn];
+            cntn[i] = idx_cur[irow[i] + sn + 1] - e0;
             firstn[i] = e0;
           }
         }
@@ -284,12 +326,10 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
           cntn[i] = cntn[i] > 1 ? (cntn[i] | (e0 << 8)) : cntn[i];  // tails (rare) re-read the list from e0
         }
       };
-      if (SUM) prefetch_lists(0);
+      if (SUM) prefetch_lists(s[0], s[1]);
       for (int st = 0; st < p.NS; ++st) {
-        const uint32_t slot = it % p.nstage, ph = (it / p.nstage) & 1;
-        const int q = st * UG_KC + kc;
-        const bool inq = q < p.Q;
-        const int k = q * 8, s = inq ? k / CS : 0, c = k - s * CS;
+        const int coff = (CS == 128 && (st & 1)) ? 64 : 0;
+        const int step = (CS == 128) ? (st & 1) : SPS;
         int firstc[4], cntc[4];
         if (SUM) {
 #pragma unroll
@@ -297,27 +337,28 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
             firstc[i] = firstn[i];
             cntc[i] = cntn[i];
           }
-          if (st + 1 < p.NS) prefetch_lists(st + 1);
+          if (st + 1 < p.NS) prefetch_lists(s[0] + step, s[1] + step);
         }
-        if (pt == 0) UG_TRACE(0, 0, it);
+        UG_TRACE(0, 0, st);
         mbar_wait(&empty_bar[slot], ph ^ 1);
-        if (pt == 0) UG_TRACE(0, 1, it);
+        UG_TRACE(0, 1, st);
         const uint32_t dst0 = a_base + slot * UG_STAGE_BYTES;
-        if (inq && !(p.dbg & 1)) {
+        if (!(p.dbg & 1)) {
           if (!SUM) {
             int row[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) row[i] = idx_cur[irow[i] + s];
+            for (int i = 0; i < 4; ++i) row[i] = (s[i & 1] < p.S) ? idx_cur[irow[i] + s[i & 1]] : 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              cp_async16(dst0 + row_off[i], srcb[i] + (size_t)row[i] * CS + c, valid[i] ? 16u : 0u);
+              if (s[i & 1] < p.S)
+                cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, valid[i] ? 16u : 0u);
           } else {
             // gather-sum in a fixed order: the four first entries in flight together, then the (rare) longer tails
             float acc[4][8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if (cntc[i] > 0) {
-                Io<__nv_bfloat16>::ld8(srcb[i] + (size_t)firstc[i] * CS + c, acc[i]);
+                Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)firstc[i] * CS + coff, acc[i]);
               } else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) acc[i][t] = 0.f;
@@ -328,52 +369,38 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
               const int cnt = cntc[i] & 0xff, e0 = cntc[i] >> 8;
               for (int e = 1; e < cnt; ++e) {
                 float v[8];
-                Io<__nv_bfloat16>::ld8(srcb[i] + (size_t)__ldg(p.list + e0 + e) * CS + c, v);
+                Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)__ldg(p.list + e0 + e) * CS + coff, v);
 #pragma unroll
                 for (int t = 0; t < 8; ++t) acc[i][t] += v[t];
               }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 o = make_uint4(pack_bf16x2(acc[i][0], acc[i][1]), pack_bf16x2(acc[i][2], acc[i][3]),
-                                         pack_bf16x2(acc[i][4], acc[i][5]), pack_bf16x2(acc[i][6], acc[i][7]));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(o.x), "r"(o.y),
-                           "r"(o.z), "r"(o.w)
-                           : "memory");
+              if (s[i & 1] < p.S) {
+                const uint4 o = make_uint4(pack_bf16x2(acc[i][0], acc[i][1]), pack_bf16x2(acc[i][2], acc[i][3]),
+                                           pack_bf16x2(acc[i][4], acc[i][5]), pack_bf16x2(acc[i][6], acc[i][7]));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(o.x), "r"(o.y),
+                             "r"(o.z), "r"(o.w)
+                             : "memory");
+              }
             }
           }
         }
-        if (pt == 0) UG_TRACE(0, 2, it);
-        ++it;
+        UG_TRACE(0, 2, st);
         if (!SUM) {
-          if (p.noinc) {
-            cp_async_mbar_arrive_noinc(&full_bar[slot]);
-          } else {
-            cp_async_commit();
-            if (it - published > UG_LAG) {
-              cp_async_wait_group<UG_LAG>();
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&full_bar[published % p.nstage]);
-              ++published;
-            }
-          }
+          cp_async_mbar_arrive_noinc(&full_bar[slot]);  // one (counted) arrival when this thread's copies have landed
         } else {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[slot]);
         }
+        if (++slot == nstage) { slot = 0; ph ^= 1; }
+        s[0] += step;
+        s[1] += step;
       }
       // publish the next tile's index block; every producer is past its reads of that buffer (barrier of the previous tile)
       store_idx_block((tcount + 1) & 1);
       asm volatile("bar.sync 1, %0;" ::"n"(UG_PROD_THREADS) : "memory");
-    }
-    if (!SUM && !p.noinc) {  // drain: publish the stages still in flight
-      cp_async_wait_group<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      for (; published < it; ++published)
-        if (lane == 0) mbar_arrive(&full_bar[published % p.nstage]);
     }
   }
 
@@ -393,14 +420,14 @@ void umma_set_trace(long long* buf) { g_trace = buf; }
 static size_t ug_smem_bytes(int NPAD, int Q, int nstage, int S) {
   return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES + (size_t)2 * UG_BM * (S + 1) * 4;
 }
-constexpr size_t UG_SMEM_MAX = 227 * 1024 - 1024;  // leave room for the static barriers
+constexpr size_t UG_SMEM_MAX = 227 * 1024 - 2048;  // leave room for the static smem (barriers, bias)
 
 static int ug_npad(int Cd) { return ((Cd + 15) / 16) * 16; }
 
 bool umma_gather_gemm_supported(int Cs, int Cd, int S) {
   if (!(Cs == 16 || Cs == 32 || Cs == 64 || Cs == 128)) return false;
   const int NPAD = ug_npad(Cd);
-  if (NPAD > 256) return false;
+  if (NPAD > 256 || Cd > 256) return false;
   if (UG_BM * (S + 1) > UG_IDX_PER_THREAD * UG_PROD_THREADS) return false;  // S <= 15
   return ug_smem_bytes(NPAD, S * Cs / 8, UG_LAG + 1, S) <= UG_SMEM_MAX;
 }
@@ -526,7 +553,9 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  constexpr uint32_t SBO = BKM * 16;  // MN-direction core-matrix stride; K-direction (row groups of 8) stride = 128
+  // MN-direction core-matrix stride (+16 B of padding: the two 16-byte halves of a returning 32-byte sector are consecutive
+  // MN chunks and must not share banks); K-direction (row groups of 8) stride = 128
+  constexpr uint32_t SBO = BKM * 16 + 16;
 
   if (warp < UG_EPI_WARPS) {
     // ================================================================ epilogue: TMEM -> fp32 partial in the workspace
@@ -686,7 +715,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
   }
 }
 
-static size_t uw_stage_bytes(int KT, int NPAD, int bkm) { return (size_t)KT * 16 * bkm * 16 + (size_t)(NPAD / 8) * bkm * 16; }
+static size_t uw_stage_bytes(int KT, int NPAD, int bkm) { return ((size_t)KT * 16 + (size_t)(NPAD / 8)) * (bkm * 16 + 16); }
 
 struct UWPlan { int bkm, nstage, KT, NPAD, grid; size_t smem; uint32_t cols; bool ok; };
 
@@ -746,7 +775,7 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
   p.rows_per_cta = per;
   p.rows_in = rows_in; p.rows_out = rows_out; p.S = S; p.Cout = Cout; p.NPAD = pl.NPAD; p.K = S * Cin; p.Q = p.K / 8;
   p.KT = pl.KT; p.NQ = pl.NPAD / 8; p.nstage = pl.nstage;
-  p.a_stage_bytes = (uint32_t)pl.KT * 16 * pl.bkm * 16; p.b_stage_bytes = (uint32_t)(pl.NPAD / 8) * pl.bkm * 16;
+  p.a_stage_bytes = (uint32_t)pl.KT * 16 * (pl.bkm * 16 + 16); p.b_stage_bytes = (uint32_t)(pl.NPAD / 8) * (pl.bkm * 16 + 16);
   p.tmem_cols = pl.cols;
   int rc;
 #define UW_DISPATCH(C)                                                                                          \
