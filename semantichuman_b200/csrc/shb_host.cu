@@ -58,6 +58,17 @@ int shb_build_inverse_spiral_by_slot(const int32_t* table, int rows_out, int S, 
   return 0;
 }
 
+int shb_build_inverse_spiral_pairs(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, int32_t* pairs) {
+  if (!keyptr || !rows || !pairs || rows_in <= 0 || S <= 0) return SHB_E_ARG;
+  const long long nkeys = (long long)rows_in * S;
+  for (long long k = 0; k < nkeys; ++k) {
+    const int e0 = keyptr[k], cnt = keyptr[k + 1] - e0;
+    pairs[2 * k] = cnt >= 1 ? rows[e0] : -1;
+    pairs[2 * k + 1] = cnt == 2 ? rows[e0 + 1] : (cnt > 2 ? -2 : -1);
+  }
+  return 0;
+}
+
 int shb_dense_to_csr(const float* dense, int rows, int cols, int32_t* rowptr, int32_t* colidx, float* vals,
                      int64_t cap, int64_t* nnz_out) {
   if (!dense || rows <= 0 || cols <= 0 || !nnz_out) return SHB_E_ARG;

@@ -7,7 +7,8 @@ namespace shb {
 
 // tcgen05 gather-GEMM (shb_spiralconv_umma.cu): bf16 storage, gather width Cs in {16,32,64,128}.
 bool umma_gather_gemm_supported(int Cs, int Cd, int S);
-int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* list, const void* w, const float* bias,
+int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* keyptr, const int32_t* list, const void* w,
+                     const float* bias,
                      void* dst, int B, int rows_src, int rows_dst, int S, int Cs, int Cd, int act, int zero_last,
                      int skip_last, bool sum_mode, cudaStream_t st);
 

@@ -479,7 +479,7 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
   if (dtype == SHB_F32) return launch_gather_gemm<float, false>(p, st);
   if (dtype == SHB_BF16) {
     if (umma_enabled() && umma_gather_gemm_supported(Cin, Cout, S))  // tensor-core path (tcgen05 + TMEM)
-      return umma_gather_gemm(x, table, nullptr, w, (const float*)bias, y, B, rows_in, rows_out, S, Cin, Cout, act,
+      return umma_gather_gemm(x, table, nullptr, nullptr, w, (const float*)bias, y, B, rows_in, rows_out, S, Cin, Cout, act,
                               zero_last_row, 0, false, st);
     return launch_gather_gemm<__nv_bfloat16, false>(p, st);
   }
@@ -561,7 +561,8 @@ int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz
   return SHB_E_DTYPE;
 }
 
-int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const void* w, void* gx,
+int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const int32_t* pairs,
+                             const void* w, void* gx,
                              int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dummy_row_grad,
                              int dtype, void* stream) {
   if (!gz || !keyptr || !rows || !w || !gx) return SHB_E_ARG;
@@ -575,8 +576,8 @@ int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_
   int rc;
   if (dtype == SHB_F32) rc = launch_gather_gemm<float, true>(p, st);
   else if (dtype == SHB_BF16) {
-    if (umma_enabled() && umma_gather_gemm_supported(Cout, Cin, S))
-      rc = umma_gather_gemm(gz, keyptr, rows, w, nullptr, gx, B, rows_out, rows_in, S, Cout, Cin, SHB_ACT_IDENTITY, 0, 1,
+    if (umma_enabled() && pairs != nullptr && umma_gather_gemm_supported(Cout, Cin, S))
+      rc = umma_gather_gemm(gz, pairs, keyptr, rows, w, nullptr, gx, B, rows_out, rows_in, S, Cout, Cin, SHB_ACT_IDENTITY, 0, 1,
                             true, st);
     else
       rc = launch_gather_gemm<__nv_bfloat16, true>(p, st);

@@ -35,16 +35,22 @@ constexpr int UG_STAGE_BYTES = (UG_BM / 8) * UG_SBO;
 constexpr int UG_EPI_WARPS = 4, UG_PROD_WARPS = 8;
 constexpr int UG_PROD_THREADS = UG_PROD_WARPS * 32;
 constexpr int UG_THREADS = (UG_EPI_WARPS + 1 + UG_PROD_WARPS) * 32;
+// the gather-SUM (input-gradient) variant is bound by load latency, not by issue: it runs 16 producer warps (2 row-items
+// per thread instead of 4), one CTA per SM
+constexpr int ug_prod_warps(bool sum) { return sum ? 16 : 8; }
+constexpr int ug_threads(bool sum) { return (UG_EPI_WARPS + 1 + ug_prod_warps(sum)) * 32; }
 constexpr int UG_MAX_STAGES = 8;
 // A producer thread keeps this many cp.async groups (stages) in flight behind the one it is issuing; a stage is
 // published (one mbarrier arrival per WARP -- per-thread arrivals serialise on the barrier at ~16 cycles each) once
 // cp.async.wait_group says it has landed.  Must be < ring depth.
 constexpr int UG_LAG = 2;
-constexpr int UG_IDX_PER_THREAD = 8;  // per-tile index block: 128 rows x (S or S+1) entries <= 8 * 256
+constexpr int UG_IDX_PER_THREAD = 16;  // per-tile index block: 128 rows x (S or 2S) entries <= 16 * 256
 
 struct UGParams {
   const __nv_bfloat16* src;  // (B, rows_src, CS)
-  const int32_t* table;      // forward: (rows_dst, S) source rows.  dgrad: keyptr (rows_dst*S + 1)
+  const int32_t* table;      // forward: (rows_dst, S) source rows.  dgrad: pairs (rows_dst, S, 2): first two source rows of
+                             //   key (u,s) inline; -1 = none; second == -2 = three or more entries -> CSR below
+  const int32_t* keyptr;     // dgrad: (rows_dst*S + 1) CSR of the (u,s)-keyed inverse relation (overflow path only)
   const int32_t* list;       // dgrad: concatenated source rows per key
   const __nv_bfloat16* w;    // nn.Linear weight (Cout, S*Cin), bf16
   const float* bias;         // (Cd) fp32 or null
@@ -80,7 +86,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // clock64 timeline: ~6 cycles per instruction), so the loops below carry NO runtime divisions, keep ring slot/phase
 // as incremented counters, and advance precomputed UMMA descriptors by adding to their low word.
 template <int CS, bool SUM>
-__global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const UGParams p) {
+__global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm_kernel(const UGParams p) {
+  constexpr int NPW = ug_prod_warps(SUM);   // producer warps
+  constexpr int NPT = NPW * 32;             // producer threads
+  constexpr int NTH = ug_threads(SUM);      // CTA threads
+  constexpr int NIT = UG_BM * UG_KC / NPT;  // (row, chunk) items per producer thread per stage: 4 or 2
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[UG_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UG_MAX_STAGES];
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
   // ---------------------------------------------------------------- prologue: weights -> smem (core-matrix layout)
   {
     const int total_chunks = p.NPAD * p.Q;
-    for (int i = tid; i < total_chunks; i += UG_THREADS) {
+    for (int i = tid; i < total_chunks; i += NTH) {
       const int n = i / p.Q, q = i - n * p.Q;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (n < p.Cd) {
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
   }
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) {
-      mbar_init(&full_bar[i], SUM ? UG_PROD_WARPS : UG_PROD_THREADS);
+      mbar_init(&full_bar[i], SUM ? NPW : NPT);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -237,10 +247,10 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
     //   * the chunks of that line land in different banks -- hence the 144-byte K stride (UG_LBO) of the A ring.
     // The tile's block of the index table (128 rows x SP entries) is staged in shared memory, double-buffered, the NEXT
     // tile's block being prefetched into registers while the current tile is gathered.
-    const int pt = tid - (UG_EPI_WARPS + 1) * 32;  // 0..255
+    const int pt = tid - (UG_EPI_WARPS + 1) * 32;  // 0..NPT-1
     const int pw = pt >> 5, kc = pt & 7, rr = (pt >> 3) & 3;
     const uint32_t a_base = smem_u32(a_ring);
-    const int SP = SUM ? p.S + 1 : p.S;            // dgrad also needs the end pointer of each key
+    const int SP = SUM ? 2 * p.S : p.S;            // dgrad: (first, second) source row per key
     int32_t* idx_s = reinterpret_cast<int32_t*>(a_ring + (size_t)p.nstage * UG_STAGE_BYTES);  // [2][128*SP]
     const int nidx = UG_BM * SP;
     const unsigned rows_dst = (unsigned)p.rows_dst;
@@ -250,11 +260,12 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
     const int sl0 = CS <= 64 ? kc / CPS : 0;             // slot of this chunk column within a stage
     const int c0 = CS <= 64 ? (kc % CPS) * 8 : kc * 8;   // channel offset (+64 on odd stages when CS = 128)
     // index-block coordinates of the entries this thread prefetches (tile independent)
-    int pre[UG_IDX_PER_THREAD];
-    unsigned pre_r[UG_IDX_PER_THREAD];
+    constexpr int IPT = UG_IDX_PER_THREAD / 2;           // 8 entries per thread: 128 x S over 256, or 128 x 2S over 512
+    int pre[IPT];
+    unsigned pre_r[IPT];
 #pragma unroll
-    for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
-      const unsigned e = (unsigned)pt + u * UG_PROD_THREADS;
+    for (int u = 0; u < IPT; ++u) {
+      const unsigned e = (unsigned)pt + u * NPT;
       const unsigned r = e / (unsigned)SP;
       pre_r[u] = (e < (unsigned)nidx) ? ((r << 8) | (e - r * (unsigned)SP)) : 0xffffffffu;  // row << 8 | slot
     }
@@ -263,24 +274,24 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
       const unsigned m0 = (unsigned)tile * UG_BM;
       const unsigned j0 = live ? m0 % rows_dst : 0;
 #pragma unroll
-      for (int u = 0; u < UG_IDX_PER_THREAD; ++u) {
+      for (int u = 0; u < IPT; ++u) {
         pre[u] = 0;
         if (live && pre_r[u] != 0xffffffffu) {
           const unsigned r = pre_r[u] >> 8, sl = pre_r[u] & 0xff;
           unsigned j = j0 + r;
           if (j >= rows_dst) j = (rows_dst >= UG_BM) ? j - rows_dst : j % rows_dst;
-          if ((long long)(m0 + r) < p.M) pre[u] = __ldg(p.table + (size_t)j * p.S + sl);
+          if ((long long)(m0 + r) < p.M) pre[u] = __ldg(p.table + (size_t)j * SP + sl);
         }
       }
     };
     auto store_idx_block = [&](int buf) {
 #pragma unroll
-      for (int u = 0; u < UG_IDX_PER_THREAD; ++u)
-        if (pre_r[u] != 0xffffffffu) idx_s[buf * nidx + pt + u * UG_PROD_THREADS] = pre[u];
+      for (int u = 0; u < IPT; ++u)
+        if (pre_r[u] != 0xffffffffu) idx_s[buf * nidx + pt + u * NPT] = pre[u];
     };
     fetch_idx_block(blockIdx.x);
     store_idx_block(0);
-    asm volatile("bar.sync 1, %0;" ::"n"(UG_PROD_THREADS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
     uint32_t slot = 0, ph = 0;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
@@ -288,13 +299,13 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
       fetch_idx_block(tile + gridDim.x);  // next tile's block: in flight during this tile's stages
       const unsigned m0 = (unsigned)tile * UG_BM;
       const unsigned b0 = m0 / rows_dst, j0 = m0 - b0 * rows_dst;
-      bool valid[4];
-      const __nv_bfloat16* srcc[4];
-      uint32_t row_off[4];
-      int irow[4];
+      bool valid[NIT];
+      const __nv_bfloat16* srcc[NIT];
+      uint32_t row_off[NIT];
+      int irow[NIT], urow[NIT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned r = i * 32 + pw * 4 + rr;
+      for (int i = 0; i < NIT; ++i) {
+        const unsigned r = i * (UG_BM / NIT) + pw * 4 + rr;
         unsigned j = j0 + r, b = b0;
         if (j >= rows_dst) {
           if (rows_dst >= UG_BM) { j -= rows_dst; b += 1; } else { b += j / rows_dst; j %= rows_dst; }
@@ -303,104 +314,89 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gather_gemm_kernel(const U
         if (SUM && p.skip_last && j == rows_dst - 1) valid[i] = false;
         srcc[i] = p.src + (valid[i] ? (size_t)b * p.rows_src * CS : 0) + c0;
         irow[i] = r * SP;
+        urow[i] = (int)j;
         row_off[i] = (uint32_t)(r >> 3) * UG_SBO + (uint32_t)(r & 7) * 16 + (uint32_t)kc * UG_LBO;
       }
-      int s[2] = {sl0, sl0};  // spiral slot of this thread's chunk column in the current stage (kept as a pair: see items)
-      int firstn[4] = {0, 0, 0, 0}, cntn[4] = {0, 0, 0, 0};
-      auto prefetch_lists = [&](int sa, int sb) {  // dgrad: first list entry of each key, one stage ahead
+      int s = sl0;  // spiral slot of this thread's chunk column in the current stage
+      // gather-sum: raw (first, second) entries of every item, loaded one stage ahead of their use
+      uint4 va[NIT], vb[NIT];
+      int eflag[NIT];
+      auto issue_sum_loads = [&](int sn, int coff) {
+        int ea[NIT], eb[NIT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int sn = (i & 1) ? sb : sa;
-          firstn[i] = 0;
-          cntn[i] = 0;
-          if (valid[i] && sn < p.S) {
-            const int e0 = idx_cur[irow[i] + sn];
-            cntn[i] = idx_cur[irow[i] + sn + 1] - e0;
-            firstn[i] = e0;
-          }
+        for (int i = 0; i < NIT; ++i) {
+          const bool on = valid[i] && sn < p.S;
+          ea[i] = on ? idx_cur[irow[i] + 2 * sn] : -1;
+          eb[i] = on ? idx_cur[irow[i] + 2 * sn + 1] : -1;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e0 = firstn[i];
-          firstn[i] = cntn[i] > 0 ? __ldg(p.list + e0) : 0;
-          cntn[i] = cntn[i] > 1 ? (cntn[i] | (e0 << 8)) : cntn[i];  // tails (rare) re-read the list from e0
+        for (int i = 0; i < NIT; ++i) {
+          va[i] = ea[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)ea[i] * CS + coff)) : make_uint4(0, 0, 0, 0);
+          vb[i] = eb[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)eb[i] * CS + coff)) : make_uint4(0, 0, 0, 0);
+          eflag[i] = eb[i];
         }
       };
-      if (SUM) prefetch_lists(s[0], s[1]);
+      if (SUM) issue_sum_loads(s, 0);
       for (int st = 0; st < p.NS; ++st) {
         const int coff = (CS == 128 && (st & 1)) ? 64 : 0;
         const int step = (CS == 128) ? (st & 1) : SPS;
-        int firstc[4], cntc[4];
-        if (SUM) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            firstc[i] = firstn[i];
-            cntc[i] = cntn[i];
-          }
-          if (st + 1 < p.NS) prefetch_lists(s[0] + step, s[1] + step);
-        }
         UG_TRACE(0, 0, st);
         mbar_wait(&empty_bar[slot], ph ^ 1);
         UG_TRACE(0, 1, st);
         const uint32_t dst0 = a_base + slot * UG_STAGE_BYTES;
-        if (!(p.dbg & 1)) {
+        if (s < p.S && !(p.dbg & 1)) {
           if (!SUM) {
-            int row[4];
+            int row[NIT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) row[i] = (s[i & 1] < p.S) ? idx_cur[irow[i] + s[i & 1]] : 0;
+            for (int i = 0; i < NIT; ++i) row[i] = idx_cur[irow[i] + s];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (s[i & 1] < p.S)
-                cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, valid[i] ? 16u : 0u);
+            for (int i = 0; i < NIT; ++i)
+              cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, valid[i] ? 16u : 0u);
           } else {
-            // gather-sum in a fixed order: the four first entries in flight together, then the (rare) longer tails
-            float acc[4][8];
+            // fixed summation order: first entry + second entry, then (rare: 3+ entries) the CSR tail, ascending
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (cntc[i] > 0) {
-                Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)firstc[i] * CS + coff, acc[i]);
-              } else {
+            for (int i = 0; i < NIT; ++i) {
+              float acc[8];
+              const uint32_t wa[4] = {va[i].x, va[i].y, va[i].z, va[i].w}, wb[4] = {vb[i].x, vb[i].y, vb[i].z, vb[i].w};
 #pragma unroll
-                for (int t = 0; t < 8; ++t) acc[i][t] = 0.f;
+              for (int q = 0; q < 4; ++q) {
+                acc[2 * q] = __uint_as_float(wa[q] << 16) + __uint_as_float(wb[q] << 16);
+                acc[2 * q + 1] = __uint_as_float(wa[q] & 0xffff0000u) + __uint_as_float(wb[q] & 0xffff0000u);
               }
-            }
+              if (eflag[i] == -2) {
+                const int k = urow[i] * p.S + s;
+                const int e0 = __ldg(p.keyptr + k), e1 = __ldg(p.keyptr + k + 1);
+                for (int e = e0 + 1; e < e1; ++e) {
+                  float v[8];
+                  Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)__ldg(p.list + e) * CS + coff, v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int cnt = cntc[i] & 0xff, e0 = cntc[i] >> 8;
-              for (int e = 1; e < cnt; ++e) {
-                float v[8];
-                Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)__ldg(p.list + e0 + e) * CS + coff, v);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) acc[i][t] += v[t];
+                  for (int q = 0; q < 8; ++q) acc[q] += v[q];
+                }
               }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (s[i & 1] < p.S) {
-                const uint4 o = make_uint4(pack_bf16x2(acc[i][0], acc[i][1]), pack_bf16x2(acc[i][2], acc[i][3]),
-                                           pack_bf16x2(acc[i][4], acc[i][5]), pack_bf16x2(acc[i][6], acc[i][7]));
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(o.x), "r"(o.y),
-                             "r"(o.z), "r"(o.w)
-                             : "memory");
-              }
+              const uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(o.x), "r"(o.y),
+                           "r"(o.z), "r"(o.w)
+                           : "memory");
             }
           }
         }
         UG_TRACE(0, 2, st);
+        s += step;
         if (!SUM) {
           cp_async_mbar_arrive_noinc(&full_bar[slot]);  // one (counted) arrival when this thread's copies have landed
         } else {
+          // next stage's loads go out BEFORE this stage's fence/arrive so that their latency overlaps the hand-shake
+          if (st + 1 < p.NS) issue_sum_loads(s, (CS == 128 && ((st + 1) & 1)) ? 64 : 0);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[slot]);
         }
         if (++slot == nstage) { slot = 0; ph ^= 1; }
-        s[0] += step;
-        s[1] += step;
       }
       // publish the next tile's index block; every producer is past its reads of that buffer (barrier of the previous tile)
       store_idx_block((tcount + 1) & 1);
-      asm volatile("bar.sync 1, %0;" ::"n"(UG_PROD_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
     }
   }
 
@@ -418,7 +414,7 @@ static long long* g_trace = nullptr;
 void umma_set_trace(long long* buf) { g_trace = buf; }
 
 static size_t ug_smem_bytes(int NPAD, int Q, int nstage, int S) {
-  return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES + (size_t)2 * UG_BM * (S + 1) * 4;
+  return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES + (size_t)2 * UG_BM * (2 * S) * 4;
 }
 constexpr size_t UG_SMEM_MAX = 227 * 1024 - 2048;  // leave room for the static smem (barriers, bias)
 
@@ -428,7 +424,7 @@ bool umma_gather_gemm_supported(int Cs, int Cd, int S) {
   if (!(Cs == 16 || Cs == 32 || Cs == 64 || Cs == 128)) return false;
   const int NPAD = ug_npad(Cd);
   if (NPAD > 256 || Cd > 256) return false;
-  if (UG_BM * (S + 1) > UG_IDX_PER_THREAD * UG_PROD_THREADS) return false;  // S <= 15
+  if (S > 16) return false;  // per-tile index block: 8 entries per producer thread
   return ug_smem_bytes(NPAD, S * Cs / 8, UG_LAG + 1, S) <= UG_SMEM_MAX;
 }
 
@@ -450,22 +446,24 @@ template <int CS, bool SUM> static int ug_launch(const UGParams& p, size_t smem,
     regs = fa.numRegs;
     cudaFuncSetAttribute(umma_gather_gemm_kernel<CS, SUM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   }
-  const int by_regs = 65536 / (((regs + 7) / 8 * 8) * UG_THREADS);
+  const int by_regs = 65536 / (((regs + 7) / 8 * 8) * ug_threads(SUM));
   const int by_smem = (int)((228 * 1024) / (smem + 2048));
   int occ = by_regs < by_smem ? by_regs : by_smem;
   if (occ < 1) occ = 1;
   int grid = kNumSMs * (occ < want_per_sm ? occ : want_per_sm);
   if (grid > p.num_tiles) grid = p.num_tiles;
-  umma_gather_gemm_kernel<CS, SUM><<<grid, UG_THREADS, smem, st>>>(p);
+  umma_gather_gemm_kernel<CS, SUM><<<grid, ug_threads(SUM), smem, st>>>(p);
   SHB_LAUNCH_CHECK();
   return 0;
 }
 
-int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* list, const void* w, const float* bias,
+int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* keyptr, const int32_t* list, const void* w,
+                     const float* bias,
                      void* dst, int B, int rows_src, int rows_dst, int S, int Cs, int Cd, int act, int zero_last,
                      int skip_last, bool sum_mode, cudaStream_t st) {
   UGParams p{};
-  p.src = (const __nv_bfloat16*)src; p.table = table; p.list = list; p.w = (const __nv_bfloat16*)w; p.bias = bias;
+  p.src = (const __nv_bfloat16*)src; p.table = table; p.keyptr = keyptr; p.list = list; p.w = (const __nv_bfloat16*)w;
+  p.bias = bias;
   p.dst = (__nv_bfloat16*)dst;
   p.M = (long long)B * rows_dst;
   p.rows_src = rows_src; p.rows_dst = rows_dst; p.S = S; p.Cd = Cd; p.NPAD = ug_npad(Cd);
@@ -484,7 +482,7 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* list,
   while (nstage > UG_LAG + 1 && ug_smem_bytes(p.NPAD, p.Q, nstage, S) > UG_SMEM_MAX) --nstage;
   // two CTAs per SM when both fit with a deep enough ring: more gathers in flight
   int ctas_per_sm = 1;
-  if (ug_smem_bytes(p.NPAD, p.Q, 4, S) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }
+  if (!sum_mode && ug_smem_bytes(p.NPAD, p.Q, 4, S) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }
   p.nstage = nstage;
   uint32_t cols = 32;
   while (cols < 2u * p.NPAD) cols <<= 1;

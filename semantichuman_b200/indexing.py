@@ -55,6 +55,15 @@ def build_inverse_spiral_by_slot(table, rows_in):
     return keyptr, rows
 
 
+def build_inverse_spiral_pairs(keyptr, rows, rows_in, S):
+    """(rows_in, S, 2) host int32: first two entries of every (u,s) key inline; -1 none; second == -2 -> 3+ entries."""
+    keyptr, rows = _i32(keyptr), _i32(rows)
+    pairs = np.empty((rows_in, S, 2), np.int32)
+    check(lib.shb_build_inverse_spiral_pairs(keyptr.ctypes.data, rows.ctypes.data, rows_in, S, pairs.ctypes.data),
+          "shb_build_inverse_spiral_pairs")
+    return pairs
+
+
 def dense_to_csr(dense):
     """fp32 dense (rows, cols) -> (rowptr, colidx, vals) host arrays, exact zeros dropped."""
     d = np.ascontiguousarray(dense, dtype=np.float32)
@@ -103,6 +112,7 @@ class SpiralGeometry:
         self.table = torch.from_numpy(table).to(self.device)
         self.keyptr = torch.from_numpy(keyptr).to(self.device)
         self.inv_rows = torch.from_numpy(rows).to(self.device)
+        self.inv_pairs = torch.from_numpy(build_inverse_spiral_pairs(keyptr, rows, self.rows_in, self.S)).to(self.device)
 
     @classmethod
     def from_spiral(cls, spiral_adj, device, **kw):
