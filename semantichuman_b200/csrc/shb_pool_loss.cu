@@ -6,32 +6,34 @@
 namespace shb {
 
 // ------------------------------------------------------------------------------------------------ Pool SpMM
-// One thread per (b, r, V-wide channel vector).  V = 4 (16 B fp32 / 8 B bf16) when C % 4 == 0, else 1.
+// One thread per (b, r, V-wide channel vector): V = 16 bytes' worth when C allows (8 bf16 / 4 fp32), else 1.
+// 32-bit index arithmetic (the host checks the item count fits).
 template <typename T, int V>
 __global__ void __launch_bounds__(256) pool_spmm_kernel(const T* __restrict__ x, const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx, const float* __restrict__ vals,
-                                                        T* __restrict__ y, long long total, int rows_in, int rows_out, int CV) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int cv = (int)(i % CV);
-    const long long br = i / CV;
-    const int r = (int)(br % rows_out);
-    const long long b = br / rows_out;
+                                                        T* __restrict__ y, unsigned total, unsigned rows_in, unsigned rows_out,
+                                                        unsigned CV) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned br = i / CV, cv = i - br * CV;
+    const unsigned b = br / rows_out, r = br - b * rows_out;
     const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
-    const T* xb = x + (b * rows_in) * (long long)(CV * V) + cv * V;
+    const T* xb = x + ((size_t)b * rows_in) * (CV * V) + cv * V;
     for (int e = e0; e < e1; ++e) {
       const float a = __ldg(vals + e);
-      const T* px = xb + (long long)__ldg(colidx + e) * (CV * V);
+      const T* px = xb + (size_t)__ldg(colidx + e) * (CV * V);
       float v[V];
-      if (V == 4) Io<T>::ld4(px, v); else v[0] = Io<T>::ld(px);
+      if (V == 8) Io<T>::ld8(px, v); else if (V == 4) Io<T>::ld4(px, v); else v[0] = Io<T>::ld(px);
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] = fmaf(a, v[k], acc[k]);
     }
-    T* py = y + br * (long long)(CV * V) + cv * V;
-    if (V == 4) Io<T>::st4(py, acc); else Io<T>::st(py, acc[0]);
+    T* py = y + (size_t)br * (CV * V) + cv * V;
+    if (V == 8) { Io<T>::st4(py, acc); Io<T>::st4(py + 4, acc + 4); }
+    else if (V == 4) Io<T>::st4(py, acc);
+    else Io<T>::st(py, acc[0]);
   }
 }
 
@@ -115,20 +117,26 @@ int shb_pool_spmm(const void* x, const int32_t* rowptr, const int32_t* colidx, c
   if (!x || !rowptr || !colidx || !vals || !y) return SHB_E_ARG;
   if (B <= 0 || rows_in <= 0 || rows_out <= 0 || C <= 0) return SHB_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool v4 = (C % 4) == 0;
-  const int CV = v4 ? C / 4 : C;
-  const long long total = (long long)B * rows_out * CV;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+  int V = 1;
+  if (dtype == SHB_BF16 && C % 8 == 0) V = 8;
+  else if (C % 4 == 0) V = 4;
+  const unsigned CV = (unsigned)(C / V);
+  const unsigned long long total64 = (unsigned long long)B * rows_out * CV;
+  if (total64 >= (1ull << 32)) return SHB_E_SHAPE;
+  const unsigned total = (unsigned)total64;
+  unsigned blocks = (total + 255) / 256;
+  if (blocks > 32u * kNumSMs) blocks = 32u * kNumSMs;
+#define SHB_POOL_LAUNCH(TT, VV)                                                                                        \
+  pool_spmm_kernel<TT, VV><<<blocks, 256, 0, st>>>((const TT*)x, rowptr, colidx, vals, (TT*)y, total, (unsigned)rows_in, \
+                                                   (unsigned)rows_out, CV)
   if (dtype == SHB_F32) {
-    if (v4) pool_spmm_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, rowptr, colidx, vals, (float*)y, total, rows_in, rows_out, CV);
-    else pool_spmm_kernel<float, 1><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, rowptr, colidx, vals, (float*)y, total, rows_in, rows_out, CV);
+    if (V == 4) SHB_POOL_LAUNCH(float, 4); else SHB_POOL_LAUNCH(float, 1);
   } else if (dtype == SHB_BF16) {
-    if (v4) pool_spmm_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rowptr, colidx, vals, (__nv_bfloat16*)y, total, rows_in, rows_out, CV);
-    else pool_spmm_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rowptr, colidx, vals, (__nv_bfloat16*)y, total, rows_in, rows_out, CV);
+    if (V == 8) SHB_POOL_LAUNCH(__nv_bfloat16, 8); else if (V == 4) SHB_POOL_LAUNCH(__nv_bfloat16, 4); else SHB_POOL_LAUNCH(__nv_bfloat16, 1);
   } else {
     return SHB_E_DTYPE;
   }
+#undef SHB_POOL_LAUNCH
   SHB_LAUNCH_CHECK();
   return 0;
 }

@@ -227,6 +227,25 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ gy, 
   }
 }
 
+// 16-byte vectorised variant for the un-padded case (C % VEC == 0): one thread per VEC-wide channel chunk, 32-bit math
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) act_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gz,
+                                                          unsigned chunks, unsigned chunks_per_row, unsigned rows_out, int act,
+                                                          int zero_last) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += stride) {
+    const unsigned row = i / chunks_per_row;
+    const bool zero = zero_last && (row % rows_out) == rows_out - 1;
+    float g[VEC], o[VEC], r[VEC];
+    if (VEC == 8) { Io<T>::ld8(gy + (size_t)i * VEC, g); Io<T>::ld8(y + (size_t)i * VEC, o); }
+    else { Io<T>::ld4(gy + (size_t)i * VEC, g); Io<T>::ld4(y + (size_t)i * VEC, o); }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r[k] = zero ? 0.f : g[k] * act_bwd_from_out(o[k], act);
+    Io<T>::st4(gz + (size_t)i * VEC, r);
+    if (VEC == 8) Io<T>::st4(gz + (size_t)i * VEC + 4, r + 4);
+  }
+}
+
 // dst[row, c] = c < C ? (Tdst)src[row, c] : 0   -- channel zero-padding (+ fp32 -> bf16 cast) so that 3-channel
 // mesh coordinates can use the 16-byte-chunk tensor-core gather path
 template <typename TS, typename TD>
@@ -495,6 +514,20 @@ int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int r
   const unsigned long long n = rows * gz_channels;
   const int blocks = (int)((n + 255) / 256 < 16ULL * kNumSMs ? (n + 255) / 256 : 16ULL * kNumSMs);
   cudaStream_t st = (cudaStream_t)stream;
+  const int vec = dtype == SHB_BF16 ? 8 : 4;
+  if (gz_channels == Cout && Cout % vec == 0 && n / vec < (1ull << 32) && (dtype == SHB_F32 || dtype == SHB_BF16)) {
+    const unsigned chunks = (unsigned)(n / vec), cpr = (unsigned)(Cout / vec);
+    const int vb = (int)((chunks + 255) / 256 < 16u * kNumSMs ? (chunks + 255) / 256 : 16u * kNumSMs);
+    if (dtype == SHB_F32)
+      act_bwd_vec_kernel<float, 4><<<vb, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, chunks, cpr,
+                                                       (unsigned)rows_out, act, zero_last_row);
+    else
+      act_bwd_vec_kernel<__nv_bfloat16, 8><<<vb, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+                                                               (__nv_bfloat16*)gz, chunks, cpr, (unsigned)rows_out, act,
+                                                               zero_last_row);
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == SHB_F32)
     act_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, (unsigned)rows,
                                                   (unsigned)rows_out, Cout, gz_channels, act, zero_last_row);

@@ -685,13 +685,25 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParam
   }
 }
 
+// out[i] = sum over parts of ws[c*n + i], in a FIXED order: warp y of the block sums parts c = y, y+8, ... (coalesced
+// 128-byte rows of 32 consecutive outputs), then warp 0 adds the eight partials in ascending y.  Deterministic, and
+// parallel over the parts (the naive one-thread-per-output loop was latency-bound: 148 dependent-free but serial loads).
 __global__ void __launch_bounds__(256) uw_reduce_kernel(const float* __restrict__ ws, int parts, long long n,
                                                         float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ float red[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + x;
   float a = 0.f;
-  for (int c = 0; c < parts; ++c) a += ws[(size_t)c * n + i];
-  out[i] = a;
+  if (i < n)
+    for (int c = y; c < parts; c += 8) a += ws[(size_t)c * n + i];
+  red[y][x] = a;
+  __syncthreads();
+  if (y == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][x];
+    out[i] = s;
+  }
 }
 
 // column sums of gz (bias gradient): per-block partials in fixed order, then a fixed-order final pass
@@ -790,7 +802,7 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
 #undef UW_DISPATCH
   if (rc != 0) return rc;
   const long long n = (long long)Cout * p.K;
-  uw_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, grid, n, gw);
+  uw_reduce_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(p.ws, grid, n, gw);
   SHB_LAUNCH_CHECK();
   if (gb != nullptr) {
     float* part = (float*)workspace + (size_t)kNumSMs * Cout * p.K;
@@ -801,7 +813,7 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
     const long long rpb = (p.M + blocks - 1) / blocks;
     colsum_partial_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gz, p.M, Cout, CP, rpb, part);
     SHB_LAUNCH_CHECK();
-    uw_reduce_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(part, blocks, Cout, gb);
+    uw_reduce_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, blocks, Cout, gb);
     SHB_LAUNCH_CHECK();
   }
   return 0;
