@@ -59,9 +59,10 @@ int shb_build_inverse_spiral_csr(const int32_t* table, int rows_out, int S, int 
 int shb_build_inverse_spiral_by_slot(const int32_t* table, int rows_out, int S, int rows_in, int32_t* keyptr,
                                      int32_t* rows);
 
-/* Inline form of the (u,s)-keyed relation: pairs[u,s] = (first, second) output rows of the key, -1 = none,
- * second = -2 when the key holds three or more entries.  HOST keyptr/rows as produced above, HOST pairs (rows_in*S*2). */
-int shb_build_inverse_spiral_pairs(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, int32_t* pairs);
+/* Inline form of the (u,s)-keyed relation: quads[u,s,0..3] = the first four output rows of the key as uint16
+ * (0xFFFF = none).  A key with five or more entries stores three rows and 0xFFFE in the fourth position: entries 3..
+ * continue in the CSR.  Row ids must be <= 0xFFFD.  HOST keyptr/rows as produced above, HOST quads (rows_in*S*4). */
+int shb_build_inverse_spiral_quads(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, uint16_t* quads);
 
 /* Dense padded sampling matrix (main.py:183-193: D/U .todense(), +1 row/col, corner 1) -> CSR, dropping exact
  * zeros.  Call with colidx==NULL to count: *nnz_out receives the number of non-zeros.
@@ -113,12 +114,13 @@ int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz
 /* Input gradient: gx[b,u,:] = sum_{(j,s): table[j,s]==u} gz[b,j,:] . W[:, s*Cin:(s+1)*Cin], evaluated as a
  * gather-sum GEMM over the (u,s)-keyed inverse table -- no float atomics, fixed summation order.  Replaces
  * mm (dA = dZ.W) + index_put_(accumulate=True) of the autograd of models.py:42,45.
- *   pairs (rows_in, S, 2) int32 or NULL: the first two entries of every key inline (-1 = none; second == -2 = the key
- *   has three or more entries, continue in the CSR) -- lets the tensor-core path issue all loads of a tile without
- *   dependent index loads; built by shb_build_inverse_spiral_pairs().  NULL selects the CUDA-core path.
+ *   quads (rows_in, S, 4) uint16 or NULL: the first four entries of every key inline (see
+ *   shb_build_inverse_spiral_quads) -- lets the tensor-core path issue all loads of a tile without dependent index
+ *   loads (with two inline entries ~93 % of warp-stages still took the three-round-trip CSR path; with four, ~7 %).
+ *   NULL selects the CUDA-core path.
  *   dummy_row_grad: 0 -> gx[b, rows_in-1, :] = 0 (its producer masks it: every layer but the first decoder
  *   conv of the plain AE); 1 -> computed by a segmented fixed-order reduction. */
-int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const int32_t* pairs,
+int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const uint16_t* quads,
                              const void* w, void* gx,
                              int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dummy_row_grad,
                              int dtype, void* stream);

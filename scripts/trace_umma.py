@@ -10,6 +10,9 @@ dev = "cuda:0"; B = 256
 h = Hierarchy("2222")
 geom = shb.SpiralGeometry.from_spiral(h.spirals(dev)[lvl], dev)
 x = torch.randn(B, geom.rows_in, cin, device=dev).bfloat16()
+MODE = os.environ.get("MODE", "fwd")
+if MODE == "dgrad":
+    x.requires_grad_(True)
 w = torch.randn(cout, geom.S * cin, device=dev) / (geom.S * cin) ** 0.5
 b = torch.zeros(cout, device=dev)
 lib = ctypes.CDLL(_capi.LIB_PATH)
@@ -18,13 +21,15 @@ for _ in range(3): y = shb.spiral_conv(x, w, b, geom, "elu")
 tr = torch.zeros(3 * 4 * 512, dtype=torch.int64, device=dev)
 lib.shbdbg_set_trace(tr.data_ptr())
 y = shb.spiral_conv(x, w, b, geom, "elu")
+if MODE == "dgrad":
+    y.backward(torch.randn_like(y))   # the input-gradient kernel runs last and owns the trace buffer
 torch.cuda.synchronize()
 lib.shbdbg_set_trace(None)
 t = tr.cpu().numpy().reshape(3, 4, 512)
 t0 = t[t > 0].min()
 P, M, E = t[0], t[1], t[2]
 print("stage: prod[wait_begin wait_end issued] mma[wait_begin wait_end committed]  (cycles since start)")
-for i in list(range(0, 40)) + list(range(200, 216)):
+for i in list(range(0, 16)):
     if P[0, i] == 0: break
     print(f"{i:4d}  P {P[0,i]-t0:8d} {P[1,i]-t0:8d} {P[2,i]-t0:8d}   M {M[0,i]-t0:8d} {M[1,i]-t0:8d} {M[2,i]-t0:8d}")
 n = int((P[0] > 0).sum())

@@ -17,7 +17,7 @@ SIGNATURES = {
     "shb_error_string": (ctypes.c_char_p, [c_int]),
     "shb_build_inverse_spiral_csr": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "shb_build_inverse_spiral_by_slot": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
-    "shb_build_inverse_spiral_pairs": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+    "shb_build_inverse_spiral_quads": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "shb_csr_transpose": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 9 + [c_vp]),

@@ -58,13 +58,20 @@ int shb_build_inverse_spiral_by_slot(const int32_t* table, int rows_out, int S, 
   return 0;
 }
 
-int shb_build_inverse_spiral_pairs(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, int32_t* pairs) {
-  if (!keyptr || !rows || !pairs || rows_in <= 0 || S <= 0) return SHB_E_ARG;
+int shb_build_inverse_spiral_quads(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, uint16_t* quads) {
+  if (!keyptr || !rows || !quads || rows_in <= 0 || S <= 0) return SHB_E_ARG;
   const long long nkeys = (long long)rows_in * S;
   for (long long k = 0; k < nkeys; ++k) {
     const int e0 = keyptr[k], cnt = keyptr[k + 1] - e0;
-    pairs[2 * k] = cnt >= 1 ? rows[e0] : -1;
-    pairs[2 * k + 1] = cnt == 2 ? rows[e0 + 1] : (cnt > 2 ? -2 : -1);
+    for (int t = 0; t < 4; ++t) {
+      uint16_t v = 0xFFFF;  // none
+      if (t < cnt) {
+        if (rows[e0 + t] < 0 || rows[e0 + t] > 0xFFFD) return SHB_E_SHAPE;  // row ids must fit 16 bits
+        v = (uint16_t)rows[e0 + t];
+      }
+      quads[4 * k + t] = v;
+    }
+    if (cnt > 4) quads[4 * k + 3] = 0xFFFE;  // overflow: entries 3.. continue in the CSR
   }
   return 0;
 }

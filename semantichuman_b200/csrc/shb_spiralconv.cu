@@ -594,7 +594,7 @@ int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz
   return SHB_E_DTYPE;
 }
 
-int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const int32_t* pairs,
+int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const uint16_t* quads,
                              const void* w, void* gx,
                              int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dummy_row_grad,
                              int dtype, void* stream) {
@@ -609,8 +609,8 @@ int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_
   int rc;
   if (dtype == SHB_F32) rc = launch_gather_gemm<float, true>(p, st);
   else if (dtype == SHB_BF16) {
-    if (umma_enabled() && pairs != nullptr && umma_gather_gemm_supported(Cout, Cin, S))
-      rc = umma_gather_gemm(gz, pairs, keyptr, rows, w, nullptr, gx, B, rows_out, rows_in, S, Cout, Cin, SHB_ACT_IDENTITY, 0, 1,
+    if (umma_enabled() && quads != nullptr && umma_gather_gemm_supported(Cout, Cin, S))
+      rc = umma_gather_gemm(gz, (const int32_t*)quads, keyptr, rows, w, nullptr, gx, B, rows_out, rows_in, S, Cout, Cin, SHB_ACT_IDENTITY, 0, 1,
                             true, st);
     else
       rc = launch_gather_gemm<__nv_bfloat16, true>(p, st);

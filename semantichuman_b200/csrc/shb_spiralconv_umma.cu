@@ -48,8 +48,8 @@ constexpr int UG_IDX_PER_THREAD = 16;  // per-tile index block: 128 rows x (S or
 
 struct UGParams {
   const __nv_bfloat16* src;  // (B, rows_src, CS)
-  const int32_t* table;      // forward: (rows_dst, S) source rows.  dgrad: pairs (rows_dst, S, 2): first two source rows of
-                             //   key (u,s) inline; -1 = none; second == -2 = three or more entries -> CSR below
+  const int32_t* table;      // forward: (rows_dst, S) source rows.  dgrad: quads (rows_dst, S, 4 x uint16) viewed as 2 words per
+                             //   key: first four source rows inline; 0xFFFF = none; [3] == 0xFFFE = 5+ entries -> CSR below
   const int32_t* keyptr;     // dgrad: (rows_dst*S + 1) CSR of the (u,s)-keyed inverse relation (overflow path only)
   const int32_t* list;       // dgrad: concatenated source rows per key
   const __nv_bfloat16* w;    // nn.Linear weight (Cout, S*Cin), bf16
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
           UG_TRACE(1, 0, st);
           mbar_wait_backoff(&full_bar[slot], ph, 20);
           UG_TRACE(1, 1, st);
+          if (SUM) fence_proxy_async_smem();  // producers wrote this stage with generic st.shared (see the producer loop)
           tc_fence_after();
           if (!(p.dbg & 2)) {
             if (left >= UG_KC) {
@@ -259,44 +260,31 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
     constexpr int SPS = CS <= 64 ? UG_KC / CPS : 1;      // slots per stage (CS = 128: one slot spans two stages)
     const int sl0 = CS <= 64 ? kc / CPS : 0;             // slot of this chunk column within a stage
     const int c0 = CS <= 64 ? (kc % CPS) * 8 : kc * 8;   // channel offset (+64 on odd stages when CS = 128)
-    // index-block coordinates of the entries this thread prefetches (tile independent)
-    constexpr int IPT = UG_IDX_PER_THREAD / 2;           // 8 entries per thread: 128 x S over 256, or 128 x 2S over 512
-    int pre[IPT];
-    unsigned pre_r[IPT];
-#pragma unroll
-    for (int u = 0; u < IPT; ++u) {
-      const unsigned e = (unsigned)pt + u * NPT;
-      const unsigned r = e / (unsigned)SP;
-      pre_r[u] = (e < (unsigned)nidx) ? ((r << 8) | (e - r * (unsigned)SP)) : 0xffffffffu;  // row << 8 | slot
-    }
-    auto fetch_idx_block = [&](int tile) {  // global -> registers
+    // The tile's block of the index table goes global -> shared with 4-byte cp.async (no registers: a register-held
+    // prefetch array spilled under the register cap and serialised its loads); one commit group per block, waited for
+    // at the end of the previous tile.
+    const uint32_t idx_base = smem_u32(idx_s);
+    auto prefetch_idx_block = [&](int tile, int buf) {
       const bool live = tile < p.num_tiles;
       const unsigned m0 = (unsigned)tile * UG_BM;
       const unsigned j0 = live ? m0 % rows_dst : 0;
-#pragma unroll
-      for (int u = 0; u < IPT; ++u) {
-        pre[u] = 0;
-        if (live && pre_r[u] != 0xffffffffu) {
-          const unsigned r = pre_r[u] >> 8, sl = pre_r[u] & 0xff;
-          unsigned j = j0 + r;
-          if (j >= rows_dst) j = (rows_dst >= UG_BM) ? j - rows_dst : j % rows_dst;
-          if ((long long)(m0 + r) < p.M) pre[u] = __ldg(p.table + (size_t)j * SP + sl);
-        }
+      for (unsigned e = (unsigned)pt; e < (unsigned)nidx; e += NPT) {
+        const unsigned r = e / (unsigned)SP, sl = e - r * (unsigned)SP;
+        unsigned j = j0 + r;
+        if (j >= rows_dst) j = (rows_dst >= UG_BM) ? j - rows_dst : j % rows_dst;
+        const bool on = live && (long long)(m0 + r) < p.M;
+        cp_async4(idx_base + (uint32_t)(buf * nidx + (int)e) * 4, p.table + (on ? (size_t)j * SP + sl : 0), on ? 4u : 0u);
       }
+      cp_async_commit();
     };
-    auto store_idx_block = [&](int buf) {
-#pragma unroll
-      for (int u = 0; u < IPT; ++u)
-        if (pre_r[u] != 0xffffffffu) idx_s[buf * nidx + pt + u * NPT] = pre[u];
-    };
-    fetch_idx_block(blockIdx.x);
-    store_idx_block(0);
+    prefetch_idx_block(blockIdx.x, 0);
+    cp_async_wait_group<0>();
     asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
     uint32_t slot = 0, ph = 0;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int32_t* idx_cur = idx_s + (tcount & 1) * nidx;
-      fetch_idx_block(tile + gridDim.x);  // next tile's block: in flight during this tile's stages
+      prefetch_idx_block(tile + gridDim.x, (tcount + 1) & 1);  // next tile's block: in flight during this tile's stages
       const unsigned m0 = (unsigned)tile * UG_BM;
       const unsigned b0 = m0 / rows_dst, j0 = m0 - b0 * rows_dst;
       bool valid[NIT];
@@ -318,22 +306,25 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
         row_off[i] = (uint32_t)(r >> 3) * UG_SBO + (uint32_t)(r & 7) * 16 + (uint32_t)kc * UG_LBO;
       }
       int s = sl0;  // spiral slot of this thread's chunk column in the current stage
-      // gather-sum: raw (first, second) entries of every item, loaded one stage ahead of their use
-      uint4 va[NIT], vb[NIT];
-      int eflag[NIT];
+      // gather-sum: raw rows of the (up to four) inline entries of every item, loaded one stage ahead of their use
+      uint4 vq[NIT][4];
+      bool over[NIT];
       auto issue_sum_loads = [&](int sn, int coff) {
-        int ea[NIT], eb[NIT];
+        uint32_t w0[NIT], w1[NIT];
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
           const bool on = valid[i] && sn < p.S;
-          ea[i] = on ? idx_cur[irow[i] + 2 * sn] : -1;
-          eb[i] = on ? idx_cur[irow[i] + 2 * sn + 1] : -1;
+          w0[i] = on ? (uint32_t)idx_cur[irow[i] + 2 * sn] : 0xFFFFFFFFu;
+          w1[i] = on ? (uint32_t)idx_cur[irow[i] + 2 * sn + 1] : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
-          va[i] = ea[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)ea[i] * CS + coff)) : make_uint4(0, 0, 0, 0);
-          vb[i] = eb[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)eb[i] * CS + coff)) : make_uint4(0, 0, 0, 0);
-          eflag[i] = eb[i];
+          const uint32_t e[4] = {w0[i] & 0xFFFFu, w0[i] >> 16, w1[i] & 0xFFFFu, w1[i] >> 16};
+          over[i] = e[3] == 0xFFFEu;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            vq[i][t] = e[t] < 0xFFFEu ? __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)e[t] * CS + coff))
+                                      : make_uint4(0, 0, 0, 0);
         }
       };
       if (SUM) issue_sum_loads(s, 0);
@@ -353,20 +344,25 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
             for (int i = 0; i < NIT; ++i)
               cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, valid[i] ? 16u : 0u);
           } else {
-            // fixed summation order: first entry + second entry, then (rare: 3+ entries) the CSR tail, ascending
+            // fixed summation order: inline entries 0..3 ascending, then (rare: 5+ entries) the CSR tail from entry 3
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
               float acc[8];
-              const uint32_t wa[4] = {va[i].x, va[i].y, va[i].z, va[i].w}, wb[4] = {vb[i].x, vb[i].y, vb[i].z, vb[i].w};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                acc[2 * q] = __uint_as_float(wa[q] << 16) + __uint_as_float(wb[q] << 16);
-                acc[2 * q + 1] = __uint_as_float(wa[q] & 0xffff0000u) + __uint_as_float(wb[q] & 0xffff0000u);
+              for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const uint32_t wv[4] = {vq[i][t].x, vq[i][t].y, vq[i][t].z, vq[i][t].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  acc[2 * q] += __uint_as_float(wv[q] << 16);
+                  acc[2 * q + 1] += __uint_as_float(wv[q] & 0xffff0000u);
+                }
               }
-              if (eflag[i] == -2) {
+              if (over[i]) {
                 const int k = urow[i] * p.S + s;
                 const int e0 = __ldg(p.keyptr + k), e1 = __ldg(p.keyptr + k + 1);
-                for (int e = e0 + 1; e < e1; ++e) {
+                for (int e = e0 + 3; e < e1; ++e) {
                   float v[8];
                   Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)__ldg(p.list + e) * CS + coff, v);
 #pragma unroll
@@ -386,16 +382,18 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
         if (!SUM) {
           cp_async_mbar_arrive_noinc(&full_bar[slot]);  // one (counted) arrival when this thread's copies have landed
         } else {
-          // next stage's loads go out BEFORE this stage's fence/arrive so that their latency overlaps the hand-shake
+          // Next stage's loads go out before the hand-shake and STAY in flight across it: the generic->async proxy fence is
+          // executed by the CONSUMER (the MMA thread, after it acquires the full barrier), not here -- a producer-side
+          // fence.proxy.async is a MEMBAR that drains this thread's outstanding loads, i.e. one exposed L2 round trip per
+          // stage.  Ordering: st.shared -> __syncwarp -> arrive(release) -> try_wait(acquire) -> fence.proxy.async -> mma.
           if (st + 1 < p.NS) issue_sum_loads(s, (CS == 128 && ((st + 1) & 1)) ? 64 : 0);
-          fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[slot]);
         }
         if (++slot == nstage) { slot = 0; ph ^= 1; }
       }
-      // publish the next tile's index block; every producer is past its reads of that buffer (barrier of the previous tile)
-      store_idx_block((tcount + 1) & 1);
+      // the next tile's index block must have landed (its commit group is the only committed one), for every producer
+      cp_async_wait_group<0>();
       asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
     }
   }

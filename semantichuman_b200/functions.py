@@ -187,7 +187,7 @@ class SpiralConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             _call("spiralconv_bwd_dgrad" + tag, meta, lib.shb_spiralconv_bwd_dgrad, _p(gz), _p(geom.keyptr),
-                  _p(geom.inv_rows), _p(geom.inv_pairs), _p(w), _p(gx), B, rows_in, geom.rows_out, S, cin_p, cout_p,
+                  _p(geom.inv_rows), _p(geom.inv_quads), _p(w), _p(gx), B, rows_in, geom.rows_out, S, cin_p, cout_p,
                   int(geom.dummy_row_grad), dt, st)
             _count(2 if geom.dummy_row_grad else 1)
             if cin_p != cin:

@@ -55,13 +55,14 @@ def build_inverse_spiral_by_slot(table, rows_in):
     return keyptr, rows
 
 
-def build_inverse_spiral_pairs(keyptr, rows, rows_in, S):
-    """(rows_in, S, 2) host int32: first two entries of every (u,s) key inline; -1 none; second == -2 -> 3+ entries."""
+def build_inverse_spiral_quads(keyptr, rows, rows_in, S):
+    """(rows_in, S, 4) host uint16: first four entries of every (u,s) key inline; 0xFFFF none; [3] == 0xFFFE -> 5+ entries
+    (entries 3.. continue in the CSR)."""
     keyptr, rows = _i32(keyptr), _i32(rows)
-    pairs = np.empty((rows_in, S, 2), np.int32)
-    check(lib.shb_build_inverse_spiral_pairs(keyptr.ctypes.data, rows.ctypes.data, rows_in, S, pairs.ctypes.data),
-          "shb_build_inverse_spiral_pairs")
-    return pairs
+    quads = np.empty((rows_in, S, 4), np.uint16)
+    check(lib.shb_build_inverse_spiral_quads(keyptr.ctypes.data, rows.ctypes.data, rows_in, S, quads.ctypes.data),
+          "shb_build_inverse_spiral_quads")
+    return quads
 
 
 def dense_to_csr(dense):
@@ -112,7 +113,11 @@ class SpiralGeometry:
         self.table = torch.from_numpy(table).to(self.device)
         self.keyptr = torch.from_numpy(keyptr).to(self.device)
         self.inv_rows = torch.from_numpy(rows).to(self.device)
-        self.inv_pairs = torch.from_numpy(build_inverse_spiral_pairs(keyptr, rows, self.rows_in, self.S)).to(self.device)
+        # uint16 rows: viewed as int16 for torch; None (-> CUDA-core dgrad) when row ids do not fit
+        self.inv_quads = None
+        if self.rows_out <= 0xFFFD:
+            q = build_inverse_spiral_quads(keyptr, rows, self.rows_in, self.S)
+            self.inv_quads = torch.from_numpy(q.view(np.int16)).to(self.device)
 
     @classmethod
     def from_spiral(cls, spiral_adj, device, **kw):
