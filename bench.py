@@ -8,7 +8,9 @@
 
 One step = forward + L1 loss + backward (+ gradient all-reduce when N>1) + Adam (main.py:262 hyper-parameters) over
 one batch of synthetic meshes; weights are deterministic random-init; per-GPU batch 256 (weak scaling: N=8 is
-BASELINE.json's global batch 2048).  Prints ONE JSON line on rank 0.
+BASELINE.json's global batch 2048).  Prints ONE JSON line on rank 0.  The headline is north_star's bf16 mode (bf16
+operands, fp32 accumulation and master weights, parity 2e-2); the exact-fp32 mode (parity 1e-4) is timed in the same
+run and reported under "other_mode".
 """
 import argparse
 import json
@@ -25,6 +27,13 @@ FENC = [[3, 16, 32, 64, 128], [[], [], [], [], []]]  # configure/cfgs.py:11
 FDEC = [[128, 64, 32, 32, 16], [[], [], [], [], 3]]  # configure/cfgs.py:12
 NZ = 256  # traincfg.yaml:10
 METRIC = "train meshes/sec (6890-vert SpiralAE fwd+bwd)"
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can come out on top, from the
+# ncu --set full captures summarised under profiles/ (B=256, bf16).  key = the timer tag bench.py reports as roofline.kernel
+NCU_TRAFFIC_BYTES = {
+    "spiralconv_bwd_dgrad[6891>6891x14x32>16]": (57.39e6 + 67.35e6, "profiles/r01_e_ncu_fwd_and_dgrad.csv"),
+    "spiralconv_fwd[6891>6891x14x32>16]": (113.37e6 + 35.14e6, "profiles/r01_e_ncu_fwd_and_dgrad.csv"),
+    "spiralconv_bwd_wgrad[6891>6891x14x32>16]": (230.23e6 + 3.88e6, "profiles/r01_b_ncu_umma_first.csv"),
+}
 N_INPUT_BATCHES = 8  # distinct resident batches rotated through the timed loop
 
 
@@ -276,12 +285,36 @@ def run_own(args):
         achieved = top["bytes"] / top["launches"] / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"]}
-    roof.update({"traffic": None, "kernel": top_name, "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / ms,
+    traffic = NCU_TRAFFIC_BYTES.get(top_name) if args.dtype == "bf16" and B == 256 else None
+    roof.update({"traffic": None if traffic is None else traffic[0],
+                 "traffic_source": None if traffic is None else traffic[1], "kernel": top_name, "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / ms,
                  "peak_source": peaks["source"] + " (sustained figures: kernel timed inside a long step)",
                  "arith_intensity_flop_per_byte": ai})
     kernels = sorted(((k, v["ms"] / args.steps) for k, v in per.items()), key=lambda kv: -kv[1])
     step_flops = sum(v["flops"] for v in per.values()) / args.steps
     step_bytes = sum(v["bytes"] for v in per.values()) / args.steps
+
+    # the other precision mode, a few steps, same process (reported beside the headline; not the headline)
+    other = None
+    if world == 1 and not args.no_other_mode:
+        odt = torch.float32 if dtype == torch.bfloat16 else torch.bfloat16
+        model.set_compute_dtype(odt)
+        for i in range(3):
+            step(resident[i % N_INPUT_BATCHES])
+        torch.cuda.synchronize()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_other = 10
+        o0.record()
+        for i in range(n_other):
+            step(resident[i % N_INPUT_BATCHES])
+        o1.record()
+        torch.cuda.synchronize()
+        oms = o0.elapsed_time(o1) / n_other
+        other = {"dtype": "f32" if odt == torch.float32 else "bf16", "ms_per_step": oms, "value": B / (oms * 1e-3),
+                 "unit": "meshes/s", "steps": n_other,
+                 "note": "exact-fp32 CUDA-core kernels, 1e-4 parity mode" if odt == torch.float32 else
+                         "bf16 tcgen05 kernels, 2e-2 parity mode"}
+        model.set_compute_dtype(dtype)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -299,7 +332,7 @@ def run_own(args):
                     "h2d_bytes_per_step": host[0].numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "loss": last_loss, "loss_e2e_mean": seen / args.steps,
+            "other_mode": other, "loss": last_loss, "loss_e2e_mean": seen / args.steps,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in kernels[:12]},
             "algorithmic_per_step": {"gflop_convs_pools": step_flops / 1e9, "gbytes": step_bytes / 1e9}}
     print(json.dumps(line), flush=True)
@@ -313,7 +346,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="shb200", choices=["shb200", "reference"])
-    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16 (default): bf16 operands / fp32 accumulate on the tcgen05 kernels, north_star's 2e-2 mode; "
+                         "fp32: exact-fp32 CUDA-core kernels, the 1e-4 mode")
+    ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

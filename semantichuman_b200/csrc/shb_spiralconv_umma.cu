@@ -411,8 +411,8 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
 static long long* g_trace = nullptr;
 void umma_set_trace(long long* buf) { g_trace = buf; }
 
-static size_t ug_smem_bytes(int NPAD, int Q, int nstage, int S) {
-  return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES + (size_t)2 * UG_BM * (2 * S) * 4;
+static size_t ug_smem_bytes(int NPAD, int Q, int nstage, int S, bool sum = true) {
+  return ((size_t)NPAD * Q * 16 + 127) / 128 * 128 + (size_t)nstage * UG_STAGE_BYTES + (size_t)2 * UG_BM * ((sum ? 2 : 1) * S) * 4;
 }
 constexpr size_t UG_SMEM_MAX = 227 * 1024 - 2048;  // leave room for the static smem (barriers, bias)
 
@@ -477,15 +477,16 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* keypt
     p.trace = g_trace;
   }
   int nstage = 6;
-  while (nstage > UG_LAG + 1 && ug_smem_bytes(p.NPAD, p.Q, nstage, S) > UG_SMEM_MAX) --nstage;
+  while (nstage > UG_LAG + 1 && ug_smem_bytes(p.NPAD, p.Q, nstage, S, sum_mode) > UG_SMEM_MAX) --nstage;
   // two CTAs per SM when both fit with a deep enough ring: more gathers in flight
   int ctas_per_sm = 1;
-  if (!sum_mode && ug_smem_bytes(p.NPAD, p.Q, 4, S) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }
+  if (!sum_mode && ug_smem_bytes(p.NPAD, p.Q, 4, S, false) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }
+  else if (!sum_mode && ug_smem_bytes(p.NPAD, p.Q, 3, S, false) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 3; }
   p.nstage = nstage;
   uint32_t cols = 32;
   while (cols < 2u * p.NPAD) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = ug_smem_bytes(p.NPAD, p.Q, nstage, S);
+  const size_t smem = ug_smem_bytes(p.NPAD, p.Q, nstage, S, sum_mode);
 #define UG_DISPATCH(CSV)                                                                   \
   case CSV:                                                                                \
     return sum_mode ? ug_launch<CSV, true>(p, smem, ctas_per_sm, st) : ug_launch<CSV, false>(p, smem, ctas_per_sm, st);
