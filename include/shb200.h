@@ -82,10 +82,12 @@ int shb_csr_transpose(const int32_t* rowptr, const int32_t* colidx, const float*
  * + mask (:49-51) with one fused gather-GEMM.
  *   x (B, rows_in, Cin); w (Cout, S*Cin) -- nn.Linear's own layout, k = s*Cin + c, stored as `dtype`;
  *   bias (Cout) ALWAYS fp32, or NULL;  y (B, rows_out, Cout).
- *   rows_out may be smaller than rows_in (conv fused with a selection down-pool). */
+ *   rows_out may be smaller than rows_in (conv fused with a selection down-pool).
+ *   src_dummy_zero != 0 is a promise that x[b, rows_in-1, :] == 0 (the producer masked it, models.py:51): gathers of the
+ *   dummy row (13-22 % of all slots) are then zero-filled without touching memory.  0 is always correct. */
 int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const void* bias, void* y, int B,
-                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row, int dtype,
-                       void* stream);
+                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row,
+                       int src_dummy_zero, int dtype, void* stream);
 
 /* gz = gy * act'(.) expressed through the saved OUTPUT y, zero on the dummy row when zero_last_row
  * (ELU' = y+1 for y<=0 etc.).  Replaces EluBackward/MulBackward of models.py:46,51.
@@ -109,7 +111,7 @@ int shb_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cp, in
 size_t shb_spiralconv_wgrad_workspace(int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dtype);
 int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz, void* gw, void* gb,
                              void* workspace, size_t workspace_bytes, int B, int rows_in, int rows_out, int S,
-                             int Cin, int Cout, int dtype, void* stream);
+                             int Cin, int Cout, int src_dummy_zero, int dtype, void* stream);
 
 /* Input gradient: gx[b,u,:] = sum_{(j,s): table[j,s]==u} gz[b,j,:] . W[:, s*Cin:(s+1)*Cin], evaluated as a
  * gather-sum GEMM over the (u,s)-keyed inverse table -- no float atomics, fixed summation order.  Replaces

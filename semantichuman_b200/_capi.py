@@ -20,11 +20,11 @@ SIGNATURES = {
     "shb_build_inverse_spiral_quads": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "shb_csr_transpose": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
-    "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 9 + [c_vp]),
+    "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
     "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
     "shb_pad_channels": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "shb_spiralconv_wgrad_workspace": (c_size, [c_int] * 7),
-    "shb_spiralconv_bwd_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size] + [c_int] * 7 + [c_vp]),
+    "shb_spiralconv_bwd_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size] + [c_int] * 8 + [c_vp]),
     "shb_spiralconv_bwd_dgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),
     "shb_pool_spmm": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 5 + [c_vp]),
     "shb_l1_loss_workspace": (c_size, [c_i64]),

@@ -16,7 +16,7 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* keypt
 bool umma_wgrad_supported(int Cin, int Cout, int S);
 size_t umma_wgrad_workspace(int B, int rows_out, int S, int Cin, int Cout);
 int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, float* gb, void* workspace, int B,
-               int rows_in, int rows_out, int S, int Cin, int Cout, cudaStream_t st);
+               int rows_in, int rows_out, int S, int Cin, int Cout, int src_dummy_zero, cudaStream_t st);
 
 // debug: device buffer of 3*4*512 int64 receiving CTA 0's per-stage clock64 stamps (null = off)
 void umma_set_trace(long long* buf);

@@ -484,8 +484,8 @@ extern "C" {
 void shbdbg_set_trace(void* buf) { umma_set_trace((long long*)buf); }
 
 int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const void* bias, void* y, int B,
-                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row, int dtype,
-                       void* stream) {
+                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row,
+                       int src_dummy_zero, int dtype, void* stream) {
   if (!x || !table || !w || !y) return SHB_E_ARG;
   if (B <= 0 || rows_in <= 0 || rows_out <= 0 || S <= 0 || Cin <= 0 || Cout <= 0) return SHB_E_ARG;
   if (act < SHB_ACT_IDENTITY || act > SHB_ACT_TANH) return SHB_E_ARG;
@@ -499,7 +499,7 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
   if (dtype == SHB_BF16) {
     if (umma_enabled() && umma_gather_gemm_supported(Cin, Cout, S))  // tensor-core path (tcgen05 + TMEM)
       return umma_gather_gemm(x, table, nullptr, nullptr, w, (const float*)bias, y, B, rows_in, rows_out, S, Cin, Cout, act,
-                              zero_last_row, 0, false, st);
+                              zero_last_row, src_dummy_zero, false, st);
     return launch_gather_gemm<__nv_bfloat16, false>(p, st);
   }
   return SHB_E_DTYPE;
@@ -573,13 +573,13 @@ size_t shb_spiralconv_wgrad_workspace(int B, int rows_in, int rows_out, int S, i
 
 int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz, void* gw, void* gb,
                              void* workspace, size_t workspace_bytes, int B, int rows_in, int rows_out, int S,
-                             int Cin, int Cout, int dtype, void* stream) {
+                             int Cin, int Cout, int src_dummy_zero, int dtype, void* stream) {
   if (!x || !table || !gz || !gw || !workspace) return SHB_E_ARG;
   if (B <= 0 || rows_in <= 0 || rows_out <= 0 || S <= 0 || Cin <= 0 || Cout <= 0) return SHB_E_ARG;
   if (workspace_bytes < shb_spiralconv_wgrad_workspace(B, rows_in, rows_out, S, Cin, Cout, dtype)) return SHB_E_WORKSPACE;
   if (dtype == SHB_BF16 && umma_enabled() && umma_wgrad_supported(Cin, Cout, S))
     return umma_wgrad(x, table, gz, (float*)gw, (float*)gb, workspace, B, rows_in, rows_out, S, Cin, Cout,
-                      (cudaStream_t)stream);
+                      src_dummy_zero, (cudaStream_t)stream);
   const WGConfig c = wgrad_config(Cin, Cout);
   const int tiles = ceil_div(Cout, c.ba) * ceil_div(Cin, c.bb);
   WGParams p{};

@@ -61,7 +61,8 @@ struct UGParams {
   int NS;       // stages per tile = ceil(Q / UG_KC)
   int nstage;   // depth of the A ring
   int num_tiles;
-  int act, zero_last, skip_last;
+  int act, zero_last;
+  int skip_last;  // gather-sum: destination dummy row not computed.  forward: source dummy row is known zero (zero-fill)
   long long* trace;  // debug timeline (CTA 0): [role 0..2][event 0..3][512] clock64 stamps, or null
   int dbg;      // SHB_UMMA_DEBUG bitmask (perf bisection only): 1 skip copies, 2 skip MMAs, 4 skip epilogue stores
   int noinc;    // 1: per-thread cp.async.mbarrier.arrive.noinc (no fence); 0: wait_group + proxy fence + per-warp arrive
@@ -340,9 +341,10 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
             int row[NIT];
 #pragma unroll
             for (int i = 0; i < NIT; ++i) row[i] = idx_cur[irow[i] + s];
+            const int zrow = p.skip_last ? p.rows_src - 1 : -1;  // known-zero source row: no memory access, zero-fill
 #pragma unroll
             for (int i = 0; i < NIT; ++i)
-              cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, valid[i] ? 16u : 0u);
+              cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, (valid[i] && row[i] != zrow) ? 16u : 0u);
           } else {
             // fixed summation order: inline entries 0..3 ascending, then (rare: 5+ entries) the CSR tail from entry 3
 #pragma unroll
@@ -520,6 +522,7 @@ struct UWParams {
   float* ws;                // [grid][Cout*K] fp32 partials
   long long M, rows_per_cta;
   int rows_in, rows_out, S, Cout, NPAD, K, Q, KT, NQ;  // Q = K/8 chunks per x row set, NQ = NPAD/8
+  int src_dummy_zero;  // x[b, rows_in-1, :] is known zero: zero-fill instead of gathering it
   int nstage;
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
 };
@@ -636,6 +639,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParam
       }
     };
     fetch_stage_idx(0, rowc, validc, mc, xbc);
+    const int zrow = p.src_dummy_zero ? p.rows_in - 1 : -1;
     for (int st = 0; st < nst; ++st) {
       const uint32_t slot = st % p.nstage, ph = (st / p.nstage) & 1;
       int rown[NI];
@@ -649,7 +653,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParam
       for (int u = 0; u < NI; ++u) {
         const int q = ql + u * QL;
         if (q < p.Q)
-          cp_async16(a_dst + (uint32_t)q * SBO, xbc + (size_t)rowc[u] * CIN + (q * 8) % CIN, validc ? 16u : 0u);
+          cp_async16(a_dst + (uint32_t)q * SBO, xbc + (size_t)rowc[u] * CIN + (q * 8) % CIN,
+                     (validc && rowc[u] != zrow) ? 16u : 0u);
       }
       const uint32_t b_dst = a_dst + p.a_stage_bytes;
       for (int q = ql; q < p.NQ; q += QL) {
@@ -772,7 +777,7 @@ template <int CIN, int BKM> static int uw_launch(const UWParams& p, int grid, si
 }
 
 int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, float* gb, void* workspace, int B,
-               int rows_in, int rows_out, int S, int Cin, int Cout, cudaStream_t st) {
+               int rows_in, int rows_out, int S, int Cin, int Cout, int src_dummy_zero, cudaStream_t st) {
   const UWPlan pl = uw_plan(Cin, Cout, S);
   if (!pl.ok) return SHB_E_SHAPE;
   UWParams p{};
@@ -786,6 +791,7 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
   p.KT = pl.KT; p.NQ = pl.NPAD / 8; p.nstage = pl.nstage;
   p.a_stage_bytes = (uint32_t)pl.KT * 16 * (pl.bkm * 16 + 16); p.b_stage_bytes = (uint32_t)(pl.NPAD / 8) * (pl.bkm * 16 + 16);
   p.tmem_cols = pl.cols;
+  p.src_dummy_zero = src_dummy_zero;
   int rc;
 #define UW_DISPATCH(C)                                                                                          \
   case C:                                                                                                       \

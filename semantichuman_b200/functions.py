@@ -142,7 +142,7 @@ class SpiralConvFn(torch.autograd.Function):
         meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, xk.element_size())
         _call(f"spiralconv_fwd[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]", meta, lib.shb_spiralconv_fwd, _p(xk),
               _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, S, cin_p, cout, act,
-              int(geom.zero_last_row), _dt(xk), _stream())
+              int(geom.zero_last_row), int(geom.src_dummy_zero), _dt(xk), _stream())
         _count()
         ctx.save_for_backward(xk, w, y)
         ctx.geom, ctx.act, ctx.has_bias = geom, act, bias is not None
@@ -177,7 +177,7 @@ class SpiralConvFn(torch.autograd.Function):
             gw = torch.empty((cout_p, S * cin_p), dtype=torch.float32, device=x.device)
             gb = torch.empty((cout_p,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
             _call("spiralconv_bwd_wgrad" + tag, meta, lib.shb_spiralconv_bwd_wgrad, _p(x), _p(geom.table), _p(gz), _p(gw),
-                  _p(gb), _p(ws), nbytes, B, rows_in, geom.rows_out, S, cin_p, cout_p, dt, st)
+                  _p(gb), _p(ws), nbytes, B, rows_in, geom.rows_out, S, cin_p, cout_p, int(geom.src_dummy_zero), dt, st)
             _count(2)
             if cout_p != cout or cin_p != cin:
                 gw = gw.view(cout_p, S, cin_p)[:cout, :, :cin].reshape(cout, S * cin)

@@ -101,12 +101,14 @@ class SpiralGeometry:
     rows_out < rows_in when the conv is fused with a selection down-pool (output rows = kept vertices + dummy).
     """
 
-    def __init__(self, table, rows_in, device, zero_last_row=True, dummy_row_grad=True):
+    def __init__(self, table, rows_in, device, zero_last_row=True, dummy_row_grad=True, src_dummy_zero=False):
         table = _i32(table)
         self.rows_out, self.S = int(table.shape[0]), int(table.shape[1])
         self.rows_in = int(rows_in)
         self.zero_last_row = bool(zero_last_row)
         self.dummy_row_grad = bool(dummy_row_grad)
+        # promise that the input's dummy row is all zeros (its producer masked it): its gathers are zero-filled
+        self.src_dummy_zero = bool(src_dummy_zero)
         self.table_host = table
         keyptr, rows = build_inverse_spiral_by_slot(table, self.rows_in)
         self.device = torch.device(device)

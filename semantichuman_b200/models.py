@@ -146,11 +146,15 @@ class _SpiralTrunk(nn.Module):
         self._enc_plan = []
         for j, lvl in enumerate(self._enc_lvl):
             last_at_level = (j + 1 == len(self._enc_lvl)) or (self._enc_lvl[j + 1] != lvl)
+            # conv 0 reads the caller's tensor (its dummy row is zero only by the dataset's convention); every later
+            # encoder conv reads a masked conv output, possibly through a pool that maps dummy -> dummy
+            geoms[lvl] = geoms[lvl].with_flags(src_dummy_zero=(j > 0))
             if not last_at_level:
                 self._enc_plan.append((j, geoms[lvl], None))
             elif fuse_pool and self._pD[lvl].is_selection and self._pD[lvl].selection_cols[-1] == geoms[lvl].rows_in - 1:
                 # D is a row selection: evaluate the conv only at the kept vertices (+ dummy)
-                self._enc_plan.append((j, geoms[lvl].restricted(self._pD[lvl].selection_cols, dummy_row_grad=False), None))
+                self._enc_plan.append((j, geoms[lvl].restricted(self._pD[lvl].selection_cols, dummy_row_grad=False,
+                                                                src_dummy_zero=(j > 0)), None))
             else:
                 self._enc_plan.append((j, geoms[lvl], self._pD[lvl]))
         # decoder plan: (conv index, geometry, pool-before or None); only the very first decoder conv can see a live
@@ -158,7 +162,9 @@ class _SpiralTrunk(nn.Module):
         self._dec_plan = []
         for j, lvl in enumerate(self._dec_lvl):
             first_at_level = (j == 0) or (self._dec_lvl[j - 1] != lvl)
-            g = geoms[lvl].with_flags(dummy_row_grad=True) if j == 0 else geoms[lvl]
+            # decoder conv 0 sees the live FC row; all later decoder convs read masked outputs (through U: dummy -> dummy)
+            g = geoms[lvl].with_flags(dummy_row_grad=True, src_dummy_zero=False) if j == 0 else \
+                geoms[lvl].with_flags(src_dummy_zero=True)
             self._dec_plan.append((j, g, self._pU[lvl] if first_at_level else None))
         self.compute_dtype = torch.float32
 

@@ -34,7 +34,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_argument_errors_are_reported_not_crashed():
     # null pointers are rejected before any launch (no GPU needed)
-    assert _capi.lib.shb_spiralconv_fwd(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 0, 1, 0, None) == -1
+    assert _capi.lib.shb_spiralconv_fwd(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, None) == -1
     assert _capi.lib.shb_pool_spmm(None, None, None, None, None, 1, 1, 1, 1, 0, None) == -1
     with pytest.raises(RuntimeError):
         _capi.check(-3, "x")
