@@ -136,3 +136,25 @@ def test_parameter_order_matches_reference_state_dict():
         assert groups[0] == "conv" and groups[-1] == "dconv", groups
         inner = [p for p in pos if p is not None]
         assert inner == sorted(inner), groups
+
+
+def test_inverse_quads_table():
+    """quads[u,s,0..3]: first four entries of key (u,s) inline as uint16, 0xFFFF none, [3]==0xFFFE -> 5+ entries."""
+    h = Hierarchy("2222")
+    t = indexing.normalise_spiral(h.spirals()[0])
+    n, S = t.shape
+    kp, rows = indexing.build_inverse_spiral_by_slot(t, n)
+    q = indexing.build_inverse_spiral_quads(kp, rows, n, S)
+    assert q.shape == (n, S, 4) and q.dtype == np.uint16
+    cnt = np.diff(kp).reshape(n, S)
+    for (u, s) in [(0, 0), (17, 1), (n - 2, 3), (414, 0), (n - 1, 2)]:
+        e0, c = kp[u * S + s], cnt[u, s]
+        want = [rows[e0 + i] if i < c else 0xFFFF for i in range(4)]
+        if c > 4:
+            want[3] = 0xFFFE
+        assert q[u, s].tolist() == want
+    # vectorised check of the whole table
+    first = np.where(cnt > 0, rows[np.minimum(kp[:-1], len(rows) - 1)].reshape(n, S), 0xFFFF)
+    assert (q[..., 0] == first).all()
+    assert ((q[..., 3] == 0xFFFE) == (cnt > 4)).all()
+    assert ((q[..., 1] == 0xFFFF) == (cnt < 2)).all()
