@@ -103,6 +103,7 @@ def base_config(args, world):
                         "N=8 is configs[3]'s global batch 2048)",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "params": 28559811, "optimizer": "Adam(lr=1e-3, wd=5e-5)", "parallelism": f"dp{world}",
+            "cuda_graph": bool(world == 1 and not getattr(args, "no_graph", False)),
             "cache": f"{N_INPUT_BATCHES} distinct input batches rotated; per-step working set (activations + 114 MB "
                      "weights + Adam state) exceeds the 126 MB L2"}
 
@@ -201,7 +202,8 @@ def run_own(args):
                                   spirals=h.spirals(dev), D=Dsp, U=Usp, device=dev)
     fill_deterministic_(model, seed=2)
     model = model.to(dev).set_compute_dtype(dtype)
-    step = TrainStep(model)
+    use_graph = world == 1 and not args.no_graph  # whole step replayed as one CUDA graph (single process only)
+    step = TrainStep(model, graph=use_graph)
     B = args.batch
     host = [synthetic_meshes(h.verts0, B, seed=1000 * rank + i).pin_memory() for i in range(N_INPUT_BATCHES)]
     resident = [x.to(dev) for x in host]
@@ -221,6 +223,10 @@ def run_own(args):
 
     for i in range(args.warmup):
         step(resident[i % N_INPUT_BATCHES])
+    if use_graph:
+        step.capture(resident[0])
+        for i in range(2):
+            step(resident[i % N_INPUT_BATCHES])
     barrier()
 
     # ---- timed region 1: inputs resident in HBM (the headline `value`; nothing but the step inside)
@@ -312,13 +318,13 @@ def run_own(args):
         odt = torch.float32 if dtype == torch.bfloat16 else torch.bfloat16
         model.set_compute_dtype(odt)
         for i in range(3):
-            step(resident[i % N_INPUT_BATCHES])
+            step._eager(resident[i % N_INPUT_BATCHES])
         torch.cuda.synchronize()
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_other = 10
         o0.record()
         for i in range(n_other):
-            step(resident[i % N_INPUT_BATCHES])
+            step._eager(resident[i % N_INPUT_BATCHES])
         o1.record()
         torch.cuda.synchronize()
         oms = o0.elapsed_time(o1) / n_other
@@ -362,6 +368,7 @@ def main():
                     help="bf16 (default): bf16 operands / fp32 accumulate on the tcgen05 kernels, north_star's 2e-2 mode; "
                          "fp32: exact-fp32 CUDA-core kernels, the 1e-4 mode")
     ap.add_argument("--no-other-mode", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph (N=1 only uses it)")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -93,9 +93,14 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
  * (ELU' = y+1 for y<=0 etc.).  Replaces EluBackward/MulBackward of models.py:46,51.
  *   gy, y (B, rows_out, Cout);  gz (B, rows_out, gz_channels), gz_channels >= Cout, extra channels zero-filled
  *   (the host pads 3-channel gradients to 16 so that they can take the tensor-core path).
- *   In place (gz==gy) is allowed when gz_channels == Cout. */
+ *   In place (gz==gy) is allowed when gz_channels == Cout.
+ *   gb (Cout) fp32 or NULL: the bias gradient sum_{b,j} gz[b,j,:] (the column sums AddmmBackward produces for
+ *   models.py:45), accumulated in the same pass (fixed-order two-stage reduction); needs `workspace` of
+ *   shb_spiralconv_bwd_act_workspace(gz_channels) bytes. */
+size_t shb_spiralconv_bwd_act_workspace(int gz_channels);
 int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int gz_channels,
-                           int act, int zero_last_row, int dtype, void* stream);
+                           int act, int zero_last_row, void* gb, void* workspace, size_t workspace_bytes, int dtype,
+                           void* stream);
 
 /* dst[r, c] = c < C ? src[r, c] : 0, converting between fp32 and bf16 on the way: channel zero-padding of
  * narrow activations (the 3-channel mesh coordinates of models.py:157) to a 16-byte-chunk multiple.

@@ -21,7 +21,8 @@ SIGNATURES = {
     "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "shb_csr_transpose": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
-    "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
+    "shb_spiralconv_bwd_act_workspace": (c_size, [c_int]),
+    "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_size, c_int, c_vp]),
     "shb_pad_channels": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "shb_spiralconv_wgrad_workspace": (c_size, [c_int] * 7),
     "shb_spiralconv_bwd_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size] + [c_int] * 8 + [c_vp]),

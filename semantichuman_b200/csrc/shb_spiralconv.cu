@@ -228,11 +228,17 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ gy, 
 }
 
 // 16-byte vectorised variant for the un-padded case (C % VEC == 0): one thread per VEC-wide channel chunk, 32-bit math
+// When `colpart` is given (chunks_per_row divides 256, so a thread always sees the same channel chunk) the kernel also
+// accumulates the per-channel sums of gz -- the bias gradient -- and writes one fixed-order partial per block.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) act_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gz,
                                                           unsigned chunks, unsigned chunks_per_row, unsigned rows_out, int act,
-                                                          int zero_last) {
+                                                          int zero_last, float* __restrict__ colpart) {
+  __shared__ float red[256][VEC + 1];
   const unsigned stride = gridDim.x * blockDim.x;
+  float csum[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) csum[k] = 0.f;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += stride) {
     const unsigned row = i / chunks_per_row;
     const bool zero = zero_last && (row % rows_out) == rows_out - 1;
@@ -240,9 +246,61 @@ __global__ void __launch_bounds__(256) act_bwd_vec_kernel(const T* __restrict__ 
     if (VEC == 8) { Io<T>::ld8(gy + (size_t)i * VEC, g); Io<T>::ld8(y + (size_t)i * VEC, o); }
     else { Io<T>::ld4(gy + (size_t)i * VEC, g); Io<T>::ld4(y + (size_t)i * VEC, o); }
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r[k] = zero ? 0.f : g[k] * act_bwd_from_out(o[k], act);
+    for (int k = 0; k < VEC; ++k) {
+      r[k] = zero ? 0.f : g[k] * act_bwd_from_out(o[k], act);
+      csum[k] += r[k];
+    }
     Io<T>::st4(gz + (size_t)i * VEC, r);
     if (VEC == 8) Io<T>::st4(gz + (size_t)i * VEC + 4, r + 4);
+  }
+  if (colpart != nullptr) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) red[threadIdx.x][k] = csum[k];
+    __syncthreads();
+    const unsigned C = chunks_per_row * VEC;
+    if (threadIdx.x < C) {  // column c: threads j*cpr + c/VEC (ascending j) hold its partial sums
+      const unsigned cc = threadIdx.x / VEC, k = threadIdx.x % VEC;
+      float s = 0.f;
+      for (unsigned j = cc; j < 256; j += chunks_per_row) s += red[j][k];
+      colpart[(size_t)blockIdx.x * C + threadIdx.x] = s;
+    }
+  }
+}
+
+// generic column sums of a (rows, C) tensor in fp32: per-block partials (fixed order), used when the fused path is off
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_generic(const T* __restrict__ g, unsigned long long rows, int C, int CP,
+                                                              unsigned long long rows_per_block, float* __restrict__ part) {
+  __shared__ float red[256];
+  const int tx = threadIdx.x % CP, ty = threadIdx.x / CP, ny = 256 / CP;
+  const unsigned long long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float a = 0.f;
+  if (tx < C)
+    for (unsigned long long r = r0 + ty; r < r1; r += ny) a += Io<T>::ld(g + r * C + tx);
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (ty == 0 && tx < C) {
+    float s = 0.f;
+    for (int q = 0; q < ny; ++q) s += red[q * CP + tx];
+    part[(size_t)blockIdx.x * C + tx] = s;
+  }
+}
+
+// out[i] = sum_c part[c*n + i]: eight part-lanes per output, combined in ascending order (deterministic)
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ ws, int parts, int n, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int x = threadIdx.x & 31, yy = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + x;
+  float a = 0.f;
+  if (i < n)
+    for (int c = yy; c < parts; c += 8) a += ws[(size_t)c * n + i];
+  red[yy][x] = a;
+  __syncthreads();
+  if (yy == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][x];
+    out[i] = s;
   }
 }
 
@@ -396,10 +454,10 @@ static int wgrad_splits(long long M, int S, int tiles) {
 
 struct WGConfig { int ba, bb; };
 static WGConfig wgrad_config(int Cin, int Cout) {
-  const int mn = Cin < Cout ? Cin : Cout;
-  if (mn > 32) return {64, 64};
-  if (mn > 16) return {32, 32};
-  return {16, 16};
+  // output tile BA (Cout) x BB (Cin), each dimension 16 / 32 / 64 by the layer's own size: a thread then owns a
+  // (BA/16) x (BB/16) micro-tile instead of the 1 x 1 the old square 16 x 16 tile gave narrow layers
+  auto pick = [](int c) { return c > 32 ? 64 : (c > 16 ? 32 : 16); };
+  return {pick(Cout), pick(Cin)};
 }
 
 // ------------------------------------------------------------------------------------------------ dummy-row dgrad
@@ -456,9 +514,19 @@ static int wgrad_launch(const WGParams& p0, int splits, void* gw, void* gb, cuda
   const int tiles_a = ceil_div(p.Cout, c.ba);
   p.tiles_b = ceil_div(p.Cin, c.bb);
   dim3 grid((unsigned)splits, (unsigned)p.S, (unsigned)(tiles_a * p.tiles_b));
-  if (c.ba == 64) wgrad_kernel<T, 64, 64, 4, 4><<<grid, WG_NT, 0, st>>>(p);
-  else if (c.ba == 32) wgrad_kernel<T, 32, 32, 2, 2><<<grid, WG_NT, 0, st>>>(p);
-  else wgrad_kernel<T, 16, 16, 1, 1><<<grid, WG_NT, 0, st>>>(p);
+#define SHB_WG(A, B_) wgrad_kernel<T, A, B_, A / 16, B_ / 16><<<grid, WG_NT, 0, st>>>(p)
+  switch (c.ba * 100 + c.bb) {
+    case 6464: SHB_WG(64, 64); break;
+    case 6432: SHB_WG(64, 32); break;
+    case 6416: SHB_WG(64, 16); break;
+    case 3264: SHB_WG(32, 64); break;
+    case 3232: SHB_WG(32, 32); break;
+    case 3216: SHB_WG(32, 16); break;
+    case 1664: SHB_WG(16, 64); break;
+    case 1632: SHB_WG(16, 32); break;
+    default: SHB_WG(16, 16); break;
+  }
+#undef SHB_WG
   SHB_LAUNCH_CHECK();
   const long long n_w = (long long)p.Cout * p.K, per = n_w + p.Cout;
   wgrad_reduce_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(p.ws, splits, per, n_w, (float*)gw, (float*)gb);
@@ -505,40 +573,73 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
   return SHB_E_DTYPE;
 }
 
+constexpr int ACT_MAX_BLOCKS = 16 * kNumSMs;
+
+size_t shb_spiralconv_bwd_act_workspace(int gz_channels) {
+  return ((size_t)ACT_MAX_BLOCKS + 1) * (size_t)(gz_channels > 0 ? gz_channels : 0) * sizeof(float);
+}
+
 int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int gz_channels,
-                           int act, int zero_last_row, int dtype, void* stream) {
+                           int act, int zero_last_row, void* gb, void* workspace, size_t workspace_bytes, int dtype,
+                           void* stream) {
   if (!gy || !y || !gz || B <= 0 || rows_out <= 0 || Cout <= 0 || gz_channels < Cout) return SHB_E_ARG;
   if (act < SHB_ACT_IDENTITY || act > SHB_ACT_TANH) return SHB_E_ARG;
+  if (dtype != SHB_F32 && dtype != SHB_BF16) return SHB_E_DTYPE;
+  if (gb != nullptr && (workspace == nullptr || workspace_bytes < shb_spiralconv_bwd_act_workspace(gz_channels)))
+    return SHB_E_WORKSPACE;
   const unsigned long long rows = (unsigned long long)B * rows_out;
   if (rows >= (1ull << 32)) return SHB_E_SHAPE;
   const unsigned long long n = rows * gz_channels;
-  const int blocks = (int)((n + 255) / 256 < 16ULL * kNumSMs ? (n + 255) / 256 : 16ULL * kNumSMs);
   cudaStream_t st = (cudaStream_t)stream;
   const int vec = dtype == SHB_BF16 ? 8 : 4;
-  if (gz_channels == Cout && Cout % vec == 0 && n / vec < (1ull << 32) && (dtype == SHB_F32 || dtype == SHB_BF16)) {
+  float* part = (float*)workspace;
+  if (gz_channels == Cout && Cout % vec == 0 && n / vec < (1ull << 32)) {
+    // 16-byte vectorised pass; the bias gradient rides along when a thread keeps one channel chunk
     const unsigned chunks = (unsigned)(n / vec), cpr = (unsigned)(Cout / vec);
-    const int vb = (int)((chunks + 255) / 256 < 16u * kNumSMs ? (chunks + 255) / 256 : 16u * kNumSMs);
+    const unsigned want = (chunks + 255) / 256;
+    const int vb = (int)(want < (unsigned)ACT_MAX_BLOCKS ? want : (unsigned)ACT_MAX_BLOCKS);
+    const bool fuse = gb != nullptr && cpr <= 256 && (256 % cpr) == 0;
     if (dtype == SHB_F32)
       act_bwd_vec_kernel<float, 4><<<vb, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, chunks, cpr,
-                                                       (unsigned)rows_out, act, zero_last_row);
+                                                       (unsigned)rows_out, act, zero_last_row, fuse ? part : nullptr);
     else
       act_bwd_vec_kernel<__nv_bfloat16, 8><<<vb, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
                                                                (__nv_bfloat16*)gz, chunks, cpr, (unsigned)rows_out, act,
-                                                               zero_last_row);
+                                                               zero_last_row, fuse ? part : nullptr);
     SHB_LAUNCH_CHECK();
-    return 0;
+    if (fuse) {
+      partial_reduce_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, vb, Cout, (float*)gb);
+      SHB_LAUNCH_CHECK();
+      return 0;
+    }
+  } else {
+    const int blocks = (int)((n + 255) / 256 < (unsigned long long)ACT_MAX_BLOCKS ? (n + 255) / 256 : ACT_MAX_BLOCKS);
+    if (dtype == SHB_F32)
+      act_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, (unsigned)rows,
+                                                    (unsigned)rows_out, Cout, gz_channels, act, zero_last_row);
+    else
+      act_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+                                                            (__nv_bfloat16*)gz, (unsigned)rows, (unsigned)rows_out, Cout,
+                                                            gz_channels, act, zero_last_row);
+    SHB_LAUNCH_CHECK();
   }
+  if (gb == nullptr) return 0;
+  // bias gradient from gz in a separate pass (odd channel counts / padded gz): two fixed-order stages
+  int CP = 1;
+  while (CP < gz_channels) CP <<= 1;
+  if (CP > 256) return SHB_E_SHAPE;
+  const int nb = 4 * kNumSMs;
+  const unsigned long long rpb = (rows + nb - 1) / nb;
+  float* tot = part + (size_t)nb * gz_channels;  // gz_channels floats after the partials
   if (dtype == SHB_F32)
-    act_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)y, (float*)gz, (unsigned)rows,
-                                                  (unsigned)rows_out, Cout, gz_channels, act, zero_last_row);
-  else if (dtype == SHB_BF16)
-    act_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
-                                                          (__nv_bfloat16*)gz, (unsigned)rows, (unsigned)rows_out, Cout,
-                                                          gz_channels, act, zero_last_row);
+    colsum_partial_generic<float><<<nb, 256, 0, st>>>((const float*)gz, rows, gz_channels, CP, rpb, part);
   else
-    return SHB_E_DTYPE;
+    colsum_partial_generic<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16*)gz, rows, gz_channels, CP, rpb, part);
   SHB_LAUNCH_CHECK();
-  return 0;
+  partial_reduce_kernel<<<(gz_channels + 31) / 32, 256, 0, st>>>(part, nb, gz_channels, tot);
+  SHB_LAUNCH_CHECK();
+  const cudaError_t e = cudaMemcpyAsync(gb, tot, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 int shb_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cp, int dtype_src, int dtype_dst, void* stream) {

@@ -164,24 +164,26 @@ class SpiralConvFn(torch.autograd.Function):
         gz = torch.empty((B, geom.rows_out, cout_p), dtype=x.dtype, device=x.device)
         tag = f"[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]"
         meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, x.element_size())
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        gb = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_gb else None
+        abytes = lib.shb_spiralconv_bwd_act_workspace(cout_p) if want_gb else 0
+        aws = torch.empty(abytes, dtype=torch.uint8, device=x.device) if want_gb else None
         _call("spiralconv_bwd_act" + tag, {"bytes": (2.0 * gy.numel() + gz.numel()) * gy.element_size()},
               lib.shb_spiralconv_bwd_act, _p(gy), _p(y), _p(gz), B, geom.rows_out, cout, cout_p, act,
-              int(geom.zero_last_row), dt, st)
-        _count()
+              int(geom.zero_last_row), _p(gb), _p(aws), abytes, dt, st)
+        _count(3 if want_gb else 1)
         if cout_p != cout:  # zero rows for the padded output channels
             w = torch.nn.functional.pad(w, (0, 0, 0, cout_p - cout)).contiguous()
-        gx = gw = gb = None
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        gx = gw = None
+        if ctx.needs_input_grad[1]:
             nbytes = lib.shb_spiralconv_wgrad_workspace(B, rows_in, geom.rows_out, S, cin_p, cout_p, dt)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             gw = torch.empty((cout_p, S * cin_p), dtype=torch.float32, device=x.device)
-            gb = torch.empty((cout_p,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
             _call("spiralconv_bwd_wgrad" + tag, meta, lib.shb_spiralconv_bwd_wgrad, _p(x), _p(geom.table), _p(gz), _p(gw),
-                  _p(gb), _p(ws), nbytes, B, rows_in, geom.rows_out, S, cin_p, cout_p, int(geom.src_dummy_zero), dt, st)
+                  None, _p(ws), nbytes, B, rows_in, geom.rows_out, S, cin_p, cout_p, int(geom.src_dummy_zero), dt, st)
             _count(2)
             if cout_p != cout or cin_p != cin:
                 gw = gw.view(cout_p, S, cin_p)[:cout, :, :cin].reshape(cout, S * cin)
-                gb = None if gb is None else gb[:cout]
             if ctx.wdtype != torch.float32:
                 gw = gw.to(ctx.wdtype)
         if ctx.needs_input_grad[0]:

@@ -5,7 +5,9 @@
 
 The reference loop calls optim.zero_grad / model / loss_fn / backward / optim.step itself and can keep doing so
 with the drop-in model; this class is the same sequence packaged for the benchmark and for data-parallel runs
-(gradient buckets + overlapped all-reduce from dp.GradSync), with pinned-host staging for the end-to-end path.
+(gradient buckets + overlapped all-reduce from dp.GradSync), with pinned-host staging for the end-to-end path and,
+on one GPU, optional CUDA-graph replay of the whole step (shapes are static; ~150 launches and their Python glue
+collapse into one graph launch).
 """
 import torch
 
@@ -14,15 +16,20 @@ from .dp import GradSync
 
 
 class TrainStep:
-    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True):
+    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False):
         self.model = model
         self.sync = GradSync(model)
-        self.optim = (torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True)
-                      if optimizer else None)
+        self.graph_enabled = bool(graph) and self.sync.world == 1
+        self.optim = (torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
+                                       capturable=self.graph_enabled) if optimizer else None)
         self._copy_stream = None
         self._staged = None
+        self._graph = None
+        self._gx = None
+        self._gloss = None
+        self.launches_per_step = None
 
-    def __call__(self, x):
+    def _eager(self, x):
         self.sync.reset()
         xh, _z = self.model(x)
         loss = fn.l1_loss(x, xh)  # train_funcs.py:501  loss_fn(tx, tx_hat)
@@ -31,6 +38,34 @@ class TrainStep:
         if self.optim is not None:
             self.optim.step()
         return loss
+
+    def capture(self, example_x, warmup=3):
+        """Capture one whole step into a CUDA graph (static input buffer; later calls copy into it and replay)."""
+        if not self.graph_enabled:
+            raise RuntimeError("graph capture is only enabled for single-process runs (graph=True, world size 1)")
+        self._gx = example_x.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up on a side stream, as torch.cuda.graph requires
+            for _ in range(warmup):
+                self._eager(self._gx)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = fn.LAUNCHES["n"]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._gloss = self._eager(self._gx)
+        self.launches_per_step = fn.LAUNCHES["n"] - n0
+        self._graph = g
+        return self
+
+    def __call__(self, x):
+        if self._graph is not None and fn.TIMER is None and x.shape == self._gx.shape and x.dtype == self._gx.dtype:
+            self._gx.copy_(x, non_blocking=True)
+            self._graph.replay()
+            fn.LAUNCHES["n"] += self.launches_per_step  # the replay launches the captured kernels again
+            return self._gloss
+        return self._eager(x)
 
     # ---- end-to-end path: inputs start in pinned host memory, the loss ends in host memory
     def stage(self, x_host_pinned):
@@ -49,5 +84,5 @@ class TrainStep:
         torch.cuda.current_stream().wait_event(ev)
         xd.record_stream(torch.cuda.current_stream())
         loss = self(xd)
-        loss_host_pinned.copy_(loss.detach(), non_blocking=True)
+        loss_host_pinned.copy_(loss.detach().reshape(loss_host_pinned.shape), non_blocking=True)
         return loss
