@@ -527,8 +527,9 @@ struct UWParams {
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
 };
 
-template <int CIN, int BKM>
-__global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParams p) {
+// NI: index registers per producer thread per stage (>= Q / QL); the NI = 8 variant fits two CTAs per SM (MINB = 2)
+template <int CIN, int BKM, int NI, int MINB>
+__global__ void __launch_bounds__(UG_THREADS, MINB) umma_wgrad_kernel(const UWParams p) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[UW_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UW_MAX_STAGES];
@@ -617,7 +618,6 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_wgrad_kernel(const UWParam
     const int mr = pw * RPW + l / QL, ql = l % QL;
     const uint32_t base = smem_u32(dyn_smem);
     int published = 0;
-    constexpr int NI = 16;  // index registers per stage per thread: Q / QL <= 16
     int rowc[NI];
     bool validc = false;
     long long mc = 0;
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
 
 static size_t uw_stage_bytes(int KT, int NPAD, int bkm) { return ((size_t)KT * 16 + (size_t)(NPAD / 8)) * (bkm * 16 + 16); }
 
-struct UWPlan { int bkm, nstage, KT, NPAD, grid; size_t smem; uint32_t cols; bool ok; };
+struct UWPlan { int bkm, nstage, KT, NPAD, grid; size_t smem; uint32_t cols; bool ok; bool two; };
 
 static UWPlan uw_plan(int Cin, int Cout, int S) {
   UWPlan pl{};
@@ -752,6 +752,15 @@ static UWPlan uw_plan(int Cin, int Cout, int S) {
     if (ns >= 3) { pl.bkm = bkm; pl.nstage = ns; pl.smem = sb * ns; pl.ok = true; break; }
   }
   pl.grid = kNumSMs;
+  // two CTAs per SM when TMEM (2 x cols <= 512), shared memory (2 x 3 stages) and the index registers (Q / QL <= 8) allow:
+  // the kernel is bound by gather latency/L1TEX issue, and a second CTA doubles the gathers in flight
+  pl.two = false;
+  if (pl.ok && pl.bkm == 32 && K / 8 <= 64 && pl.cols * 2 <= 512) {
+    const size_t sb = uw_stage_bytes(pl.KT, pl.NPAD, 32);
+    int ns = (int)((UG_SMEM_MAX / 2 - 2048) / sb);
+    if (ns > 4) ns = 4;
+    if (ns >= 3) { pl.two = true; pl.nstage = ns; pl.smem = sb * ns; pl.grid = 2 * kNumSMs; }
+  }
   return pl;
 }
 
@@ -760,18 +769,19 @@ bool umma_wgrad_supported(int Cin, int Cout, int S) { return uw_plan(Cin, Cout, 
 size_t umma_wgrad_workspace(int B, int rows_out, int S, int Cin, int Cout) {
   (void)B; (void)rows_out;
   // per-CTA fp32 partials of gw, then per-block partials of the bias gradient
-  return (size_t)kNumSMs * Cout * S * Cin * sizeof(float) + (size_t)4 * kNumSMs * Cout * sizeof(float);
+  return (size_t)2 * kNumSMs * Cout * S * Cin * sizeof(float) + (size_t)4 * kNumSMs * Cout * sizeof(float);
 }
 
-template <int CIN, int BKM> static int uw_launch(const UWParams& p, int grid, size_t smem, cudaStream_t st) {
+template <int CIN, int BKM, int NI, int MINB> static int uw_launch(const UWParams& p, int grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<CIN, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<CIN, BKM, NI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)UG_SMEM_MAX);
     if (e != cudaSuccess) return (int)e;
+    cudaFuncSetAttribute(umma_wgrad_kernel<CIN, BKM, NI, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
-  umma_wgrad_kernel<CIN, BKM><<<grid, UG_THREADS, smem, st>>>(p);
+  umma_wgrad_kernel<CIN, BKM, NI, MINB><<<grid, UG_THREADS, smem, st>>>(p);
   SHB_LAUNCH_CHECK();
   return 0;
 }
@@ -795,7 +805,8 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
   int rc;
 #define UW_DISPATCH(C)                                                                                          \
   case C:                                                                                                       \
-    rc = pl.bkm == 32 ? uw_launch<C, 32>(p, grid, pl.smem, st) : uw_launch<C, 16>(p, grid, pl.smem, st);        \
+    rc = pl.two ? uw_launch<C, 32, 8, 2>(p, grid, pl.smem, st)                                                   \
+                : (pl.bkm == 32 ? uw_launch<C, 32, 16, 1>(p, grid, pl.smem, st) : uw_launch<C, 16, 16, 1>(p, grid, pl.smem, st)); \
     break;
   switch (Cin) {
     UW_DISPATCH(16)
@@ -810,7 +821,7 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
   uw_reduce_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(p.ws, grid, n, gw);
   SHB_LAUNCH_CHECK();
   if (gb != nullptr) {
-    float* part = (float*)workspace + (size_t)kNumSMs * Cout * p.K;
+    float* part = (float*)workspace + (size_t)2 * kNumSMs * Cout * p.K;
     int CP = 1;
     while (CP < Cout) CP <<= 1;
     if (CP > 256) return SHB_E_SHAPE;

@@ -39,8 +39,11 @@ class GradSync:
         # NCCL averages inside the collective; gloo (CPU tests of this logic) has no AVG: sum, then scale in finish()
         self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self._params = [p for _, p in named]
         self.buckets = []
         self._handles = []
+        if self.world == 1:
+            return  # nothing to exchange: no flat buckets, gradients are plain per-parameter tensors (reset() drops them)
         for b in range(3):
             members = [(n, p) for n, p in named if _bucket_of(n) == b]
             if not members:
@@ -67,6 +70,10 @@ class GradSync:
 
     def reset(self):
         """Call before each backward (instead of optimizer.zero_grad(set_to_none=True), which would drop the views)."""
+        if self.world == 1:
+            for p in self._params:
+                p.grad = None
+            return
         for b in self.buckets:
             b["flat"].zero_()
             b["pending"] = len(b["params"])
@@ -84,4 +91,6 @@ class GradSync:
                 raise RuntimeError("GradSync.finish(): a bucket never completed -- was backward run, and reset() called?")
 
     def grad_bytes(self):
+        if self.world == 1:
+            return sum(p.numel() * p.element_size() for p in self._params)
         return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)
