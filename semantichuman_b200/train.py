@@ -6,8 +6,8 @@
 The reference loop calls optim.zero_grad / model / loss_fn / backward / optim.step itself and can keep doing so
 with the drop-in model; this class is the same sequence packaged for the benchmark and for data-parallel runs
 (gradient buckets + overlapped all-reduce from dp.GradSync), with pinned-host staging for the end-to-end path and,
-on one GPU, optional CUDA-graph replay of the whole step (shapes are static; ~150 launches and their Python glue
-collapse into one graph launch).
+optional CUDA-graph replay of the whole step (shapes are static; ~110 launches, the bucket all-reduces and their
+Python glue collapse into one graph launch per rank).
 """
 import torch
 
@@ -19,7 +19,7 @@ class TrainStep:
     def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False):
         self.model = model
         self.sync = GradSync(model)
-        self.graph_enabled = bool(graph) and self.sync.world == 1
+        self.graph_enabled = bool(graph)
         self.optim = (torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
                                        capturable=self.graph_enabled) if optimizer else None)
         self._copy_stream = None
@@ -42,22 +42,37 @@ class TrainStep:
     def capture(self, example_x, warmup=3):
         """Capture one whole step into a CUDA graph (static input buffer; later calls copy into it and replay)."""
         if not self.graph_enabled:
-            raise RuntimeError("graph capture is only enabled for single-process runs (graph=True, world size 1)")
+            raise RuntimeError("construct TrainStep(graph=True) to capture (Adam must be built capturable)")
         self._gx = example_x.clone()
+        # warm-up and capture share one side stream: autograd's AccumulateGrad nodes (kept alive by the bucket hooks in
+        # multi-process runs) remember the stream they were created on, and a mismatch would make the engine
+        # synchronise with the default stream in the middle of the capture
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up on a side stream, as torch.cuda.graph requires
+        with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._eager(self._gx)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = fn.LAUNCHES["n"]
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # multi-process: the bucket all-reduces are captured too (NCCL forks/joins its stream inside the graph); the
+        # process group's watchdog thread polls events concurrently, hence thread-local capture checking there
+        mode = "global" if self.sync.world == 1 else "thread_local"
+        with torch.cuda.graph(g, stream=side, capture_error_mode=mode):
             self._gloss = self._eager(self._gx)
         self.launches_per_step = fn.LAUNCHES["n"] - n0
         self._graph = g
         return self
+
+    def release(self):
+        """Drop the captured graph (back to eager).  Must run before dist.destroy_process_group(): NCCL will not
+        tear a communicator down while a live graph still holds its kernels."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._gloss = None
+            torch.cuda.synchronize()
 
     def __call__(self, x):
         if self._graph is not None and fn.TIMER is None and x.shape == self._gx.shape and x.dtype == self._gx.dtype:
