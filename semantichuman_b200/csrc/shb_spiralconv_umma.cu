@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
     const int pt = tid - (UG_EPI_WARPS + 1) * 32;  // 0..NPT-1
     const int pw = pt >> 5, kc = pt & 7, rr = (pt >> 3) & 3;
     const uint32_t a_base = smem_u32(a_ring);
-    const int SP = SUM ? 2 * p.S : p.S;            // dgrad: (first, second) source row per key
+    const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+    const int SP = SUM ? 2 * p.S : p.S;            // int32 words per table row (dgrad: 4 x uint16 per key)
     int32_t* idx_s = reinterpret_cast<int32_t*>(a_ring + (size_t)p.nstage * UG_STAGE_BYTES);  // [2][128*SP]
     const int nidx = UG_BM * SP;
     const unsigned rows_dst = (unsigned)p.rows_dst;
@@ -261,33 +262,60 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
     constexpr int SPS = CS <= 64 ? UG_KC / CPS : 1;      // slots per stage (CS = 128: one slot spans two stages)
     const int sl0 = CS <= 64 ? kc / CPS : 0;             // slot of this chunk column within a stage
     const int c0 = CS <= 64 ? (kc % CPS) * 8 : kc * 8;   // channel offset (+64 on odd stages when CS = 128)
-    // The tile's block of the index table goes global -> shared with 4-byte cp.async (no registers: a register-held
-    // prefetch array spilled under the register cap and serialised its loads); one commit group per block, waited for
-    // at the end of the previous tile.
+    // The tile's block of the index table goes global -> shared with cp.async (no registers: a register-held prefetch
+    // array spilled under the register cap and serialised its loads); one commit group per block, waited for at the end
+    // of the previous tile.  Table rows of consecutive destination rows are contiguous, so the block is one flat run
+    // (two when the tile crosses a sample boundary), copied in the widest unit that divides a table row.
     const uint32_t idx_base = smem_u32(idx_s);
-    auto prefetch_idx_block = [&](int tile, int buf) {
-      const bool live = tile < p.num_tiles;
-      const unsigned m0 = (unsigned)tile * UG_BM;
-      const unsigned j0 = live ? m0 % rows_dst : 0;
-      for (unsigned e = (unsigned)pt; e < (unsigned)nidx; e += NPT) {
-        const unsigned r = e / (unsigned)SP, sl = e - r * (unsigned)SP;
-        unsigned j = j0 + r;
-        if (j >= rows_dst) j = (rows_dst >= UG_BM) ? j - rows_dst : j % rows_dst;
-        const bool on = live && (long long)(m0 + r) < p.M;
-        cp_async4(idx_base + (uint32_t)(buf * nidx + (int)e) * 4, p.table + (on ? (size_t)j * SP + sl : 0), on ? 4u : 0u);
+    const int ush = (SP % 4 == 0) ? 2 : ((SP % 2 == 0) ? 1 : 0);  // log2(words per copy unit)
+    auto prefetch_idx_block = [&](unsigned m0, unsigned j0, int buf) {
+      const long long left = p.M - (long long)m0;
+      const unsigned nrows = left <= 0 ? 0u : (left < UG_BM ? (unsigned)left : (unsigned)UG_BM);
+      const uint32_t dst = idx_base + (uint32_t)(buf * nidx) * 4;
+      if (rows_dst >= (unsigned)UG_BM) {
+        const unsigned n1 = nrows < rows_dst - j0 ? nrows : rows_dst - j0;  // rows before the wrap to the next sample
+        const unsigned total = nrows * (unsigned)SP, split = n1 * (unsigned)SP, first = j0 * (unsigned)SP;
+        if (ush == 2) {
+          for (unsigned e = (unsigned)pt * 4; e < (unsigned)nidx; e += NPT * 4) {
+            const bool on = e < total;
+            cp_async16(dst + e * 4, p.table + (on ? (e < split ? first + e : e - split) : 0u), on ? 16u : 0u);
+          }
+        } else if (ush == 1) {
+          for (unsigned e = (unsigned)pt * 2; e < (unsigned)nidx; e += NPT * 2) {
+            const bool on = e < total;
+            cp_async8(dst + e * 4, p.table + (on ? (e < split ? first + e : e - split) : 0u), on ? 8u : 0u);
+          }
+        } else {
+          for (unsigned e = (unsigned)pt; e < (unsigned)nidx; e += NPT) {
+            const bool on = e < total;
+            cp_async4(dst + e * 4, p.table + (on ? (e < split ? first + e : e - split) : 0u), on ? 4u : 0u);
+          }
+        }
+      } else {  // tiny levels: a tile spans several samples
+        for (unsigned e = (unsigned)pt; e < (unsigned)nidx; e += NPT) {
+          const unsigned r = e / (unsigned)SP, sl = e - r * (unsigned)SP;
+          const unsigned j = (j0 + r) % rows_dst;
+          const bool on = r < nrows;
+          cp_async4(dst + e * 4, p.table + (on ? (size_t)j * SP + sl : 0), on ? 4u : 0u);
+        }
       }
       cp_async_commit();
     };
-    prefetch_idx_block(blockIdx.x, 0);
+    // tile coordinates (sample b0, first row j0) advance by a constant per iteration: no division in the loop
+    const unsigned tile_rows = gridDim.x * (unsigned)UG_BM;
+    const unsigned step_b = tile_rows / rows_dst, step_j = tile_rows - step_b * rows_dst;
+    unsigned m0 = blockIdx.x * (unsigned)UG_BM;
+    unsigned b0 = m0 / rows_dst, j0 = m0 - b0 * rows_dst;
+    prefetch_idx_block(m0, j0, 0);
     cp_async_wait_group<0>();
     asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
     uint32_t slot = 0, ph = 0;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int32_t* idx_cur = idx_s + (tcount & 1) * nidx;
-      prefetch_idx_block(tile + gridDim.x, (tcount + 1) & 1);  // next tile's block: in flight during this tile's stages
-      const unsigned m0 = (unsigned)tile * UG_BM;
-      const unsigned b0 = m0 / rows_dst, j0 = m0 - b0 * rows_dst;
+      unsigned bn = b0 + step_b, jn = j0 + step_j;
+      if (jn >= rows_dst) { jn -= rows_dst; bn += 1; }
+      prefetch_idx_block(m0 + tile_rows, jn, (tcount + 1) & 1);  // next tile's block: in flight during this tile's stages
       bool valid[NIT];
       const __nv_bfloat16* srcc[NIT];
       uint32_t row_off[NIT];
@@ -297,7 +325,7 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
         const unsigned r = i * (UG_BM / NIT) + pw * 4 + rr;
         unsigned j = j0 + r, b = b0;
         if (j >= rows_dst) {
-          if (rows_dst >= UG_BM) { j -= rows_dst; b += 1; } else { b += j / rows_dst; j %= rows_dst; }
+          if (rows_dst >= (unsigned)UG_BM) { j -= rows_dst; b += 1; } else { b += j / rows_dst; j %= rows_dst; }
         }
         valid[i] = (long long)(m0 + r) < p.M;
         if (SUM && p.skip_last && j == rows_dst - 1) valid[i] = false;
@@ -307,25 +335,34 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
         row_off[i] = (uint32_t)(r >> 3) * UG_SBO + (uint32_t)(r & 7) * 16 + (uint32_t)kc * UG_LBO;
       }
       int s = sl0;  // spiral slot of this thread's chunk column in the current stage
-      // gather-sum: raw rows of the (up to four) inline entries of every item, loaded one stage ahead of their use
-      uint4 vq[NIT][4];
+      // gather-sum: raw 16-byte chunks of the (up to four) inline entries of every item, loaded one stage ahead of their
+      // use.  Entries 0 and 1 are always requested (predicated per lane); entries 2 and 3 exist for 4 % / 0.7 % of the keys,
+      // so their loads and adds sit behind warp votes.  `more` keeps the votes: bit (2i) = some lane has entry 2 of item i,
+      // bit (2i+1) = entry 3.
+      uint4 v0[NIT], v1[NIT], v2[NIT], v3[NIT];
       bool over[NIT];
+      uint32_t more = 0;
       auto issue_sum_loads = [&](int sn, int coff) {
-        uint32_t w0[NIT], w1[NIT];
+        more = 0;
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
-          const bool on = valid[i] && sn < p.S;
-          w0[i] = on ? (uint32_t)idx_cur[irow[i] + 2 * sn] : 0xFFFFFFFFu;
-          w1[i] = on ? (uint32_t)idx_cur[irow[i] + 2 * sn + 1] : 0xFFFFFFFFu;
-        }
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          const uint32_t e[4] = {w0[i] & 0xFFFFu, w0[i] >> 16, w1[i] & 0xFFFFu, w1[i] >> 16};
-          over[i] = e[3] == 0xFFFEu;
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            vq[i][t] = e[t] < 0xFFFEu ? __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)e[t] * CS + coff))
-                                      : make_uint4(0, 0, 0, 0);
+          uint2 q = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+          if (valid[i] && sn < p.S) q = *reinterpret_cast<const uint2*>(idx_cur + irow[i] + 2 * sn);
+          const uint32_t e0 = q.x & 0xFFFFu, e1 = q.x >> 16, e2 = q.y & 0xFFFFu, e3 = q.y >> 16;
+          const __nv_bfloat16* base = srcc[i] + coff;
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          v0[i] = e0 < 0xFFFEu ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)e0 * CS)) : z;
+          v1[i] = e1 < 0xFFFEu ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)e1 * CS)) : z;
+          const bool h2 = e2 < 0xFFFEu, h3 = e3 < 0xFFFEu;
+          if (__any_sync(0xFFFFFFFFu, h2)) {
+            v2[i] = h2 ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)e2 * CS)) : z;
+            more |= 1u << (2 * i);
+            if (__any_sync(0xFFFFFFFFu, h3)) {  // entries are packed: an entry 3 implies an entry 2
+              v3[i] = h3 ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)e3 * CS)) : z;
+              more |= 2u << (2 * i);
+            }
+          }
+          over[i] = e3 == 0xFFFEu;
         }
       };
       if (SUM) issue_sum_loads(s, 0);
@@ -333,11 +370,11 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
         const int coff = (CS == 128 && (st & 1)) ? 64 : 0;
         const int step = (CS == 128) ? (st & 1) : SPS;
         UG_TRACE(0, 0, st);
-        mbar_wait(&empty_bar[slot], ph ^ 1);
+        mbar_wait(empty_u32 + slot * 8, ph ^ 1);
         UG_TRACE(0, 1, st);
         const uint32_t dst0 = a_base + slot * UG_STAGE_BYTES;
-        if (s < p.S && !(p.dbg & 1)) {
-          if (!SUM) {
+        if (!SUM) {
+          if (s < p.S && !(p.dbg & 1)) {
             int row[NIT];
 #pragma unroll
             for (int i = 0; i < NIT; ++i) row[i] = idx_cur[irow[i] + s];
@@ -345,44 +382,31 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
 #pragma unroll
             for (int i = 0; i < NIT; ++i)
               cp_async16(dst0 + row_off[i], srcc[i] + (size_t)row[i] * CS + coff, (valid[i] && row[i] != zrow) ? 16u : 0u);
-          } else {
-            // fixed summation order: inline entries 0..3 ascending, then (rare: 5+ entries) the CSR tail from entry 3
+          }
+        } else if (!(p.dbg & 1)) {
+          // fixed summation order: inline entries 0..3 ascending, then (rare: 5+ entries) the CSR tail from entry 3.
+          // Packed bf16 adds: each step rounds the exact sum once, i.e. what an fp32 add + cast gives for two entries.
 #pragma unroll
-            for (int i = 0; i < NIT; ++i) {
-              float acc[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const uint32_t wv[4] = {vq[i][t].x, vq[i][t].y, vq[i][t].z, vq[i][t].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  acc[2 * q] += __uint_as_float(wv[q] << 16);
-                  acc[2 * q + 1] += __uint_as_float(wv[q] & 0xffff0000u);
-                }
-              }
-              if (over[i]) {
-                const int k = urow[i] * p.S + s;
-                const int e0 = __ldg(p.keyptr + k), e1 = __ldg(p.keyptr + k + 1);
-                for (int e = e0 + 3; e < e1; ++e) {
-                  float v[8];
-                  Io<__nv_bfloat16>::ld8(srcc[i] + (size_t)__ldg(p.list + e) * CS + coff, v);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) acc[q] += v[q];
-                }
-              }
-              const uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(o.x), "r"(o.y),
-                           "r"(o.z), "r"(o.w)
-                           : "memory");
+          for (int i = 0; i < NIT; ++i) {
+            uint4 acc = bf16x8_add(v0[i], v1[i]);
+            if (more & (1u << (2 * i))) acc = bf16x8_add(acc, v2[i]);
+            if (more & (2u << (2 * i))) acc = bf16x8_add(acc, v3[i]);
+            if (over[i]) {
+              const int k = urow[i] * p.S + s;
+              const int e0 = __ldg(p.keyptr + k), e1 = __ldg(p.keyptr + k + 1);
+              for (int e = e0 + 3; e < e1; ++e)
+                acc = bf16x8_add(acc, __ldg(reinterpret_cast<const uint4*>(srcc[i] + (size_t)__ldg(p.list + e) * CS + coff)));
             }
+            if (s < p.S)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + row_off[i]), "r"(acc.x), "r"(acc.y),
+                           "r"(acc.z), "r"(acc.w)
+                           : "memory");
           }
         }
         UG_TRACE(0, 2, st);
         s += step;
         if (!SUM) {
-          cp_async_mbar_arrive_noinc(&full_bar[slot]);  // one (counted) arrival when this thread's copies have landed
+          cp_async_mbar_arrive_noinc(full_u32 + slot * 8);  // one (counted) arrival when this thread's copies have landed
         } else {
           // Next stage's loads go out before the hand-shake and STAY in flight across it: the generic->async proxy fence is
           // executed by the CONSUMER (the MMA thread, after it acquires the full barrier), not here -- a producer-side
@@ -390,13 +414,14 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
           // stage.  Ordering: st.shared -> __syncwarp -> arrive(release) -> try_wait(acquire) -> fence.proxy.async -> mma.
           if (st + 1 < p.NS) issue_sum_loads(s, (CS == 128 && ((st + 1) & 1)) ? 64 : 0);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full_bar[slot]);
+          if (lane == 0) mbar_arrive(full_u32 + slot * 8);
         }
         if (++slot == nstage) { slot = 0; ph ^= 1; }
       }
       // the next tile's index block must have landed (its commit group is the only committed one), for every producer
       cp_async_wait_group<0>();
       asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
+      m0 += tile_rows; b0 = bn; j0 = jn;
     }
   }
 

@@ -34,6 +34,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same operations on a precomputed shared-window address (hot loops: no per-call generic->shared conversion)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
 // Long waits (an epilogue warp waiting a whole tile, an MMA thread waiting for a gather) must not spin flat out:
 // every poll is an MIO/shared-memory op, and a dozen idle warps polling measurably starved the producers' LDS /
 // LDGSTS / arrive traffic (ncu: 75 % of executed warp-instructions were polls; short-scoreboard + MIO stalls).
@@ -57,6 +71,13 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 8-byte variant (index tables); src_bytes == 0 zero-fills
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 // 4-byte variant (index tables); src_bytes == 0 zero-fills
 __device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -65,6 +86,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 // returns once at most N of this thread's most recent cp.async groups are still in flight
 template <int N> __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// packed bf16 add, round-to-nearest-even per lane (one rounding of the exact sum, like an fp32 add followed by a cast)
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint4 bf16x8_add(uint4 a, uint4 b) {
+  return make_uint4(bf16x2_add(a.x, b.x), bf16x2_add(a.y, b.y), bf16x2_add(a.z, b.z), bf16x2_add(a.w, b.w));
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
