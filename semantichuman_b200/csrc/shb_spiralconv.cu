@@ -286,22 +286,15 @@ __global__ void __launch_bounds__(256) colsum_partial_generic(const T* __restric
   }
 }
 
-// out[i] = sum_c part[c*n + i]: eight part-lanes per output, combined in ascending order (deterministic)
+// out[i] = sum_c part[c*n + i]: one CTA per output column, 256 part-lanes (each ascending), then the fixed-order
+// block reduction -- deterministic, and ~10 dependent loads per thread instead of ~300 (parts is a few thousand)
 __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ ws, int parts, int n, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int x = threadIdx.x & 31, yy = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + x;
+  __shared__ float red[8];
+  const int i = blockIdx.x;
   float a = 0.f;
-  if (i < n)
-    for (int c = yy; c < parts; c += 8) a += ws[(size_t)c * n + i];
-  red[yy][x] = a;
-  __syncthreads();
-  if (yy == 0 && i < n) {
-    float s = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s += red[q][x];
-    out[i] = s;
-  }
+  for (int c = threadIdx.x; c < parts; c += 256) a += ws[(size_t)c * n + i];
+  a = block_sum<256>(a, red);
+  if (threadIdx.x == 0) out[i] = a;
 }
 
 // dst[row, c] = c < C ? (Tdst)src[row, c] : 0   -- channel zero-padding (+ fp32 -> bf16 cast) so that 3-channel
@@ -507,6 +500,73 @@ __global__ void __launch_bounds__(256) dgrad_dummy_kernel(const T* __restrict__ 
   for (int c = t; c < Cin; c += 256) Io<T>::st(gx + ((long long)b * rows_in + u) * Cin + c, out[c]);
 }
 
+// Vectorised version (Cout a multiple of V = 16 bytes' worth of T, S*Cout/V <= 512, Cin <= 512): all S slots at once.
+// Phase 1: thread = (group g, slot s, V-wide channel chunk); entries e0+g, e0+g+NG, ... of key (dummy, s) in ascending
+// order, four loads in flight; the NG groups are combined in ascending order.  Phase 2: out[c] = sum_s sum_n G[s][n] *
+// W[n, s*Cin + c], slots strided over NQ = 512/Cin thread groups, combined in ascending order.  Deterministic.
+template <typename T, int V>
+__global__ void __launch_bounds__(512) dgrad_dummy_vec_kernel(const T* __restrict__ gz, const int32_t* __restrict__ keyptr,
+                                                              const int32_t* __restrict__ rows, const T* __restrict__ w,
+                                                              T* __restrict__ gx, int rows_in, int rows_out, int S, int Cin,
+                                                              int Cout) {
+  extern __shared__ float sm[];  // part[NG][S*Cout] | G[S*Cout] | outp[NQ][Cin]
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int u = rows_in - 1;
+  const int CPR = Cout / V, NI = S * CPR, NG = 512 / NI, SC = S * Cout;
+  float* part = sm;
+  float* G = part + (size_t)NG * SC;
+  float* outp = G + SC;
+  const T* gzb = gz + (long long)b * rows_out * Cout;
+  if (t < NG * NI) {
+    const int g = t / NI, item = t - g * NI, s = item / CPR, ch = item - s * CPR;
+    const int e0 = keyptr[(long long)u * S + s], e1 = keyptr[(long long)u * S + s + 1];
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int e = e0 + g; e < e1; e += 4 * NG) {
+      float v[4][V];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int eq = e + q * NG;
+        if (eq < e1) {
+          const T* px = gzb + (long long)__ldg(rows + eq) * Cout + ch * V;
+          if (V == 8) Io<T>::ld8(px, v[q]); else Io<T>::ld4(px, v[q]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[q][k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += v[q][k];
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) part[(size_t)g * SC + s * Cout + ch * V + k] = acc[k];
+  }
+  __syncthreads();
+  for (int i = t; i < SC; i += 512) {
+    float r = 0.f;
+    for (int g = 0; g < NG; ++g) r += part[(size_t)g * SC + i];
+    G[i] = r;
+  }
+  __syncthreads();
+  const int NQ = 512 / Cin, K = S * Cin;
+  if (t < NQ * Cin) {
+    const int q = t / Cin, c = t - q * Cin;
+    float a = 0.f;
+    for (int s = q; s < S; s += NQ)
+      for (int n = 0; n < Cout; ++n) a = fmaf(G[s * Cout + n], Io<T>::ld(w + (long long)n * K + (long long)s * Cin + c), a);
+    outp[q * Cin + c] = a;
+  }
+  __syncthreads();
+  if (t < Cin) {
+    float a = 0.f;
+    for (int q = 0; q < NQ; ++q) a += outp[q * Cin + t];
+    Io<T>::st(gx + ((long long)b * rows_in + u) * Cin + t, a);
+  }
+}
+
 template <typename T>
 static int wgrad_launch(const WGParams& p0, int splits, void* gw, void* gb, cudaStream_t st) {
   WGParams p = p0;
@@ -608,7 +668,7 @@ int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int r
                                                                zero_last_row, fuse ? part : nullptr);
     SHB_LAUNCH_CHECK();
     if (fuse) {
-      partial_reduce_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, vb, Cout, (float*)gb);
+      partial_reduce_kernel<<<Cout, 256, 0, st>>>(part, vb, Cout, (float*)gb);
       SHB_LAUNCH_CHECK();
       return 0;
     }
@@ -636,7 +696,7 @@ int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int r
   else
     colsum_partial_generic<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16*)gz, rows, gz_channels, CP, rpb, part);
   SHB_LAUNCH_CHECK();
-  partial_reduce_kernel<<<(gz_channels + 31) / 32, 256, 0, st>>>(part, nb, gz_channels, tot);
+  partial_reduce_kernel<<<gz_channels, 256, 0, st>>>(part, nb, gz_channels, tot);
   SHB_LAUNCH_CHECK();
   const cudaError_t e = cudaMemcpyAsync(gb, tot, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st);
   return e == cudaSuccess ? 0 : (int)e;
@@ -717,6 +777,20 @@ int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_
       rc = launch_gather_gemm<__nv_bfloat16, true>(p, st);
   } else return SHB_E_DTYPE;
   if (rc != 0 || !dummy_row_grad) return rc;
+  const int V = dtype == SHB_F32 ? 4 : 8;
+  if (Cout % V == 0 && S * (Cout / V) <= 512 && Cin <= 512) {
+    const int NG = 512 / (S * (Cout / V)), NQ = 512 / Cin;
+    const size_t smem = ((size_t)(NG + 1) * S * Cout + (size_t)NQ * Cin) * sizeof(float);  // <= 16 KB + 16 KB + 2 KB
+    if (dtype == SHB_F32)
+      dgrad_dummy_vec_kernel<float, 4><<<B, 512, smem, st>>>((const float*)gz, keyptr, rows, (const float*)w, (float*)gx,
+                                                             rows_in, rows_out, S, Cin, Cout);
+    else
+      dgrad_dummy_vec_kernel<__nv_bfloat16, 8><<<B, 512, smem, st>>>((const __nv_bfloat16*)gz, keyptr, rows,
+                                                                     (const __nv_bfloat16*)w, (__nv_bfloat16*)gx, rows_in,
+                                                                     rows_out, S, Cin, Cout);
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (256 + (size_t)Cout + Cin) * sizeof(float);
   if (dtype == SHB_F32)
     dgrad_dummy_kernel<float><<<B, 256, smem, st>>>((const float*)gz, keyptr, rows, (const float*)w, (float*)gx, rows_in,

@@ -263,41 +263,28 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
     const int sl0 = CS <= 64 ? kc / CPS : 0;             // slot of this chunk column within a stage
     const int c0 = CS <= 64 ? (kc % CPS) * 8 : kc * 8;   // channel offset (+64 on odd stages when CS = 128)
     // The tile's block of the index table goes global -> shared with cp.async (no registers: a register-held prefetch
-    // array spilled under the register cap and serialised its loads); one commit group per block, waited for at the end
-    // of the previous tile.  Table rows of consecutive destination rows are contiguous, so the block is one flat run
-    // (two when the tile crosses a sample boundary), copied in the widest unit that divides a table row.
+    // array spilled under the register cap and serialised its loads), double-buffered, one commit group per block.
+    // Blocks are WARP-PRIVATE: a warp stages exactly the table rows its own lanes gather (NIT groups of 4 consecutive
+    // tile rows), so a block needs only cp.async.wait_group + __syncwarp -- no CTA-wide barrier at tile boundaries
+    // (ncu: 12 % of the gather-sum kernel's stall samples sat on that barrier).
     const uint32_t idx_base = smem_u32(idx_s);
-    const int ush = (SP % 4 == 0) ? 2 : ((SP % 2 == 0) ? 1 : 0);  // log2(words per copy unit)
+    const int ush = (SP % 4 == 0) ? 2 : ((SP % 2 == 0) ? 1 : 0);  // log2(words per copy unit): widest that divides a row
+    constexpr int RW = 4 * NIT;     // table rows per warp per tile
+    constexpr int PARTS = 32 / RW;  // lanes sharing one table row
+    const int cq = lane % RW, cpart = lane / RW;
+    const unsigned crow = (unsigned)((cq >> 2) * (UG_BM / NIT) + pw * 4 + (cq & 3));  // tile row this lane stages
     auto prefetch_idx_block = [&](unsigned m0, unsigned j0, int buf) {
-      const long long left = p.M - (long long)m0;
-      const unsigned nrows = left <= 0 ? 0u : (left < UG_BM ? (unsigned)left : (unsigned)UG_BM);
-      const uint32_t dst = idx_base + (uint32_t)(buf * nidx) * 4;
-      if (rows_dst >= (unsigned)UG_BM) {
-        const unsigned n1 = nrows < rows_dst - j0 ? nrows : rows_dst - j0;  // rows before the wrap to the next sample
-        const unsigned total = nrows * (unsigned)SP, split = n1 * (unsigned)SP, first = j0 * (unsigned)SP;
-        if (ush == 2) {
-          for (unsigned e = (unsigned)pt * 4; e < (unsigned)nidx; e += NPT * 4) {
-            const bool on = e < total;
-            cp_async16(dst + e * 4, p.table + (on ? (e < split ? first + e : e - split) : 0u), on ? 16u : 0u);
-          }
-        } else if (ush == 1) {
-          for (unsigned e = (unsigned)pt * 2; e < (unsigned)nidx; e += NPT * 2) {
-            const bool on = e < total;
-            cp_async8(dst + e * 4, p.table + (on ? (e < split ? first + e : e - split) : 0u), on ? 8u : 0u);
-          }
-        } else {
-          for (unsigned e = (unsigned)pt; e < (unsigned)nidx; e += NPT) {
-            const bool on = e < total;
-            cp_async4(dst + e * 4, p.table + (on ? (e < split ? first + e : e - split) : 0u), on ? 4u : 0u);
-          }
-        }
-      } else {  // tiny levels: a tile spans several samples
-        for (unsigned e = (unsigned)pt; e < (unsigned)nidx; e += NPT) {
-          const unsigned r = e / (unsigned)SP, sl = e - r * (unsigned)SP;
-          const unsigned j = (j0 + r) % rows_dst;
-          const bool on = r < nrows;
-          cp_async4(dst + e * 4, p.table + (on ? (size_t)j * SP + sl : 0), on ? 4u : 0u);
-        }
+      const bool on = (long long)(m0 + crow) < p.M;
+      unsigned j = j0 + crow;
+      if (j >= rows_dst) j = rows_dst >= (unsigned)UG_BM ? j - rows_dst : j % rows_dst;
+      const int32_t* src = p.table + (on ? (size_t)j * SP : 0);
+      const uint32_t dst = idx_base + (uint32_t)(buf * nidx + (int)crow * SP) * 4;
+      if (ush == 2) {
+        for (int w = cpart * 4; w < SP; w += PARTS * 4) cp_async16(dst + w * 4, src + w, on ? 16u : 0u);
+      } else if (ush == 1) {
+        for (int w = cpart * 2; w < SP; w += PARTS * 2) cp_async8(dst + w * 4, src + w, on ? 8u : 0u);
+      } else {
+        for (int w = cpart; w < SP; w += PARTS) cp_async4(dst + w * 4, src + w, on ? 4u : 0u);
       }
       cp_async_commit();
     };
@@ -308,7 +295,7 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
     unsigned b0 = m0 / rows_dst, j0 = m0 - b0 * rows_dst;
     prefetch_idx_block(m0, j0, 0);
     cp_async_wait_group<0>();
-    asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
+    __syncwarp();
     uint32_t slot = 0, ph = 0;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
@@ -418,9 +405,9 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
         }
         if (++slot == nstage) { slot = 0; ph ^= 1; }
       }
-      // the next tile's index block must have landed (its commit group is the only committed one), for every producer
+      // the next tile's index block must have landed, for every lane of this warp (blocks are warp-private)
       cp_async_wait_group<0>();
-      asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory");
+      __syncwarp();
       m0 += tile_rows; b0 = bn; j0 = jn;
     }
   }
