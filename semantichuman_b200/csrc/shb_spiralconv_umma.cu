@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(UG_THREADS, MINB) umma_wgrad_kernel(const UWPa
 
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) {
-      mbar_init(&full_bar[i], UG_PROD_WARPS);
+      mbar_init(&full_bar[i], UG_PROD_THREADS);  // one cp.async-completion arrival per producer thread
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&done_bar, 1);
@@ -601,20 +601,26 @@ __global__ void __launch_bounds__(UG_THREADS, MINB) umma_wgrad_kernel(const UWPa
     if (lane == 0 && nst > 0) {
       const uint32_t idesc = idesc_bf16_f32(128, p.NPAD, 1, 1);
       const uint32_t base = smem_u32(dyn_smem);
+      // descriptor = hi (SBO, version) | lo (start address >> 4, LBO = 128 B); only the start address moves
+      const uint64_t hi = ((uint64_t)(SBO >> 4) << 32) | ((uint64_t)1 << 46);
+      const uint32_t lo_flags = (128u >> 4) << 16;
+      uint32_t slot = 0, ph = 0;
       for (int st = 0; st < nst; ++st) {
-        const uint32_t slot = st % p.nstage, ph = (st / p.nstage) & 1;
         mbar_wait_backoff(&full_bar[slot], ph, 20);
+        fence_proxy_async_smem();  // the stage was written by cp.async (generic proxy); tcgen05.mma reads through the async proxy
         tc_fence_after();
-        const uint32_t a_st = base + slot * stage_bytes, b_st = a_st + p.a_stage_bytes;
+        const uint32_t a_lo = ((base + slot * stage_bytes) >> 4) | lo_flags, b_lo = a_lo + (p.a_stage_bytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < BKM / 16; ++kk) {
-          const uint64_t db = smem_desc(b_st + kk * 256, 128, SBO);
+          const uint64_t db = hi | (b_lo + kk * 16);
+          uint32_t a_t = a_lo + kk * 16;
           for (int t = 0; t < p.KT; ++t) {
-            const uint64_t da = smem_desc(a_st + (uint32_t)(t * 16) * SBO + kk * 256, 128, SBO);
-            mma_bf16(tmem_base + (uint32_t)(t * p.NPAD), da, db, idesc, (st | kk) != 0);
+            mma_bf16(tmem_base + (uint32_t)(t * p.NPAD), hi | a_t, db, idesc, (st | kk) != 0);
+            a_t += SBO;  // 16 MN-chunks of SBO bytes, >> 4
           }
         }
         mma_commit(&empty_bar[slot]);
+        if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
       }
       mma_commit(&done_bar);
     }
@@ -629,19 +635,18 @@ __global__ void __launch_bounds__(UG_THREADS, MINB) umma_wgrad_kernel(const UWPa
     constexpr int QL = 32 / RPW;   // chunk lanes per row
     const int mr = pw * RPW + l / QL, ql = l % QL;
     const uint32_t base = smem_u32(dyn_smem);
-    int published = 0;
+    const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
     int rowc[NI];
     bool validc = false;
     long long mc = 0;
     const __nv_bfloat16* xbc = p.x;
+    // (sample, row) of this thread's stage row, advanced by BKM per stage: no division in the loop
+    long long mnext = mbeg + mr;
+    unsigned bnext = (unsigned)(mnext / p.rows_out), jnext = (unsigned)(mnext - (long long)bnext * p.rows_out);
     auto fetch_stage_idx = [&](int st, int* rowv, bool& valid, long long& m, const __nv_bfloat16*& xb) {
-      m = mbeg + (long long)st * BKM + mr;
+      m = mnext;
       valid = st < nst && m < mend;
-      unsigned b = 0, j = 0;
-      if (valid) {
-        b = (unsigned)m / (unsigned)p.rows_out;
-        j = (unsigned)m - b * (unsigned)p.rows_out;
-      }
+      const unsigned b = valid ? bnext : 0u, j = valid ? jnext : 0u;
       xb = p.x + (size_t)b * p.rows_in * CIN;
       const int32_t* trow = p.table + (size_t)j * p.S;
 #pragma unroll
@@ -649,17 +654,20 @@ __global__ void __launch_bounds__(UG_THREADS, MINB) umma_wgrad_kernel(const UWPa
         const int q = ql + u * QL;
         rowv[u] = (valid && q < p.Q) ? __ldg(trow + (q * 8) / CIN) : 0;
       }
+      mnext += BKM;
+      jnext += BKM;
+      while (jnext >= (unsigned)p.rows_out) { jnext -= (unsigned)p.rows_out; ++bnext; }
     };
     fetch_stage_idx(0, rowc, validc, mc, xbc);
     const int zrow = p.src_dummy_zero ? p.rows_in - 1 : -1;
+    uint32_t slot = 0, ph = 0;
     for (int st = 0; st < nst; ++st) {
-      const uint32_t slot = st % p.nstage, ph = (st / p.nstage) & 1;
       int rown[NI];
       bool validn;
       long long mn;
       const __nv_bfloat16* xbn;
       fetch_stage_idx(st + 1, rown, validn, mn, xbn);  // next stage's indices: in flight while this stage is issued
-      mbar_wait(&empty_bar[slot], ph ^ 1);
+      mbar_wait(empty_u32 + slot * 8, ph ^ 1);
       const uint32_t a_dst = base + slot * stage_bytes + (uint32_t)mr * 16;
 #pragma unroll
       for (int u = 0; u < NI; ++u) {
@@ -673,25 +681,16 @@ __global__ void __launch_bounds__(UG_THREADS, MINB) umma_wgrad_kernel(const UWPa
         const bool in = validc && (q * 8 < p.Cout);
         cp_async16(b_dst + (uint32_t)q * SBO, p.gz + (validc ? mc : 0) * p.Cout + q * 8, in ? 16u : 0u);
       }
-      cp_async_commit();
-      if (st + 1 - published > UG_LAG) {
-        cp_async_wait_group<UG_LAG>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (l == 0) mbar_arrive(&full_bar[published % p.nstage]);
-        ++published;
-      }
+      // one (counted) arrival on the stage's barrier when this thread's copies have landed: nothing waits here, the whole
+      // ring depth stays available to the gathers (the generic->async proxy fence is on the consumer side)
+      cp_async_mbar_arrive_noinc(full_u32 + slot * 8);
 #pragma unroll
       for (int u = 0; u < NI; ++u) rowc[u] = rown[u];
       validc = validn;
       mc = mn;
       xbc = xbn;
+      if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
     }
-    cp_async_wait_group<0>();
-    fence_proxy_async_smem();
-    __syncwarp();
-    for (; published < nst; ++published)
-      if (l == 0) mbar_arrive(&full_bar[published % p.nstage]);
   }
   tc_fence_before();
   __syncthreads();
