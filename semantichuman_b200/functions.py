@@ -200,33 +200,35 @@ class SpiralConvFn(torch.autograd.Function):
 
 
 class PoolFn(torch.autograd.Function):
-    """y[b] = P . x[b] with P in CSR (models.py:127,148); backward uses the CSR of P^T."""
+    """y[b] = P . x[b] with P in CSR (models.py:127,148); backward uses the CSR of P^T.  ``transposed=True`` applies
+    P^T in the forward (and P in the backward): the inverse gather when P is a permutation."""
 
     @staticmethod
-    def forward(ctx, x, pm):
+    def forward(ctx, x, pm, transposed=False):
         _cuda(x)
         x = x.contiguous()
-        B, rows_in, C = x.shape
-        if rows_in != pm.rows_in:
-            raise ValueError(f"pool expects {pm.rows_in} rows, got {rows_in}")
-        y = torch.empty((B, pm.rows_out, C), dtype=x.dtype, device=x.device)
-        _call(f"pool_spmm[{rows_in}>{pm.rows_out}x{C}]", _pool_meta(B, pm, C, x.element_size(), False), lib.shb_pool_spmm,
-              _p(x), _p(pm.rowptr), _p(pm.colidx), _p(pm.vals), _p(y), B, rows_in, pm.rows_out, C, _dt(x), _stream())
+        B, rows, C = x.shape
+        ctx.pm, ctx.transposed = pm, bool(transposed)
+        return PoolFn._apply(x, pm, ctx.transposed, B, rows, C)
+
+    @staticmethod
+    def _apply(x, pm, transposed, B, rows, C):
+        rows_in, rows_out = (pm.rows_out, pm.rows_in) if transposed else (pm.rows_in, pm.rows_out)
+        if rows != rows_in:
+            raise ValueError(f"pool expects {rows_in} rows, got {rows}")
+        rowptr, colidx, vals = (pm.t_rowptr, pm.t_colidx, pm.t_vals) if transposed else (pm.rowptr, pm.colidx, pm.vals)
+        y = torch.empty((B, rows_out, C), dtype=x.dtype, device=x.device)
+        name = f"pool_spmm{'_bwd' if transposed else ''}[{rows_in}>{rows_out}x{C}]"
+        _call(name, _pool_meta(B, pm, C, x.element_size(), transposed), lib.shb_pool_spmm, _p(x), _p(rowptr), _p(colidx),
+              _p(vals), _p(y), B, rows_in, rows_out, C, _dt(x), _stream())
         _count()
-        ctx.pm = pm
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        pm = ctx.pm
         gy = gy.contiguous()
-        B, _, C = gy.shape
-        gx = torch.empty((B, pm.rows_in, C), dtype=gy.dtype, device=gy.device)
-        _call(f"pool_spmm_bwd[{pm.rows_out}>{pm.rows_in}x{C}]", _pool_meta(B, pm, C, gy.element_size(), True),
-              lib.shb_pool_spmm, _p(gy), _p(pm.t_rowptr), _p(pm.t_colidx), _p(pm.t_vals), _p(gx), B, pm.rows_out,
-              pm.rows_in, C, _dt(gy), _stream())
-        _count()
-        return gx, None
+        B, rows, C = gy.shape
+        return PoolFn._apply(gy, ctx.pm, not ctx.transposed, B, rows, C), None, None
 
 
 class L1LossFn(torch.autograd.Function):

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from . import functions as fn
 from ._capi import ACT_ENUM
-from .indexing import PoolMatrix, SpiralGeometry
+from .indexing import PoolMatrix, SpiralGeometry, locality_order, normalise_spiral
 
 # models.py:169,285 read cfg.CONSTANTS.newskl_list; this is its default (configure/cfgs.py:21-23).  A caller that
 # merges a yaml with a longer list (traincfg.yaml:55) can assign `model.newskl_list`.
@@ -113,7 +113,7 @@ class _SpiralTrunk(nn.Module):
     """Conv/pool stacks shared by both autoencoders (models.py:121-127,147-153 == :244-250,275-281)."""
 
     def _init_trunk(self, filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool,
-                    make_heads):
+                    make_heads, reorder=True):
         """`make_heads(enc_out_channels)` registers the latent layers; it runs between the registration of
         ``conv`` and ``dconv`` so that parameter order (hence optimizer-state order in the reference's checkpoints,
         main.py:288) is the reference's: conv, fc..., dconv (models.py:81-86,113)."""
@@ -136,12 +136,32 @@ class _SpiralTrunk(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("semantichuman_b200 models need a CUDA device; there is no CPU fallback")
         # per-level tables; level n_levels has spirals but no conv (models.py:71,90 loop to len-1)
-        geoms = [SpiralGeometry.from_spiral(spirals[i], dev, dummy_row_grad=False) for i in range(n_levels)]
+        tables = [normalise_spiral(spirals[i]) for i in range(n_levels)]
         self._pD = [as_pool_matrix(D[i], dev) for i in range(n_levels)]
         self._pU = [as_pool_matrix(U[i], dev) for i in range(n_levels)]
         for i in range(n_levels):
-            if self._pD[i].rows_in != geoms[i].rows_in or self._pU[i].rows_out != geoms[i].rows_in:
+            if self._pD[i].rows_in != tables[i].shape[0] or self._pU[i].rows_out != tables[i].shape[0]:
                 raise ValueError(f"level {i}: D/U shapes do not match the spiral table")
+        # Internal vertex order (invisible to callers): inside the trunks level l lives in the order perm[l] (new position i
+        # holds the caller's vertex perm[l][i]; the dummy row stays last), chosen so that spiral neighbourhoods are
+        # index-local.  Only tables change: spiral tables, D/U and the kept-row lists are relabelled, the level-0 tensor is
+        # row-permuted on the way in and back on the way out, and the last level keeps the caller's order (FC layout).
+        self._perm = self._level_orders(tables, n_levels) if reorder else None
+        sel_rows = [pm.selection_cols if pm.is_selection else None for pm in self._pD]
+        self._io_perm = None
+        if self._perm is not None:
+            full = [np.concatenate([q, [len(q)]]) for q in self._perm]           # + dummy
+            pos = []
+            for f in full:
+                r = np.empty(len(f), np.int64)
+                r[f] = np.arange(len(f))
+                pos.append(r)
+            tables = [pos[i][tables[i][full[i]]].astype(np.int32) for i in range(n_levels)]
+            sel_rows = [None if sel_rows[i] is None else pos[i][sel_rows[i][full[i + 1]]] for i in range(n_levels)]
+            self._pD = [self._pD[i].permuted(full[i + 1], full[i]) for i in range(n_levels)]
+            self._pU = [self._pU[i].permuted(full[i], full[i + 1]) for i in range(n_levels)]
+            self._io_perm = PoolMatrix.from_permutation(full[0], dev)
+        geoms = [SpiralGeometry(tables[i], tables[i].shape[0], dev, dummy_row_grad=False) for i in range(n_levels)]
         # encoder plan: (conv index, geometry, pool-after or None)
         self._enc_plan = []
         for j, lvl in enumerate(self._enc_lvl):
@@ -151,9 +171,9 @@ class _SpiralTrunk(nn.Module):
             geoms[lvl] = geoms[lvl].with_flags(src_dummy_zero=(j > 0))
             if not last_at_level:
                 self._enc_plan.append((j, geoms[lvl], None))
-            elif fuse_pool and self._pD[lvl].is_selection and self._pD[lvl].selection_cols[-1] == geoms[lvl].rows_in - 1:
+            elif fuse_pool and sel_rows[lvl] is not None and sel_rows[lvl][-1] == geoms[lvl].rows_in - 1:
                 # D is a row selection: evaluate the conv only at the kept vertices (+ dummy)
-                self._enc_plan.append((j, geoms[lvl].restricted(self._pD[lvl].selection_cols, dummy_row_grad=False,
+                self._enc_plan.append((j, geoms[lvl].restricted(sel_rows[lvl], dummy_row_grad=False,
                                                                 src_dummy_zero=(j > 0)), None))
             else:
                 self._enc_plan.append((j, geoms[lvl], self._pD[lvl]))
@@ -168,6 +188,25 @@ class _SpiralTrunk(nn.Module):
             self._dec_plan.append((j, g, self._pU[lvl] if first_at_level else None))
         self.compute_dtype = torch.float32
 
+    def _level_orders(self, tables, n_levels):
+        """perm[l] for l = 0..n_levels: reverse Cuthill-McKee at level 0; a coarser level inherits the order of the level
+        above when D is a row selection (so that D/U stay local too), else gets its own; the last level is the identity."""
+        try:
+            perm = [locality_order(tables[0])]
+        except ImportError:  # scipy missing: keep the caller's numbering (a performance matter only)
+            return None
+        for l in range(n_levels):
+            v_next = self._pD[l].rows_out - 1
+            if l + 1 == n_levels:
+                perm.append(np.arange(v_next, dtype=np.int64))
+            elif self._pD[l].is_selection and self._pD[l].selection_cols[-1] == self._pD[l].rows_in - 1:
+                where = np.empty(len(perm[l]) + 1, np.int64)
+                where[perm[l]] = np.arange(len(perm[l]))
+                perm.append(np.argsort(where[self._pD[l].selection_cols[:-1]], kind="stable").astype(np.int64))
+            else:
+                perm.append(locality_order(tables[l + 1]))
+        return perm
+
     def set_compute_dtype(self, dtype):
         """torch.float32 (default; exact-fp32 kernels, 1e-4 parity) or torch.bfloat16 (bf16 activations and
         operands, fp32 accumulation, fp32 master weights; 2e-2 parity)."""
@@ -179,6 +218,8 @@ class _SpiralTrunk(nn.Module):
     def _encode_trunk(self, x):
         if not x.is_cuda:
             raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
+        if self._io_perm is not None:
+            x = fn.pool(x.contiguous(), self._io_perm)  # caller's vertex order -> internal order (row gather)
         for j, geom, pm in self._enc_plan:
             x = self.conv[j](x, geom, self.compute_dtype)  # the first conv casts (and pads) its fp32 input itself
             if pm is not None:
@@ -191,14 +232,17 @@ class _SpiralTrunk(nn.Module):
             if pm is not None:
                 x = fn.pool(x, pm)
             x = self.dconv[j](x, geom)
-        return x.float()
+        x = x.float()
+        if self._io_perm is not None:
+            x = fn.PoolFn.apply(x, self._io_perm, True)  # internal order -> caller's order (the inverse gather)
+        return x
 
 
 class SpiralAutoencoder(_SpiralTrunk):
     """models.py:55-162."""
 
     def __init__(self, filters_enc, filters_dec, latent_size, sizes, spiral_sizes, spirals, D, U, device,
-                 VAE_flag=False, activation='elu', fuse_pool=True):
+                 VAE_flag=False, activation='elu', fuse_pool=True, reorder=True):
         super().__init__()
         self.latent_size = latent_size
         self.VAE_flag = VAE_flag
@@ -208,7 +252,7 @@ class SpiralAutoencoder(_SpiralTrunk):
             self.fc_latent_dec = nn.Linear(latent_size, (sizes[-1] + 1) * filters_dec[0][0])
 
         self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool,
-                         heads)
+                         heads, reorder)
 
     def _linear(self, layer, v):
         if self.compute_dtype == torch.float32:
@@ -241,7 +285,8 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
     """models.py:166-310 -- bone-guided variant: per-part shape codes + per-part keypoint (bone) codes."""
 
     def __init__(self, kps_index_list, vert_part_index_dict, filters_enc, filters_dec, latent_size, part_kps_latent_size,
-                 sizes, spiral_sizes, spirals, D, U, device, VAE_flag=False, activation='elu', fuse_pool=True):
+                 sizes, spiral_sizes, spirals, D, U, device, VAE_flag=False, activation='elu', fuse_pool=True,
+                 reorder=True):
         super().__init__()
         self.newskl_list = DEFAULT_NEWSKL_LIST
         self.kps_keep = [i for i in range(len(self.newskl_list) + 4) if i not in (3, 13, 14)]
@@ -262,7 +307,7 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
                 [nn.Linear(len(k) * 3, part_kps_latent_size).to(device) for k in kps_index_list])
 
         self._init_trunk(filters_enc, filters_dec, sizes, spiral_sizes, spirals, D, U, device, activation, fuse_pool,
-                         heads)
+                         heads, reorder)
         dev = torch.device(device)
         self._part_idx = [torch.as_tensor(p, dtype=torch.long, device=dev) for p in parts]
         self._kps_idx = [torch.as_tensor(k, dtype=torch.long, device=dev) for k in kps_index_list]
