@@ -110,24 +110,58 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
   // ---------------------------------------------------------------- prologue: weights -> smem (core-matrix layout)
   {
     const int total_chunks = p.NPAD * p.Q;
-    for (int i = tid; i < total_chunks; i += NTH) {
-      const int n = i / p.Q, q = i - n * p.Q;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (n < p.Cd) {
-        if (!SUM) {
-          v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)n * K + (size_t)q * 8));
-        } else {
-          // Bop[n][s*CS + co] = W[co*(S*Cd) + s*Cd + n]
-          const int k0 = q * 8, s = k0 / CS, co0 = k0 - s * CS;
+    if (!SUM) {
+      for (int i = tid; i < total_chunks; i += NTH) {
+        const int n = i / p.Q, q = i - n * p.Q;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (n < p.Cd) v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)n * K + (size_t)q * 8));
+        *reinterpret_cast<uint4*>(w_img + ((size_t)(n >> 3) * p.Q + q) * 128 + (n & 7) * 16) = v;
+      }
+    } else if ((p.Cd & 7) == 0) {
+      // Bop[n][s*CS + co] = W[co*(S*Cd) + s*Cd + n]: the operand is W transposed per slot.  A thread takes an 8 (co) x 8 (n)
+      // block: eight 16-byte loads along n (consecutive lanes -> consecutive n blocks: coalesced), an in-register transpose,
+      // eight 16-byte stores (one per n, contiguous 128 B).  The scalar version below issued 8 uncoalesced 2-byte loads per
+      // chunk, ~100 us of prologue per CTA on the 128-channel layers.
+      const int NB = p.NPAD >> 3, blocks = NB * p.Q;
+      const size_t rs = (size_t)p.S * p.Cd;
+      for (int i = tid; i < blocks; i += NTH) {
+        const int q = i / NB, nb = i - q * NB, n0 = nb * 8;
+        const int k0 = q * 8, sl = k0 / CS, co0 = k0 - sl * CS;
+        uint4 r[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          r[t] = n0 < p.Cd ? __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)(co0 + t) * rs + (size_t)sl * p.Cd + n0))
+                           : make_uint4(0, 0, 0, 0);
+        uint8_t* dst = w_img + ((size_t)nb * p.Q + q) * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+          uint32_t wv[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r[t]);
+            wv[t] = rw[j >> 1];
+          }
+          *reinterpret_cast<uint4*>(dst + j * 16) =
+              make_uint4(__byte_perm(wv[0], wv[1], sel), __byte_perm(wv[2], wv[3], sel), __byte_perm(wv[4], wv[5], sel),
+                         __byte_perm(wv[6], wv[7], sel));
+        }
+      }
+    } else {
+      for (int i = tid; i < total_chunks; i += NTH) {
+        const int q = i / p.NPAD, n = i - q * p.NPAD;  // n fastest: the 2-byte loads of a warp are contiguous
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (n < p.Cd) {
+          const int k0 = q * 8, sl = k0 / CS, co0 = k0 - sl * CS;
           const unsigned short* wu = reinterpret_cast<const unsigned short*>(p.w);
           const size_t rs = (size_t)p.S * p.Cd;
           uint32_t e[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) e[t] = __ldg(wu + (size_t)(co0 + t) * rs + (size_t)s * p.Cd + n);
+          for (int t = 0; t < 8; ++t) e[t] = __ldg(wu + (size_t)(co0 + t) * rs + (size_t)sl * p.Cd + n);
           v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
         }
+        *reinterpret_cast<uint4*>(w_img + ((size_t)(n >> 3) * p.Q + q) * 128 + (n & 7) * 16) = v;
       }
-      *reinterpret_cast<uint4*>(w_img + ((size_t)(n >> 3) * p.Q + q) * 128 + (n & 7) * 16) = v;
     }
     if (tid < 256) bias_s[tid] = (p.bias != nullptr && tid < p.Cd) ? __ldg(p.bias + tid) : 0.f;
     fence_proxy_async_smem();
