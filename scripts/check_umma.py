@@ -10,7 +10,7 @@ B = int(os.environ.get("B", "5"))
 h = Hierarchy("2222")
 dev = "cuda:0"
 layers = [(1, 16, 32, "elu"), (2, 32, 64, "elu"), (3, 64, 128, "elu"), (3, 128, 64, "elu"), (2, 64, 32, "elu"),
-          (1, 32, 32, "tanh"), (0, 32, 16, "elu"), (0, 16, 3, "identity"), (0, 16, 16, "relu")]
+          (1, 32, 32, "tanh"), (0, 32, 16, "elu"), (0, 16, 3, "identity"), (0, 16, 16, "relu"), (0, 3, 16, "elu"), (2, 3, 8, "elu")]
 gen = torch.Generator(device=dev).manual_seed(0)
 worst = 0
 for lvl, cin, cout, act in layers:

@@ -467,7 +467,8 @@ constexpr size_t UG_SMEM_MAX = 227 * 1024 - 2048;  // leave room for the static 
 static int ug_npad(int Cd) { return ((Cd + 15) / 16) * 16; }
 
 bool umma_gather_gemm_supported(int Cs, int Cd, int S) {
-  if (!(Cs == 16 || Cs == 32 || Cs == 64 || Cs == 128)) return false;
+  if (!(Cs == 8 || Cs == 16 || Cs == 32 || Cs == 64 || Cs == 128)) return false;
+  if ((S * Cs / 8) & 1) return false;  // an MMA consumes two 16-byte K chunks
   const int NPAD = ug_npad(Cd);
   if (NPAD > 256 || Cd > 256) return false;
   if (S > 16) return false;  // per-tile index block: 8 entries per producer thread
@@ -539,6 +540,7 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* keypt
   case CSV:                                                                                \
     return sum_mode ? ug_launch<CSV, true>(p, smem, ctas_per_sm, st) : ug_launch<CSV, false>(p, smem, ctas_per_sm, st);
   switch (Cs) {
+    UG_DISPATCH(8)
     UG_DISPATCH(16)
     UG_DISPATCH(32)
     UG_DISPATCH(64)
@@ -781,7 +783,7 @@ struct UWPlan { int bkm, nstage, KT, NPAD, grid; size_t smem; uint32_t cols; boo
 static UWPlan uw_plan(int Cin, int Cout, int S) {
   UWPlan pl{};
   pl.ok = false;
-  if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
+  if (!(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
   if ((Cout & 7) != 0) return pl;  // gz rows must be whole 16-byte chunks for cp.async
   pl.NPAD = ug_npad(Cout);
   const int K = S * Cin;
@@ -854,6 +856,7 @@ int umma_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, f
                 : (pl.bkm == 32 ? uw_launch<C, 32, 16, 1>(p, grid, pl.smem, st) : uw_launch<C, 16, 16, 1>(p, grid, pl.smem, st)); \
     break;
   switch (Cin) {
+    UW_DISPATCH(8)
     UW_DISPATCH(16)
     UW_DISPATCH(32)
     UW_DISPATCH(64)

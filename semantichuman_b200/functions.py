@@ -93,6 +93,14 @@ def _pad16(c):
     return (c + 15) // 16 * 16
 
 
+def _pad_bf16(c, S):
+    """Channel count the tcgen05 kernels take for a c-channel operand: a multiple of 16, or 8 (one 16-byte chunk per
+    gathered row -- the 3-channel mesh coordinates) when the spiral length is even (an MMA consumes two chunks of K)."""
+    if c % 16 == 0:
+        return c
+    return 8 if (c <= 8 and S % 2 == 0) else _pad16(c)
+
+
 def pad_channels(x, cp, out_dtype=None):
     """(…, C) -> (…, cp) zero-padded along the channel axis (+ optional fp32<->bf16 cast) in one kernel."""
     out_dtype = x.dtype if out_dtype is None else out_dtype
@@ -111,8 +119,8 @@ class SpiralConvFn(torch.autograd.Function):
     act' kernel + weight-gradient kernel (+ fixed-order reduce) + inverse-table input-gradient kernel.
 
     bf16 mode: operands whose channel count is not a multiple of 16 (the 3-channel mesh coordinates at both ends of
-    the autoencoder) are zero-padded to 16 so that every layer takes the tcgen05 path (16-byte gather chunks, UMMA
-    K = 16); the padding never leaves this function (gradients are sliced back)."""
+    the autoencoder) are zero-padded to 8 (even spiral length) or 16 so that every layer takes the tcgen05 path
+    (16-byte gather chunks, UMMA K = 16); the padding never leaves this function (gradients are sliced back)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, geom, act, compute_dtype):
@@ -128,7 +136,7 @@ class SpiralConvFn(torch.autograd.Function):
         if geom.table.device != x.device:
             raise RuntimeError("spiral tables live on a different device than x")
         S = geom.S
-        cin_p = _pad16(cin) if (cdt == torch.bfloat16 and cin % 16) else cin
+        cin_p = _pad_bf16(cin, S) if cdt == torch.bfloat16 else cin
         if cin_p != cin or x.dtype != cdt:
             xk = pad_channels(x, cin_p, cdt)  # pad and/or cast in one pass
         else:
@@ -160,7 +168,7 @@ class SpiralConvFn(torch.autograd.Function):
             gy = gy.to(x.dtype)
         dt, st = _dt(x), _stream()
         bf16 = x.dtype == torch.bfloat16
-        cout_p = _pad16(cout) if (bf16 and cout % 8) else cout
+        cout_p = _pad_bf16(cout, S) if (bf16 and cout % 8) else cout
         gz = torch.empty((B, geom.rows_out, cout_p), dtype=x.dtype, device=x.device)
         tag = f"[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]"
         meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, x.element_size())
