@@ -304,7 +304,12 @@ def run_own(args):
     traffic = NCU_TRAFFIC_BYTES.get(top_name) if args.dtype == "bf16" and B == 256 else None
     roof.update({"instrumented_ms_per_step": ms_instr / args.steps,
                  "traffic": None if traffic is None else traffic[0],
-                 "traffic_source": None if traffic is None else traffic[1], "kernel": top_name, "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / ms_instr,
+                 "traffic_source": None if traffic is None else traffic[1], "kernel": top_name, "avg_launch_ms": avg_ms,
+                 # share of the (clean, graph-replayed) step this kernel accounts for; the instrumented eager pass is
+                 # longer than the clean step (event pairs, host gaps), so its own wall time is not the denominator
+                 "share_of_step": (top["ms"] / args.steps) / (ms / args.steps),
+                 "kernel_family_share": sum(v["ms"] for k, v in per.items() if k.split("[")[0] == top_name.split("[")[0])
+                 / args.steps / (ms / args.steps),
                  "peak_source": peaks["source"] + " (sustained figures: kernel timed inside a long step)",
                  "arith_intensity_flop_per_byte": ai})
     kernels = sorted(((k, v["ms"] / args.steps) for k, v in per.items()), key=lambda kv: -kv[1])
