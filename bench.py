@@ -30,9 +30,9 @@ METRIC = "train meshes/sec (6890-vert SpiralAE fwd+bwd)"
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can come out on top, from the
 # ncu --set full captures summarised under profiles/ (B=256, bf16).  key = the timer tag bench.py reports as roofline.kernel
 NCU_TRAFFIC_BYTES = {
-    "spiralconv_bwd_dgrad[6891>6891x14x32>16]": (57.39e6 + 67.35e6, "profiles/r01_e_ncu_fwd_and_dgrad.csv"),
-    "spiralconv_fwd[6891>6891x14x32>16]": (113.37e6 + 35.14e6, "profiles/r01_e_ncu_fwd_and_dgrad.csv"),
-    "spiralconv_bwd_wgrad[6891>6891x14x32>16]": (230.23e6 + 3.88e6, "profiles/r01_b_ncu_umma_first.csv"),
+    "spiralconv_bwd_dgrad[6891>6891x14x32>16]": (57.34e6 + 59.71e6, "profiles/r01_g_ncu_final_l0.csv"),
+    "spiralconv_fwd[6891>6891x14x32>16]": (113.38e6 + 33.43e6, "profiles/r01_g_ncu_final_l0.csv"),
+    "spiralconv_bwd_wgrad[6891>6891x14x32>16]": (324.22e6 + 4.81e6, "profiles/r01_g_ncu_final_l0.csv"),
 }
 N_INPUT_BATCHES = 8  # distinct resident batches rotated through the timed loop
 
