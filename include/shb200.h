@@ -160,6 +160,30 @@ int shb_partnorm_loss_fwd_bwd(const float* z, const float* measure, const int32_
                               float* gz, int B, int n_parts, int L, int n_measure, int n_sel, int relative,
                               void* stream);
 
+/* ---- Bone-guided heads as grouped kernels (models.py:200-204, 233-236, 252-253, 269-273): the 17+17+17 per-part
+ * nn.Linear layers, their fancy-index gathers, the permutation scatter of models.py:270-272 and the biases, one launch
+ * per direction.  Group k owns rows idx[gptr[k] .. gptr[k+1]) of a (B, rows, C) fp32 tensor (n_k rows); its weight and
+ * bias start at w + woff[k] / bias + boff[k] of packed fp32 buffers in nn.Linear layout.  idx, gptr int32 and woff, boff
+ * int64 are device arrays.  fp32 only; L, Lin <= 32; B <= 65535.  Fixed-order reductions (no float atomics).
+ *
+ * gather form  (fc_latent_enc_list / kps_enc_list):  z[b,k,o] = bias_k[o] + sum_{p,c} W_k[o, p*C+c] * x[b, idx[gptr[k]+p], c]
+ *   W_k (L, n_k*C).  bwd: gx (B, rows, C) -- rows outside every group are zeroed; groups must not overlap when gx is
+ *   requested -- gw (packed like w), gb (packed like bias); each may be NULL.  max_group_rows = max_k n_k.
+ * scatter form (fc_latent_dec_list + models.py:270-272):  y[b, idx[gptr[k]+p], c] = bias_k[p*C+c] + sum_i W_k[p*C+c, i] * zz[b,k,i]
+ *   W_k (n_k*C, Lin); rows of y outside every group are left untouched.  bwd: gzz (B, G, Lin), gw, gb; each may be NULL. */
+int shb_group_linear_gather_fwd(const float* x, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                const float* bias, const int64_t* boff, float* z, int B, int rows, int C, int G, int L,
+                                void* stream);
+int shb_group_linear_gather_bwd(const float* x, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                const int64_t* boff, const float* gz, float* gx, float* gw, float* gb, int B, int rows, int C,
+                                int G, int L, int max_group_rows, void* stream);
+int shb_group_linear_scatter_fwd(const float* zz, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                 const float* bias, const int64_t* boff, float* y, int B, int rows, int C, int G, int Lin,
+                                 void* stream);
+int shb_group_linear_scatter_bwd(const float* zz, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                 const int64_t* boff, const float* gy, float* gzz, float* gw, float* gb, int B, int rows, int C,
+                                 int G, int Lin, int max_group_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

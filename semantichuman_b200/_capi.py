@@ -32,6 +32,10 @@ SIGNATURES = {
     "shb_l1_loss_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_size, c_vp, c_int, c_vp]),
     "shb_l1_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
     "shb_partnorm_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_group_linear_gather_fwd": (c_int, [c_vp] * 8 + [c_int] * 5 + [c_vp]),
+    "shb_group_linear_gather_bwd": (c_int, [c_vp] * 10 + [c_int] * 6 + [c_vp]),
+    "shb_group_linear_scatter_fwd": (c_int, [c_vp] * 8 + [c_int] * 5 + [c_vp]),
+    "shb_group_linear_scatter_bwd": (c_int, [c_vp] * 10 + [c_int] * 6 + [c_vp]),
 }
 
 ACT_ENUM = {"identity": 0, "relu": 1, "elu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5}

@@ -1,0 +1,224 @@
+// Bone-guided heads as grouped kernels (models.py:200-204, 233-236, 252-253, 269-273).
+//
+// The reference runs 17 + 17 + 17 tiny nn.Linear layers from Python list comprehensions, each on a fancy-indexed copy of
+// the coarsest-level features, then scatters the decoder pieces back with a permutation and concatenates the dummy row.
+// Here a "group" k owns the rows idx[gptr[k] .. gptr[k+1]) of a (B, rows, C) tensor; its weight and bias live at
+// w + woff[k] and bias + boff[k] of packed fp32 buffers (nn.Linear layout, row-major):
+//
+//   gather ("encode") form :  z[b,k,o]         = bias_k[o] + sum_{p,c} W_k[o, p*C+c] * x[b, idx[gptr[k]+p], c]     W_k (L, n_k*C)
+//   scatter ("decode") form:  y[b,idx[..+p],c] = bias_k[p*C+c] + sum_i W_k[p*C+c, i] * zz[b,k,i]                   W_k (n_k*C, Lin)
+//
+// One launch per direction instead of 17; the gathers, the permutation scatter and the bias are folded into the kernels.
+// All reductions run in a fixed order (no float atomics).  fp32 only: the heads stay fp32 in both compute modes.
+#include "shb_common.cuh"
+
+namespace shb {
+
+constexpr int GL_MAX = 32;      // widest latent side (L, Lin) the register accumulators hold
+constexpr int GL_THREADS = 128;
+
+// ---- gather form, forward (also: scatter form, gradient w.r.t. zz -- same contraction, no bias)
+// grid (G, B).  out[b,k,o] = (bias ? bias_k[o] : 0) + sum_j Wt(o,j) * v[b,j]  where  v[b, p*C+c] = x[b, idx[g0+p], c]  and
+// Wt(o,j) = w_k[o*K + j]  (w_is_KxL == 0)   or   w_k[j*L + o]  (w_is_KxL != 0: the decode weight read transposed).
+__global__ void __launch_bounds__(GL_THREADS) gl_contract_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                                                 const int32_t* __restrict__ gptr, const float* __restrict__ w,
+                                                                 const int64_t* __restrict__ woff, const float* __restrict__ bias,
+                                                                 const int64_t* __restrict__ boff, float* __restrict__ out,
+                                                                 int rows, int C, int G, int L, int w_is_KxL) {
+  __shared__ float red[GL_THREADS / 32][GL_MAX];
+  const int k = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int g0 = gptr[k], n = gptr[k + 1] - g0, K = n * C;
+  const float* wk = w + woff[k];
+  const float* xb = x + (size_t)b * rows * C;
+  float acc[GL_MAX];
+#pragma unroll
+  for (int o = 0; o < GL_MAX; ++o) acc[o] = 0.f;
+  for (int j = t; j < K; j += GL_THREADS) {
+    const int p = j / C, c = j - p * C;
+    const float v = xb[(size_t)__ldg(idx + g0 + p) * C + c];
+    if (w_is_KxL) {
+#pragma unroll
+      for (int o = 0; o < GL_MAX; ++o)
+        if (o < L) acc[o] = fmaf(__ldg(wk + (size_t)j * L + o), v, acc[o]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < GL_MAX; ++o)
+        if (o < L) acc[o] = fmaf(__ldg(wk + (size_t)o * K + j), v, acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < GL_MAX; ++o) {
+    if (o < L) {  // L is uniform across the block
+      const float s = warp_sum(acc[o]);
+      if ((t & 31) == 0) red[t >> 5][o] = s;
+    }
+  }
+  __syncthreads();
+  if (t < L) {
+    float s = bias ? __ldg(bias + boff[k] + t) : 0.f;
+#pragma unroll
+    for (int q = 0; q < GL_THREADS / 32; ++q) s += red[q][t];
+    out[((size_t)b * G + k) * L + t] = s;
+  }
+}
+
+// ---- scatter form, forward (also: gather form, gradient w.r.t. x -- same expansion, no bias)
+// grid (G, B).  y[b, idx[g0+p], c] = (bias ? bias_k[j] : 0) + sum_i Wt(j,i) * zz[b,k,i],  j = p*C+c,
+// Wt(j,i) = w_k[j*L + i]  (w_is_KxL != 0)   or   w_k[i*K + j]  (the encode weight read transposed).
+__global__ void __launch_bounds__(GL_THREADS) gl_expand_kernel(const float* __restrict__ zz, const int32_t* __restrict__ idx,
+                                                               const int32_t* __restrict__ gptr, const float* __restrict__ w,
+                                                               const int64_t* __restrict__ woff, const float* __restrict__ bias,
+                                                               const int64_t* __restrict__ boff, float* __restrict__ y, int rows,
+                                                               int C, int G, int L, int w_is_KxL) {
+  __shared__ float zs[GL_MAX];
+  const int k = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int g0 = gptr[k], n = gptr[k + 1] - g0, K = n * C;
+  const float* wk = w + woff[k];
+  if (t < L) zs[t] = zz[((size_t)b * G + k) * L + t];
+  __syncthreads();
+  float* yb = y + (size_t)b * rows * C;
+  for (int j = t; j < K; j += GL_THREADS) {
+    const int p = j / C, c = j - p * C;
+    float a = bias ? __ldg(bias + boff[k] + j) : 0.f;
+    if (w_is_KxL) {
+      for (int i = 0; i < L; ++i) a = fmaf(__ldg(wk + (size_t)j * L + i), zs[i], a);
+    } else {
+      for (int i = 0; i < L; ++i) a = fmaf(__ldg(wk + (size_t)i * K + j), zs[i], a);
+    }
+    yb[(size_t)__ldg(idx + g0 + p) * C + c] = a;
+  }
+}
+
+// ---- weight (and scatter-form bias) gradients: one thread per K index j, sequential over the batch (fixed order)
+// grid (G, ceil(Kmax / GL_THREADS)).  gw_k(o,j) = sum_b g[b,k,o] * v[b,j]  with v gathered from x as above;
+// stored at gw_k[o*K + j] (w_is_KxL == 0) or gw_k[j*L + o].  gbias_j (scatter form only): gbk[j] = sum_b v[b,j].
+__global__ void __launch_bounds__(GL_THREADS) gl_wgrad_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                                              const int32_t* __restrict__ gptr, const float* __restrict__ g,
+                                                              const int64_t* __restrict__ woff, const int64_t* __restrict__ boff,
+                                                              float* __restrict__ gw, float* __restrict__ gbias_j, int B,
+                                                              int rows, int C, int G, int L, int w_is_KxL) {
+  __shared__ float gs[GL_MAX];
+  const int k = blockIdx.x, t = threadIdx.x;
+  const int g0 = gptr[k], n = gptr[k + 1] - g0, K = n * C;
+  const int j = blockIdx.y * GL_THREADS + t;
+  const bool on = j < K;  // block-uniform exit is not possible (the barrier below): inactive threads just idle
+  const int p = on ? j / C : 0, c = on ? j - p * C : 0;
+  const size_t col = on ? (size_t)__ldg(idx + g0 + p) * C + c : 0;
+  if ((int)blockIdx.y * GL_THREADS >= K) return;  // whole block beyond this group's K
+  float acc[GL_MAX];
+#pragma unroll
+  for (int o = 0; o < GL_MAX; ++o) acc[o] = 0.f;
+  float vs = 0.f;
+  for (int b = 0; b < B; ++b) {
+    __syncthreads();
+    if (t < L) gs[t] = g[((size_t)b * G + k) * L + t];
+    __syncthreads();
+    if (on) {
+      const float v = x[(size_t)b * rows * C + col];
+      vs += v;
+#pragma unroll
+      for (int o = 0; o < GL_MAX; ++o)
+        if (o < L) acc[o] = fmaf(gs[o], v, acc[o]);
+    }
+  }
+  if (!on) return;
+  float* gwk = gw + woff[k];
+#pragma unroll
+  for (int o = 0; o < GL_MAX; ++o)
+    if (o < L) gwk[w_is_KxL ? (size_t)j * L + o : (size_t)o * K + j] = acc[o];
+  if (gbias_j) gbias_j[boff[k] + j] = vs;
+}
+
+// gather-form bias gradient: gb_k[o] = sum_b g[b,k,o]; one block per group
+__global__ void __launch_bounds__(GL_THREADS) gl_bias_kernel(const float* __restrict__ g, const int64_t* __restrict__ boff,
+                                                             float* __restrict__ gb, int B, int G, int L) {
+  const int k = blockIdx.x, t = threadIdx.x;
+  if (t >= L) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += g[((size_t)b * G + k) * L + t];
+  gb[boff[k] + t] = s;
+}
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+static int gl_args_ok(const void* a, const void* b, const void* c, const void* d, const void* e, int B, int rows, int C, int G,
+                      int L) {
+  if (!a || !b || !c || !d || !e) return SHB_E_ARG;
+  if (B <= 0 || rows <= 0 || C <= 0 || G <= 0 || L <= 0) return SHB_E_ARG;
+  if (L > GL_MAX || B > 65535) return SHB_E_SHAPE;
+  return 0;
+}
+
+int shb_group_linear_gather_fwd(const float* x, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                const float* bias, const int64_t* boff, float* z, int B, int rows, int C, int G, int L,
+                                void* stream) {
+  int rc = gl_args_ok(x, idx, gptr, w, woff, B, rows, C, G, L);
+  if (rc) return rc;
+  if (!z || (bias && !boff)) return SHB_E_ARG;
+  gl_contract_kernel<<<dim3(G, B), GL_THREADS, 0, (cudaStream_t)stream>>>(x, idx, gptr, w, woff, bias, boff, z, rows, C, G, L, 0);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_group_linear_gather_bwd(const float* x, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                const int64_t* boff, const float* gz, float* gx, float* gw, float* gb, int B, int rows, int C,
+                                int G, int L, int max_group_rows, void* stream) {
+  int rc = gl_args_ok(x, idx, gptr, w, woff, B, rows, C, G, L);
+  if (rc) return rc;
+  if (!gz || max_group_rows <= 0) return SHB_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gx) {  // rows outside every group (the dummy row) get zero
+    cudaError_t e = cudaMemsetAsync(gx, 0, (size_t)B * rows * C * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    gl_expand_kernel<<<dim3(G, B), GL_THREADS, 0, st>>>(gz, idx, gptr, w, woff, nullptr, nullptr, gx, rows, C, G, L, 0);
+    SHB_LAUNCH_CHECK();
+  }
+  if (gw) {
+    const int kb = (max_group_rows * C + GL_THREADS - 1) / GL_THREADS;
+    gl_wgrad_kernel<<<dim3(G, kb), GL_THREADS, 0, st>>>(x, idx, gptr, gz, woff, nullptr, gw, nullptr, B, rows, C, G, L, 0);
+    SHB_LAUNCH_CHECK();
+  }
+  if (gb) {
+    if (!boff) return SHB_E_ARG;
+    gl_bias_kernel<<<G, GL_THREADS, 0, st>>>(gz, boff, gb, B, G, L);
+    SHB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int shb_group_linear_scatter_fwd(const float* zz, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                 const float* bias, const int64_t* boff, float* y, int B, int rows, int C, int G, int Lin,
+                                 void* stream) {
+  int rc = gl_args_ok(zz, idx, gptr, w, woff, B, rows, C, G, Lin);
+  if (rc) return rc;
+  if (!y || (bias && !boff)) return SHB_E_ARG;
+  gl_expand_kernel<<<dim3(G, B), GL_THREADS, 0, (cudaStream_t)stream>>>(zz, idx, gptr, w, woff, bias, boff, y, rows, C, G, Lin, 1);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_group_linear_scatter_bwd(const float* zz, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                                 const int64_t* boff, const float* gy, float* gzz, float* gw, float* gb, int B, int rows, int C,
+                                 int G, int Lin, int max_group_rows, void* stream) {
+  int rc = gl_args_ok(zz, idx, gptr, w, woff, B, rows, C, G, Lin);
+  if (rc) return rc;
+  if (!gy || max_group_rows <= 0) return SHB_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gzz) {
+    gl_contract_kernel<<<dim3(G, B), GL_THREADS, 0, st>>>(gy, idx, gptr, w, woff, nullptr, nullptr, gzz, rows, C, G, Lin, 1);
+    SHB_LAUNCH_CHECK();
+  }
+  if (gw || gb) {
+    if (!gw || (gb && !boff)) return SHB_E_ARG;
+    const int kb = (max_group_rows * C + GL_THREADS - 1) / GL_THREADS;
+    gl_wgrad_kernel<<<dim3(G, kb), GL_THREADS, 0, st>>>(gy, idx, gptr, zz, woff, boff, gw, gb, B, rows, C, G, Lin, 1);
+    SHB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // extern "C"

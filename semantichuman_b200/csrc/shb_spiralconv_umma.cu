@@ -7,8 +7,9 @@
 //
 // Persistent warp-specialised CTAs (one or two per SM), 128-row tiles:
 //   * the whole weight operand lives in shared memory for the lifetime of the CTA (un-swizzled K-major core-matrix layout);
-//   * 8 producer warps gather 16-byte channel chunks of neighbour rows straight into the K-major core-matrix layout of a
-//     multi-stage A ring -- cp.async (LDGSTS) for the forward gather, register gather-sum (fixed order, no atomics) for dgrad;
+//   * 8 (forward) or 16 (dgrad) producer warps gather 16-byte channel chunks of neighbour rows straight into the K-major
+//     core-matrix layout of a multi-stage A ring -- cp.async (LDGSTS) for the forward gather, a register gather-sum
+//     (packed bf16 adds in a fixed order, no atomics) for dgrad; the tile's index block is staged per warp in shared memory;
 //   * one thread issues tcgen05.mma (M=128, N=Cd, K=16 per instruction) into a double-buffered TMEM accumulator and
 //     releases A stages / publishes accumulators with tcgen05.commit -> mbarrier;
 //   * 4 epilogue warps read the accumulator with tcgen05.ld, apply bias + activation + dummy-row mask, and store bf16.
@@ -40,11 +41,7 @@ constexpr int UG_THREADS = (UG_EPI_WARPS + 1 + UG_PROD_WARPS) * 32;
 constexpr int ug_prod_warps(bool sum) { return sum ? 16 : 8; }
 constexpr int ug_threads(bool sum) { return (UG_EPI_WARPS + 1 + ug_prod_warps(sum)) * 32; }
 constexpr int UG_MAX_STAGES = 8;
-// A producer thread keeps this many cp.async groups (stages) in flight behind the one it is issuing; a stage is
-// published (one mbarrier arrival per WARP -- per-thread arrivals serialise on the barrier at ~16 cycles each) once
-// cp.async.wait_group says it has landed.  Must be < ring depth.
-constexpr int UG_LAG = 2;
-constexpr int UG_IDX_PER_THREAD = 16;  // per-tile index block: 128 rows x (S or 2S) entries <= 16 * 256
+constexpr int UG_MIN_STAGES = 3;       // shallowest A ring the kernels are launched with
 
 struct UGParams {
   const __nv_bfloat16* src;  // (B, rows_src, CS)
@@ -65,7 +62,6 @@ struct UGParams {
   int skip_last;  // gather-sum: destination dummy row not computed.  forward: source dummy row is known zero (zero-fill)
   long long* trace;  // debug timeline (CTA 0): [role 0..2][event 0..3][512] clock64 stamps, or null
   int dbg;      // SHB_UMMA_DEBUG bitmask (perf bisection only): 1 skip copies, 2 skip MMAs, 4 skip epilogue stores
-  int noinc;    // 1: per-thread cp.async.mbarrier.arrive.noinc (no fence); 0: wait_group + proxy fence + per-warp arrive
   uint32_t tmem_cols;
 };
 
@@ -247,7 +243,9 @@ __global__ void __launch_bounds__(ug_threads(SUM), SUM ? 1 : 2) umma_gather_gemm
           UG_TRACE(1, 0, st);
           mbar_wait_backoff(&full_bar[slot], ph, 20);
           UG_TRACE(1, 1, st);
-          if (SUM) fence_proxy_async_smem();  // producers wrote this stage with generic st.shared (see the producer loop)
+          // producers fill the stage through the generic proxy (cp.async / st.shared); tcgen05.mma reads it through the
+          // async proxy: the cross-proxy fence sits here, after the acquire, on the one consuming thread
+          fence_proxy_async_smem();
           tc_fence_after();
           if (!(p.dbg & 2)) {
             if (left >= UG_KC) {
@@ -472,7 +470,7 @@ bool umma_gather_gemm_supported(int Cs, int Cd, int S) {
   const int NPAD = ug_npad(Cd);
   if (NPAD > 256 || Cd > 256) return false;
   if (S > 16) return false;  // per-tile index block: 8 entries per producer thread
-  return ug_smem_bytes(NPAD, S * Cs / 8, UG_LAG + 1, S) <= UG_SMEM_MAX;
+  return ug_smem_bytes(NPAD, S * Cs / 8, UG_MIN_STAGES, S) <= UG_SMEM_MAX;
 }
 
 template <int CS, bool SUM> static int ug_launch(const UGParams& p, size_t smem, int want_per_sm, cudaStream_t st) {
@@ -519,14 +517,12 @@ int umma_gather_gemm(const void* src, const int32_t* table, const int32_t* keypt
   p.num_tiles = (int)((p.M + UG_BM - 1) / UG_BM);
   p.act = act; p.zero_last = zero_last; p.skip_last = skip_last;
   {
-    static const int mode = [] { const char* e = getenv("SHB_UMMA_NOINC"); return (e && e[0] == '0') ? 0 : 1; }();
-    p.noinc = mode;
     static const int dbg = [] { const char* e = getenv("SHB_UMMA_DEBUG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
     p.trace = g_trace;
   }
   int nstage = 6;
-  while (nstage > UG_LAG + 1 && ug_smem_bytes(p.NPAD, p.Q, nstage, S, sum_mode) > UG_SMEM_MAX) --nstage;
+  while (nstage > UG_MIN_STAGES && ug_smem_bytes(p.NPAD, p.Q, nstage, S, sum_mode) > UG_SMEM_MAX) --nstage;
   // two CTAs per SM when both fit with a deep enough ring: more gathers in flight
   int ctas_per_sm = 1;
   if (!sum_mode && ug_smem_bytes(p.NPAD, p.Q, 4, S, false) * 2 + 4096 <= UG_SMEM_MAX) { ctas_per_sm = 2; nstage = 4; }

@@ -296,6 +296,131 @@ class PartNormLossFn(torch.autograd.Function):
         return gz * g, None, None, None, None
 
 
+class GroupLayout:
+    """Device-side description of a set of row groups (the body parts of the bone-guided model) and of the packed
+    parameter buffers of their per-group nn.Linear layers: idx/gptr (int32), weight/bias offsets (int64)."""
+
+    def __init__(self, groups, rows, channels, latent, gather, device):
+        import numpy as np
+
+        self.G, self.rows, self.C, self.L, self.gather = len(groups), int(rows), int(channels), int(latent), bool(gather)
+        sizes = [len(g) for g in groups]
+        self.sizes, self.max_rows = sizes, max(sizes)
+        flat = np.concatenate([np.asarray(g, dtype=np.int64) for g in groups])
+        if flat.min() < 0 or flat.max() >= rows:
+            raise ValueError("group row index out of range")
+        self.disjoint = len(np.unique(flat)) == len(flat)
+        self.w_numel = [n * channels * latent for n in sizes]
+        self.b_numel = [latent if gather else n * channels for n in sizes]
+        dev = torch.device(device)
+        self.idx = torch.as_tensor(flat, dtype=torch.int32, device=dev)
+        self.gptr = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32, device=dev)
+        self.woff = torch.as_tensor(np.concatenate([[0], np.cumsum(self.w_numel)[:-1]]), dtype=torch.int64, device=dev)
+        self.boff = torch.as_tensor(np.concatenate([[0], np.cumsum(self.b_numel)[:-1]]), dtype=torch.int64, device=dev)
+
+    def supported(self):
+        return self.L <= 32
+
+    def pack(self, layers):
+        """Packed (weight, bias) buffers of the group's nn.Linear layers; differentiable (torch.cat)."""
+        for lay, wn in zip(layers, self.w_numel):
+            if lay.weight.numel() != wn:
+                raise ValueError("per-group Linear shape does not match the group layout")
+        return (torch.cat([lay.weight.reshape(-1) for lay in layers]), torch.cat([lay.bias.reshape(-1) for lay in layers]))
+
+
+class GroupLinearGatherFn(torch.autograd.Function):
+    """z[b,k,:] = Linear_k(x[b, idx_k, :].reshape(-1))  for every group k in one launch (models.py:234,252)."""
+
+    @staticmethod
+    def forward(ctx, x, wcat, bcat, lay):
+        _cuda(x, wcat, bcat)
+        x, wcat, bcat = x.float().contiguous(), wcat.float().contiguous(), bcat.float().contiguous()
+        B = x.shape[0]
+        if x.shape[1] != lay.rows or x.shape[2] != lay.C:
+            raise ValueError(f"grouped linear expects (B, {lay.rows}, {lay.C}), got {tuple(x.shape)}")
+        z = torch.empty((B, lay.G, lay.L), dtype=torch.float32, device=x.device)
+        _call("group_linear_gather", {"bytes": 4.0 * (x.numel() + wcat.numel() + z.numel())}, lib.shb_group_linear_gather_fwd,
+              _p(x), _p(lay.idx), _p(lay.gptr), _p(wcat), _p(lay.woff), _p(bcat), _p(lay.boff), _p(z), B, lay.rows, lay.C,
+              lay.G, lay.L, _stream())
+        _count()
+        ctx.save_for_backward(x, wcat)
+        ctx.lay = lay
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, wcat = ctx.saved_tensors
+        lay = ctx.lay
+        gz = gz.float().contiguous()
+        B = x.shape[0]
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        if need_x and not lay.disjoint:
+            raise RuntimeError("input gradient of a grouped linear needs non-overlapping groups")
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty_like(wcat) if need_w else None
+        gb = torch.empty(sum(lay.b_numel), dtype=torch.float32, device=x.device) if need_b else None
+        _call("group_linear_gather_bwd", {"bytes": 4.0 * (2 * x.numel() + 2 * wcat.numel())}, lib.shb_group_linear_gather_bwd,
+              _p(x), _p(lay.idx), _p(lay.gptr), _p(wcat), _p(lay.woff), _p(lay.boff), _p(gz), _p(gx), _p(gw), _p(gb), B,
+              lay.rows, lay.C, lay.G, lay.L, lay.max_rows, _stream())
+        _count(int(need_x) + int(need_w) + int(need_b))
+        return gx, gw, gb, None
+
+
+class GroupLinearScatterFn(torch.autograd.Function):
+    """y[b, idx_k[p], :] = Linear_k(zz[b,k,:])[p*C:(p+1)*C]  for every group, plus `extra` written to the last row
+    (models.py:269-273: per-part decode, permutation scatter, dummy-row concat) -- one launch."""
+
+    @staticmethod
+    def forward(ctx, zz, wcat, bcat, extra, lay):
+        _cuda(zz, wcat, bcat, extra)
+        zz, wcat, bcat = zz.float().contiguous(), wcat.float().contiguous(), bcat.float().contiguous()
+        B = zz.shape[0]
+        if zz.shape[1] != lay.G or zz.shape[2] != lay.L:
+            raise ValueError(f"grouped linear expects (B, {lay.G}, {lay.L}), got {tuple(zz.shape)}")
+        y = torch.zeros((B, lay.rows, lay.C), dtype=torch.float32, device=zz.device)
+        _call("group_linear_scatter", {"bytes": 4.0 * (zz.numel() + wcat.numel() + y.numel())}, lib.shb_group_linear_scatter_fwd,
+              _p(zz), _p(lay.idx), _p(lay.gptr), _p(wcat), _p(lay.woff), _p(bcat), _p(lay.boff), _p(y), B, lay.rows, lay.C,
+              lay.G, lay.L, _stream())
+        _count()
+        y[:, -1:, :] = extra.to(y.dtype).expand(B, -1, -1)
+        ctx.save_for_backward(zz, wcat)
+        ctx.lay, ctx.extra_shape, ctx.extra_dtype = lay, extra.shape, extra.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        zz, wcat = ctx.saved_tensors
+        lay = ctx.lay
+        gy = gy.float().contiguous()
+        B = zz.shape[0]
+        need_z, need_w, need_b, need_e = ctx.needs_input_grad[:4]
+        gzz = torch.empty_like(zz) if need_z else None
+        gw = torch.empty_like(wcat) if (need_w or need_b) else None
+        gb = torch.empty(sum(lay.b_numel), dtype=torch.float32, device=zz.device) if need_b else None
+        _call("group_linear_scatter_bwd", {"bytes": 4.0 * (2 * gy.numel() + 2 * wcat.numel())}, lib.shb_group_linear_scatter_bwd,
+              _p(zz), _p(lay.idx), _p(lay.gptr), _p(wcat), _p(lay.woff), _p(lay.boff), _p(gy), _p(gzz), _p(gw), _p(gb), B,
+              lay.rows, lay.C, lay.G, lay.L, lay.max_rows, _stream())
+        _count(int(need_z) + int(need_w or need_b))
+        ge = None
+        if need_e:
+            ge = gy[:, -1:, :]
+            if tuple(ctx.extra_shape) != tuple(ge.shape):
+                ge = ge.sum_to_size(ctx.extra_shape)
+            ge = ge.to(ctx.extra_dtype)
+        return gzz, (gw if need_w else None), gb, ge, None
+
+
+def group_linear_gather(x, layers, lay):
+    w, b = lay.pack(layers)
+    return GroupLinearGatherFn.apply(x, w, b, lay)
+
+
+def group_linear_scatter(zz, layers, extra, lay):
+    w, b = lay.pack(layers)
+    return GroupLinearScatterFn.apply(zz, w, b, extra, lay)
+
+
 def spiral_conv(x, weight, bias, geom, activation="elu", compute_dtype=None):
     """compute_dtype: storage/operand dtype of this layer (default: x.dtype); a differing input is cast (and, in
     bf16 mode, channel-padded) by one fused kernel."""

@@ -286,7 +286,7 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
 
     def __init__(self, kps_index_list, vert_part_index_dict, filters_enc, filters_dec, latent_size, part_kps_latent_size,
                  sizes, spiral_sizes, spirals, D, U, device, VAE_flag=False, activation='elu', fuse_pool=True,
-                 reorder=True):
+                 reorder=True, grouped_heads=True):
         super().__init__()
         self.newskl_list = DEFAULT_NEWSKL_LIST
         self.kps_keep = [i for i in range(len(self.newskl_list) + 4) if i not in (3, 13, 14)]
@@ -312,22 +312,46 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
         self._part_idx = [torch.as_tensor(p, dtype=torch.long, device=dev) for p in parts]
         self._kps_idx = [torch.as_tensor(k, dtype=torch.long, device=dev) for k in kps_index_list]
         self._re_index = torch.as_tensor(np.concatenate(parts), dtype=torch.long, device=dev)
+        # grouped-kernel form of the 17+17+17 per-part Linears: one launch per direction.  The decode form
+        # needs the parts to tile the coarsest level exactly (they do: main.py:118-126 composes D to partition it).
+        rows = sizes[-1] + 1
+        self._g_enc = fn.GroupLayout(parts, rows, self._enc_out, out_lat, True, dev)
+        self._g_dec = fn.GroupLayout(parts, rows, c_dec, latent_size + part_kps_latent_size, False, dev)
+        n_kps = max(int(np.max(k)) for k in kps_index_list) + 1
+        self._g_kps = fn.GroupLayout([np.asarray(k) for k in kps_index_list], n_kps, 3, part_kps_latent_size, True, dev)
+        self._g_kps_by_rows = {n_kps: self._g_kps}
+        covered = np.sort(np.concatenate(parts))
+        self.grouped_heads = bool(grouped_heads and self._g_enc.supported() and self._g_dec.supported()
+                                  and self._g_kps.supported() and self._g_enc.disjoint
+                                  and np.array_equal(covered, np.arange(sizes[-1])))
 
     def kps_encode(self, kps):
         B = kps.shape[0]
+        if self.grouped_heads and kps.is_cuda and not kps.requires_grad and kps.shape[1] >= self._g_kps.rows:
+            lay = self._g_kps_by_rows.get(kps.shape[1])
+            if lay is None:  # keypoint sets longer than the largest referenced index: same groups, wider row stride
+                lay = fn.GroupLayout([k.cpu().numpy() for k in self._kps_idx], kps.shape[1], 3, self.part_kps_latent_size,
+                                     True, kps.device)
+                self._g_kps_by_rows[kps.shape[1]] = lay
+            return fn.group_linear_gather(kps, self.kps_enc_list, lay)
         return torch.stack([self.kps_enc_list[k](kps[:, idx, :].reshape(B, -1)) for k, idx in enumerate(self._kps_idx)],
                            dim=1)
 
     def encode(self, x, kps, VAE_flag=None):
         bsize = x.size(0)
         x = self._encode_trunk(x).float()
-        z = torch.stack([self.fc_latent_enc_list[k](x[:, idx, :].reshape(bsize, -1))
-                         for k, idx in enumerate(self._part_idx)], dim=1)
+        if self.grouped_heads:
+            z = fn.group_linear_gather(x, self.fc_latent_enc_list, self._g_enc)
+        else:
+            z = torch.stack([self.fc_latent_enc_list[k](x[:, idx, :].reshape(bsize, -1))
+                             for k, idx in enumerate(self._part_idx)], dim=1)
         return z, self.kps_encode(kps), x[:, -1:, :]
 
     def decode(self, z, z_part_kps, dummy):
         bsize = z.size(0)
         zz = torch.cat([z, z_part_kps], dim=2)
+        if self.grouped_heads:
+            return self._decode_trunk(fn.group_linear_scatter(zz, self.fc_latent_dec_list, dummy, self._g_dec))
         pieces = [self.fc_latent_dec_list[k](zz[:, k, :]) for k in range(z.shape[1])]
         x = torch.cat(pieces, dim=1).view(bsize, self.sizes[-1], -1)
         # models.py:270-272: x[:, re_index] = x[:, arange]  (rows arrive in part-concatenated order)
