@@ -63,29 +63,41 @@ __global__ void __launch_bounds__(GL_THREADS) gl_contract_kernel(const float* __
 }
 
 // ---- scatter form, forward (also: gather form, gradient w.r.t. x -- same expansion, no bias)
-// grid (G, B).  y[b, idx[g0+p], c] = (bias ? bias_k[j] : 0) + sum_i Wt(j,i) * zz[b,k,i],  j = p*C+c,
+// grid (G, ceil(B / GL_BT)).  y[b, idx[g0+p], c] = (bias ? bias_k[j] : 0) + sum_i Wt(j,i) * zz[b,k,i],  j = p*C+c,
 // Wt(j,i) = w_k[j*L + i]  (w_is_KxL != 0)   or   w_k[i*K + j]  (the encode weight read transposed).
+// A thread keeps its weight row in registers and walks a tile of GL_BT samples with it (the weights are read once per
+// sample tile, not once per sample: they are 20x larger than the activations they produce).
+constexpr int GL_BT = 16;
 __global__ void __launch_bounds__(GL_THREADS) gl_expand_kernel(const float* __restrict__ zz, const int32_t* __restrict__ idx,
                                                                const int32_t* __restrict__ gptr, const float* __restrict__ w,
                                                                const int64_t* __restrict__ woff, const float* __restrict__ bias,
-                                                               const int64_t* __restrict__ boff, float* __restrict__ y, int rows,
-                                                               int C, int G, int L, int w_is_KxL) {
-  __shared__ float zs[GL_MAX];
-  const int k = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+                                                               const int64_t* __restrict__ boff, float* __restrict__ y, int B,
+                                                               int rows, int C, int G, int L, int w_is_KxL) {
+  __shared__ float zs[GL_BT][GL_MAX];
+  const int k = blockIdx.x, b0 = blockIdx.y * GL_BT, t = threadIdx.x;
+  const int nb = min(GL_BT, B - b0);
   const int g0 = gptr[k], n = gptr[k + 1] - g0, K = n * C;
   const float* wk = w + woff[k];
-  if (t < L) zs[t] = zz[((size_t)b * G + k) * L + t];
+  for (int q = t; q < nb * L; q += GL_THREADS) {
+    const int bb = q / L, i = q - bb * L;
+    zs[bb][i] = zz[((size_t)(b0 + bb) * G + k) * L + i];
+  }
   __syncthreads();
-  float* yb = y + (size_t)b * rows * C;
   for (int j = t; j < K; j += GL_THREADS) {
     const int p = j / C, c = j - p * C;
-    float a = bias ? __ldg(bias + boff[k] + j) : 0.f;
-    if (w_is_KxL) {
-      for (int i = 0; i < L; ++i) a = fmaf(__ldg(wk + (size_t)j * L + i), zs[i], a);
-    } else {
-      for (int i = 0; i < L; ++i) a = fmaf(__ldg(wk + (size_t)i * K + j), zs[i], a);
+    const float bj = bias ? __ldg(bias + boff[k] + j) : 0.f;
+    float wr[GL_MAX];
+#pragma unroll
+    for (int i = 0; i < GL_MAX; ++i)
+      wr[i] = i < L ? __ldg(w_is_KxL ? wk + (size_t)j * L + i : wk + (size_t)i * K + j) : 0.f;
+    float* yp = y + ((size_t)b0 * rows + __ldg(idx + g0 + p)) * C + c;
+    for (int bb = 0; bb < nb; ++bb) {
+      float a = bj;
+#pragma unroll
+      for (int i = 0; i < GL_MAX; ++i)
+        if (i < L) a = fmaf(wr[i], zs[bb][i], a);
+      yp[(size_t)bb * rows * C] = a;
     }
-    yb[(size_t)__ldg(idx + g0 + p) * C + c] = a;
   }
 }
 
@@ -174,7 +186,7 @@ int shb_group_linear_gather_bwd(const float* x, const int32_t* idx, const int32_
   if (gx) {  // rows outside every group (the dummy row) get zero
     cudaError_t e = cudaMemsetAsync(gx, 0, (size_t)B * rows * C * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
-    gl_expand_kernel<<<dim3(G, B), GL_THREADS, 0, st>>>(gz, idx, gptr, w, woff, nullptr, nullptr, gx, rows, C, G, L, 0);
+    gl_expand_kernel<<<dim3(G, (B + GL_BT - 1) / GL_BT), GL_THREADS, 0, st>>>(gz, idx, gptr, w, woff, nullptr, nullptr, gx, B, rows, C, G, L, 0);
     SHB_LAUNCH_CHECK();
   }
   if (gw) {
@@ -196,7 +208,7 @@ int shb_group_linear_scatter_fwd(const float* zz, const int32_t* idx, const int3
   int rc = gl_args_ok(zz, idx, gptr, w, woff, B, rows, C, G, Lin);
   if (rc) return rc;
   if (!y || (bias && !boff)) return SHB_E_ARG;
-  gl_expand_kernel<<<dim3(G, B), GL_THREADS, 0, (cudaStream_t)stream>>>(zz, idx, gptr, w, woff, bias, boff, y, rows, C, G, Lin, 1);
+  gl_expand_kernel<<<dim3(G, (B + GL_BT - 1) / GL_BT), GL_THREADS, 0, (cudaStream_t)stream>>>(zz, idx, gptr, w, woff, bias, boff, y, B, rows, C, G, Lin, 1);
   SHB_LAUNCH_CHECK();
   return 0;
 }
