@@ -201,3 +201,27 @@ def test_locality_order_and_permuted_pool_matrices():
     inv = np.empty(len(pr), np.int64)
     inv[pr] = np.arange(len(pr))
     assert np.array_equal(p.t_colidx.numpy(), inv)
+
+
+def test_group_layout_host_logic():
+    """Packed-parameter offsets and the overlap check of the grouped heads (functions.GroupLayout)."""
+    import torch
+    from semantichuman_b200.functions import GroupLayout
+
+    parts = [np.array([4, 0, 2]), np.array([1, 3]), np.array([5])]
+    enc = GroupLayout(parts, rows=7, channels=4, latent=8, gather=True, device="cpu")
+    assert enc.G == 3 and enc.max_rows == 3 and enc.disjoint and enc.supported()
+    assert enc.gptr.tolist() == [0, 3, 5, 6] and enc.idx.tolist() == [4, 0, 2, 1, 3, 5]
+    assert enc.woff.tolist() == [0, 3 * 4 * 8, 5 * 4 * 8] and enc.boff.tolist() == [0, 8, 16]
+    dec = GroupLayout(parts, rows=7, channels=4, latent=16, gather=False, device="cpu")
+    assert dec.boff.tolist() == [0, 12, 20] and dec.b_numel == [12, 8, 4]
+    layers = [torch.nn.Linear(len(p) * 4, 8) for p in parts]
+    w, b = enc.pack(layers)
+    assert w.numel() == sum(enc.w_numel) and b.numel() == 24
+    assert torch.equal(w[enc.woff[1]:enc.woff[1] + enc.w_numel[1]].view(8, 8), layers[1].weight)
+    assert not GroupLayout([np.array([0, 1]), np.array([1, 2])], 4, 3, 8, True, "cpu").disjoint
+    assert not GroupLayout(parts, 7, 4, 64, True, "cpu").supported()
+    with pytest.raises(ValueError):
+        GroupLayout([np.array([7])], 7, 4, 8, True, "cpu")
+    with pytest.raises(ValueError):
+        enc.pack([torch.nn.Linear(5, 8)] * 3)
