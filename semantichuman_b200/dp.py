@@ -3,12 +3,13 @@
 The reference is single-device (main.py:197-201); this is the one thing the build ADDS around the path.  One
 process per GPU (torchrun), every rank holds a full replica, the global batch is split evenly by sample, and the
 only exchange is a gradient all-reduce (NCCL over NVLink/NVSwitch, ReduceOp.AVG == global-batch mean loss because
-shards are equal).  Gradients live in three flat fp32 buckets ordered by when backward finishes them:
+shards are equal).  Gradients live in four flat fp32 buckets ordered by when backward finishes them:
 
-    decoder convs (ready first) -> the two FC layers (99 % of the bytes, ready mid-backward) -> encoder convs (last)
+    decoder convs (ready first) -> fc_latent_dec (57 MB) -> fc_latent_enc (57 MB) -> encoder convs (last)
 
 Each bucket's all-reduce is launched from an autograd post-accumulate hook the moment its last gradient lands, so
-the 114 MB FC bucket travels while the encoder backward is still computing.  ``finish()`` joins before the optimizer.
+the two 57 MB FC buckets travel while the rest of the backward is still computing (the decoder-side one starts a whole
+FC backward earlier than a single 114 MB bucket would).  ``finish()`` joins before the optimizer.
 """
 import torch
 import torch.distributed as dist
@@ -22,12 +23,18 @@ def shard_batch(global_batch, rank, world):
     return rank * per, (rank + 1) * per
 
 
+N_BUCKETS = 4
+
+
 def _bucket_of(name):
+    """Backward order: decoder convs -> decoder-side latent layers -> encoder-side latent layers -> encoder convs."""
     if name.startswith("dconv."):
         return 0
-    if name.startswith(("fc_latent", "kps_enc_list")):
+    if name.startswith("fc_latent_dec"):
         return 1
-    return 2
+    if name.startswith(("fc_latent_enc", "kps_enc_list")):
+        return 2
+    return 3
 
 
 class GradSync:
@@ -44,7 +51,7 @@ class GradSync:
         self._handles = []
         if self.world == 1:
             return  # nothing to exchange: no flat buckets, gradients are plain per-parameter tensors (reset() drops them)
-        for b in range(3):
+        for b in range(N_BUCKETS):
             members = [(n, p) for n, p in named if _bucket_of(n) == b]
             if not members:
                 continue

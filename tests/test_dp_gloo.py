@@ -83,7 +83,7 @@ def test_two_rank_average_equals_full_batch():
     for rank, grads, order, nbytes in got:
         for a, b in zip(grads, full):
             assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
-        assert order[:3] == [0, 1, 2]  # decoder convs -> FC -> encoder convs
+        assert order[:4] == [0, 1, 2, 3]  # decoder convs -> fc_latent_dec -> fc_latent_enc -> encoder convs
         assert nbytes == 4 * sum(p.numel() for p in model.parameters())
     for a, b in zip(got[0][1], got[1][1]):
         assert torch.equal(a, b)
