@@ -184,6 +184,26 @@ int shb_group_linear_scatter_bwd(const float* zz, const int32_t* idx, const int3
                                  const int64_t* boff, const float* gy, float* gzz, float* gw, float* gb, int B, int rows, int C,
                                  int G, int Lin, int max_group_rows, void* stream);
 
+/* ---- Orientation-adaptive pairwise-distance loss (utils_SH.py:442-478 angle_skl; utils_distance.py:366-376;
+ * train_funcs.py:243-284 == :353-389), fused: per part k (vertex ids idx[gptr[k] .. gptr[k+1]) of the (B, V, 3) fp32
+ * ground truth tx and reconstruction rec), over the ordered pairs i != j with w*De != 0,
+ *     relative != 0:  mean | w*De_r/De - w |        relative == 0:  mean | w*De_r - w*De |
+ * De / De_r = pairwise distances in tx / rec (De times scale[b,k] when scale != NULL); w from the angle (degrees) between
+ * v_i - v_j and the part's bone kps[bone[k][0]] - kps[bone[k][1]] (or minus the mean of two keypoints when bone[k][2] >= 0):
+ * wmode[k] = 0 all-one, 1 angle/90, 2 sin(angle), 3 angle/90 zeroed below w_threshold.  loss = sum_k part_weight[k] * mean_k.
+ * fwd writes the loss and keeps the per-part normalisers in the workspace; bwd (same arguments, same workspace) writes
+ * d loss / d rec * gscale[0] for every vertex (zero outside the parts; parts must not overlap).  Fixed-order reductions.
+ * kps (B, NK, 3); idx, gptr, bone (G,3), wmode (G) int32 and part_weight (G), scale (B,G) fp32 are device arrays. */
+size_t shb_pair_loss_workspace(int B, int G, int max_part_rows);
+int shb_pair_loss_fwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
+                      const int32_t* bone, const int32_t* wmode, const float* part_weight, const float* scale,
+                      float w_threshold, int relative, float* loss_out, void* workspace, size_t workspace_bytes, int B, int V,
+                      int NK, int G, int max_part_rows, void* stream);
+int shb_pair_loss_bwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
+                      const int32_t* bone, const int32_t* wmode, const float* scale, float w_threshold, int relative,
+                      const float* gscale, float* grec, const void* workspace, size_t workspace_bytes, int B, int V, int NK,
+                      int G, int max_part_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,6 +179,71 @@ def zpart_reg(z, measure, P, Q, relative=True):
 
 
 # ---------------------------------------------------------------------------------------------- index oracles
+def angle_weights(v, kps, part_index_lists, skl_list):
+    """utils_SH.py:442-478 (angle_skl): per part, the angle in degrees (0..90) between every vertex pair direction
+    v_i - v_j and the part's bone direction; |cos| clamped to [0, 1], NaN (i == j) -> cos = 1 -> 0 degrees.
+    v (B, V, 3), kps (B, n_kps, 3); returns a list of (B, n_p, n_p) tensors."""
+    out = []
+    for idx, bone in zip(part_index_lists, skl_list):
+        vp = v[:, idx, :]
+        d = vp[:, :, None, :] - vp[:, None, :, :]                                   # :449
+        if len(bone) == 2:                                                          # :450-453
+            kd = kps[:, bone[0], :] - kps[:, bone[1], :]
+        else:
+            kd = kps[:, bone[0], :] - (kps[:, bone[1], :] + kps[:, bone[2], :]) / 2
+        kd = kd[:, None, None, :]
+        dm = torch.sqrt(torch.sum(d * d, dim=-1))                                   # :454
+        km = torch.sqrt(torch.sum(kd * kd, dim=-1))                                 # :458
+        cos = torch.abs(torch.sum(d * kd, dim=-1) / (dm * km))                      # :459-460
+        cos = torch.where(torch.isnan(cos), torch.ones_like(cos), cos).float()      # :462
+        cos = cos.clamp(0.0, 1.0)                                                   # :463-464
+        out.append(torch.arccos(cos) * 180 / np.pi)                                 # :468
+    return out
+
+
+def euclidean_dist_matrix(x):
+    """utils_distance.py:366-376 (calc_euclidean_dist_matrix): sqrt(relu(|x_i|^2 - 2 x_i.x_j + |x_j|^2))."""
+    r = torch.sum(x ** 2, dim=2).unsqueeze(2)
+    return F.relu(r - 2 * torch.bmm(x, x.transpose(2, 1)) + r.transpose(2, 1)) ** 0.5
+
+
+def pair_distance_loss(tx, rec, kps, part_index_lists, skl_list, w_mode="linear", w_threshold=0.8, leaf_parts=(),
+                       relative=True, part_weights=None, scale=None):
+    """The orientation-adaptive pairwise-distance loss of train_funcs.py:243-284 (== :353-389 without `scale`).
+
+    Per part p: w = f(angle)/... by `w_mode` (all-one for parts in `leaf_parts`, :259-267), diagonal zeroed (:268-269);
+    De / De_r = pairwise distances of the ground truth / the reconstruction (:246-247), De optionally scaled per sample
+    (`a[:, ...]`, :248-249); over the entries with w*De != 0 (:272): mean |w*De_r/De - w| (relat_flag, :276) or
+    mean |w*De_r - w*De| (:274); summed with `part_weights` (default 1/K, :252-253)."""
+    K = len(part_index_lists)
+    ang = angle_weights(tx, kps, part_index_lists, skl_list)
+    total = 0.0
+    for p, idx in enumerate(part_index_lists):
+        De = euclidean_dist_matrix(tx[:, idx, :])
+        De_r = euclidean_dist_matrix(rec[:, idx, :])
+        if scale is not None:
+            De = De * scale[:, p][:, None, None]
+        if w_mode == "all_one" or p in leaf_parts:
+            w = torch.ones_like(ang[p])
+        elif w_mode == "linear":
+            w = ang[p].float() / 90
+        elif w_mode == "sin":
+            w = torch.sin(ang[p].float() / 180 * torch.pi)
+        elif w_mode == "threshold":
+            w = ang[p].float() / 90
+            w = torch.where(w < w_threshold, torch.zeros_like(w), w)
+        else:
+            raise NotImplementedError(w_mode)
+        w = w - torch.diag_embed(torch.diagonal(w, dim1=1, dim2=2))
+        nz = torch.where((w * De) != 0)
+        if relative:
+            lp = F.l1_loss(w[nz] * De_r[nz].float() / De[nz], w[nz] * torch.ones_like(w[nz]))
+        else:
+            lp = F.l1_loss(w[nz] * De_r[nz].float(), w[nz] * De[nz])
+        total = total + (1.0 / K if part_weights is None else part_weights[p]) * lp
+    return total
+
+
 def normalise_spiral(spiral_idx, rows_in=None):
     """-1 -> rows_in-1 (models.py:42's negative index), int32, 2-D."""
     a = np.asarray(spiral_idx)

@@ -9,7 +9,7 @@ import os
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libshb200.so")
 
-c_int, c_i64, c_size, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
+c_int, c_i64, c_size, c_vp, c_float = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_float
 
 # name -> (restype, argtypes); one entry per declaration in include/shb200.h
 SIGNATURES = {
@@ -32,6 +32,9 @@ SIGNATURES = {
     "shb_l1_loss_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_size, c_vp, c_int, c_vp]),
     "shb_l1_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
     "shb_partnorm_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_pair_loss_workspace": (c_size, [c_int] * 3),
+    "shb_pair_loss_fwd": (c_int, [c_vp] * 9 + [c_float, c_int, c_vp, c_vp, c_size] + [c_int] * 5 + [c_vp]),
+    "shb_pair_loss_bwd": (c_int, [c_vp] * 8 + [c_float, c_int, c_vp, c_vp, c_vp, c_size] + [c_int] * 5 + [c_vp]),
     "shb_group_linear_gather_fwd": (c_int, [c_vp] * 8 + [c_int] * 5 + [c_vp]),
     "shb_group_linear_gather_bwd": (c_int, [c_vp] * 10 + [c_int] * 6 + [c_vp]),
     "shb_group_linear_scatter_fwd": (c_int, [c_vp] * 8 + [c_int] * 5 + [c_vp]),

@@ -411,6 +411,92 @@ class GroupLinearScatterFn(torch.autograd.Function):
         return gzz, (gw if need_w else None), gb, ge, None
 
 
+W_MODES = {"all_one": 0, "linear": 1, "sin": 2, "threshold": 3}  # cfg.TRAIN.w_mode, train_funcs.py:259-267
+
+
+class PairLossLayout:
+    """Device tables of the orientation-adaptive pairwise-distance loss: part vertex lists, bones, per-part weight modes."""
+
+    def __init__(self, parts, skl_list, device, w_mode="linear", leaf_parts=(), part_weights=None):
+        import numpy as np
+
+        if w_mode not in W_MODES:
+            raise NotImplementedError(w_mode)
+        if len(parts) != len(skl_list):
+            raise ValueError("one bone per part")
+        sizes = [len(p) for p in parts]
+        flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in parts])
+        if len(np.unique(flat)) != len(flat):
+            raise ValueError("parts must not overlap")
+        self.G, self.max_rows, self.n_max_vertex = len(parts), max(sizes), int(flat.max())
+        self.pairs_per_sample = float(sum(n * n for n in sizes))
+        bone = np.full((self.G, 3), -1, np.int32)
+        for k, b in enumerate(skl_list):
+            if len(b) not in (2, 3):
+                raise ValueError("a bone is two keypoints, or one keypoint and the mean of two")
+            bone[k, :len(b)] = b
+        self.n_max_kps = int(bone.max())
+        mode = np.full(self.G, W_MODES[w_mode], np.int32)
+        mode[list(leaf_parts)] = 0  # leaf parts use all-one weights (train_funcs.py:259)
+        pw = np.full(self.G, 1.0 / self.G, np.float32) if part_weights is None else np.asarray(part_weights, np.float32)
+        dev = torch.device(device)
+        self.idx = torch.as_tensor(flat, dtype=torch.int32, device=dev)
+        self.gptr = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32, device=dev)
+        self.bone = torch.from_numpy(bone).to(dev)
+        self.wmode = torch.from_numpy(mode).to(dev)
+        self.pw = torch.from_numpy(pw).to(dev)
+
+
+class PairLossFn(torch.autograd.Function):
+    """train_funcs.py:243-284 as two kernels (loss, then d loss / d rec); the ground truth, keypoints and scale get no
+    gradient (they are data in the reference's loop)."""
+
+    @staticmethod
+    def forward(ctx, tx, rec, kps, scale, lay, w_threshold, relative):
+        _cuda(tx, rec, kps)
+        tx, rec, kps = tx.float().contiguous(), rec.float().contiguous(), kps.float().contiguous()
+        if tx.shape != rec.shape or tx.dim() != 3 or tx.shape[2] != 3:
+            raise ValueError("tx and rec must both be (B, V, 3)")
+        B, V, _ = tx.shape
+        if lay.n_max_vertex >= V or lay.n_max_kps >= kps.shape[1] or kps.shape[0] != B:
+            raise ValueError("part vertex / bone keypoint index out of range")
+        if scale is not None:
+            scale = scale.float().contiguous()
+            if tuple(scale.shape) != (B, lay.G):
+                raise ValueError("scale must be (B, n_parts)")
+        nbytes = lib.shb_pair_loss_workspace(B, lay.G, lay.max_rows)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=tx.device)
+        loss = torch.empty((), dtype=torch.float32, device=tx.device)
+        pairs = float(B) * lay.pairs_per_sample
+        _call("pair_loss", {"bytes": 24.0 * tx.numel() / 3, "flops": 40.0 * pairs}, lib.shb_pair_loss_fwd, _p(tx), _p(rec),
+              _p(kps), _p(lay.idx), _p(lay.gptr), _p(lay.bone), _p(lay.wmode), _p(lay.pw), _p(scale), float(w_threshold),
+              int(bool(relative)), _p(loss), _p(ws), nbytes, B, V, kps.shape[1], lay.G, lay.max_rows, _stream())
+        _count(2)
+        ctx.save_for_backward(tx, rec, kps, scale if scale is not None else tx.new_empty(0), ws)
+        ctx.lay, ctx.thr, ctx.rel, ctx.has_scale, ctx.pairs = lay, float(w_threshold), int(bool(relative)), scale is not None, pairs
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        tx, rec, kps, scale, ws = ctx.saved_tensors
+        lay = ctx.lay
+        B, V, _ = tx.shape
+        grec = None
+        if ctx.needs_input_grad[1]:
+            grec = torch.empty_like(rec)
+            gs = g.float().contiguous()
+            _call("pair_loss_bwd", {"bytes": 36.0 * tx.numel() / 3, "flops": 50.0 * ctx.pairs}, lib.shb_pair_loss_bwd, _p(tx),
+                  _p(rec), _p(kps), _p(lay.idx), _p(lay.gptr), _p(lay.bone), _p(lay.wmode), _p(scale) if ctx.has_scale else None,
+                  ctx.thr, ctx.rel, _p(gs), _p(grec), _p(ws), ws.numel(), B, V, kps.shape[1], lay.G, lay.max_rows, _stream())
+            _count()
+        return None, grec, None, None, None, None, None
+
+
+def pair_loss(tx, rec, kps, layout, scale=None, w_threshold=0.8, relative=True):
+    """Orientation-adaptive pairwise-distance loss (train_funcs.py:243-284): `layout` = PairLossLayout(parts, skl_list, ...)."""
+    return PairLossFn.apply(tx, rec, kps, scale, layout, w_threshold, relative)
+
+
 def group_linear_gather(x, layers, lay):
     w, b = lay.pack(layers)
     return GroupLinearGatherFn.apply(x, w, b, lay)

@@ -155,7 +155,7 @@ def install():
     tm = mod("trimesh")
     tm.base = mod("trimesh.base")
     tm.exchange = mod("trimesh.exchange")
-    tm.exchange.export = mod("trimesh.exchange.export")
+    tm.exchange.export = mod("trimesh.exchange.export", export_mesh=None)
     mod("tensorboardX", SummaryWriter=object)
     if "/root/reference" not in sys.path:
         sys.path.insert(0, "/root/reference")

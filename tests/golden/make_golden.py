@@ -3,7 +3,7 @@
 
 Run once in the build container (``/root/reference`` mounted read-only):
 
-    python tests/golden/make_golden.py [--only hier|ops|ae|big]
+    python tests/golden/make_golden.py [--only hier|ops|ae|pair|big]
 
 It imports the reference's ``models.py``, ``utils_spiral.py`` and ``mesh_sampling.py`` in place and
 unmodified (``_ref_stubs.install()`` supplies inert stand-ins for yacs / psbody / opendr / ...), runs them
@@ -18,6 +18,8 @@ Fixtures
   golden_ops.npz                  reference SpiralConv fwd/bwd for every activation; dense-pool fwd/bwd.
   golden_ae_small*.npz            reference SpiralAutoencoder fwd + l1 + bwd, all parameters stored.
   golden_multiz_small.npz         reference SpiralAutoencoder_multiz_partkps fwd + losses + bwd.
+  golden_pair_loss.npz            reference angle_skl + calc_euclidean_dist_matrix + the pairwise-distance loss lines
+                                  of train_funcs.py:243-284 (three weight/normalisation configurations) + d/d rec.
   golden_ae_6890.npz              full-size SpiralAutoencoder (default filters, nz=256), B=2, deterministic
                                   weights (semantichuman_b200.synthetic.fill_deterministic_), outputs and
                                   gradient samples.
@@ -251,6 +253,76 @@ def gen_multiz_small():
     print("golden_multiz_small loss", float(loss), "parts", [len(p) for p in parts])
 
 
+def ref_pair_loss(tx, rec, kps, vdict, names, skl_list, w_mode, w_threshold, leaf_list, relat_flag, scale):
+    """train_funcs.py:243-284 over the reference's own angle_skl (utils_SH.py:442) and calc_euclidean_dist_matrix
+    (utils_distance.py:366); the loop body is inline in the reference's training loop, so it is restated here line by
+    line (w_part_mode '1/K', cfgs.py:95)."""
+    import utils_SH  # noqa: E402  (reference)
+    from utils_distance import calc_euclidean_dist_matrix  # noqa: E402  (reference)
+
+    F = torch.nn.functional
+    angle_w = utils_SH.angle_skl(tx, kps, names, vdict, skl_list)                                        # :243
+    loss = 0.0
+    for i in range(len(names)):
+        idx = vdict[names[i]]
+        De = calc_euclidean_dist_matrix(tx[:, idx, :])                                                   # :246
+        De_r = calc_euclidean_dist_matrix(rec[:, idx, :])                                                # :247
+        if scale is not None:
+            De = De * scale[:, i][:, None, None]                                                         # :248-249
+        w_part = 1 / len(names)                                                                          # :252-253
+        if w_mode == 'all_one' or i in leaf_list:                                                        # :259
+            w = torch.ones_like(angle_w[i].squeeze(-1))
+        elif w_mode == 'linear':
+            w = angle_w[i].squeeze(-1).float() / 90
+        elif w_mode == 'sin':
+            w = torch.sin(angle_w[i].squeeze(-1).float() / 180 * torch.pi)
+        elif w_mode == 'threshold':
+            w = angle_w[i].squeeze(-1).float() / 90
+            w = torch.where(w < w_threshold, torch.full_like(w, 0), w)
+        for b in range(w.shape[0]):                                                                      # :268-269
+            w[b, ...] = w[b, ...] - torch.diag_embed(torch.diag(w[b, ...]))
+        nz = torch.where((w * De) != 0)                                                                  # :272
+        if not relat_flag:
+            loss = loss + w_part * F.l1_loss(w[nz] * De_r[nz].float(), w[nz] * De[nz])                   # :274
+        else:
+            loss = loss + w_part * F.l1_loss(w[nz] * De_r[nz].float() / De[nz], w[nz] * torch.ones_like(w[nz]))  # :276
+    return loss
+
+
+def gen_pair_loss():
+    """golden_pair_loss.npz: the orientation-adaptive pairwise-distance loss on the 300-vertex
+    template, 5 parts, three configurations."""
+    h = np.load(os.path.join(HERE, "hier_small.npz"))
+    verts = h["verts0"]
+    V = verts.shape[0]
+    rng = np.random.default_rng(11)
+    order = np.argsort(verts[:, 1], kind="stable")
+    sizes = [37, 80, 61, 90, V - 268]
+    parts = np.split(order, np.cumsum(sizes)[:-1])
+    names = ["p%d" % i for i in range(5)]
+    vdict = {n: torch.from_numpy(np.sort(p).astype(np.int64)) for n, p in zip(names, parts)}
+    skl_list = [[3, 1], [0, 2], [4, 1, 5], [2, 6], [7, 3, 0]]
+    B = 3
+    tx = synthetic_meshes(verts, B, seed=21, noise=0.02)[:, :-1, :].contiguous()
+    g = torch.Generator().manual_seed(9)
+    kps = torch.randn(B, 8, 3, generator=g) * 0.4
+    scale = torch.rand(B, 5, generator=g) * 0.4 + 0.8
+    out = {"tx": tx.numpy(), "kps": kps.numpy(), "scale": scale.numpy(), "skl": np.asarray([b + [-1] * (3 - len(b)) for b in skl_list]),
+           "part_sizes": np.asarray([len(p) for p in parts]), "part_idx": np.concatenate([vdict[n].numpy() for n in names])}
+    configs = {"lin_rel_leaf": ("linear", 0.8, [0, 4], True, None),
+               "thr_abs": ("threshold", 0.8, [], False, None),
+               "sin_rel_scale": ("sin", 0.8, [], True, scale)}
+    for tag, (mode, thr, leaf, rel, sc) in configs.items():
+        rec = (tx + 0.03 * torch.randn(tx.shape, generator=g)).requires_grad_(True)
+        loss = ref_pair_loss(tx, rec, kps, vdict, names, skl_list, mode, thr, leaf, rel, sc)
+        loss.backward()
+        out[tag + "_rec"] = rec.detach().numpy()
+        out[tag + "_loss"] = loss.detach().numpy()
+        out[tag + "_grec"] = rec.grad.numpy()
+        print("golden_pair_loss", tag, float(loss), float(rec.grad.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "golden_pair_loss.npz"), **out)
+
+
 def gen_big():
     h, sizes, ssz, spirals, bD, bU = load_hier_for_ref("2222")
     fenc = [[3, 16, 32, 64, 128], [[], [], [], [], []]]
@@ -292,6 +364,8 @@ def main():
     if a.only in ("all", "ae"):
         gen_ae_small()
         gen_multiz_small()
+    if a.only in ("all", "pair"):
+        gen_pair_loss()
     if a.only in ("all", "big"):
         gen_big()
 

@@ -119,3 +119,30 @@ def test_autoencoder_6890_full_size():
         stride = max(1, flat.numel() // 4096)
         assert relerr(flat[::stride][:4096], g["gsmp_" + n]) < 5e-5, n
         assert abs(float(flat.double().abs().sum()) - float(g["gabs_" + n])) <= 1e-4 * float(g["gabs_" + n]) + 1e-12, n
+
+
+PAIR_CONFIGS = {"lin_rel_leaf": ("linear", 0.8, (0, 4), True, False), "thr_abs": ("threshold", 0.8, (), False, False),
+                "sin_rel_scale": ("sin", 0.8, (), True, True)}
+
+
+def pair_inputs(g):
+    sizes = [int(v) for v in g["part_sizes"]]
+    parts = [torch.from_numpy(p.astype("int64")) for p in np.split(g["part_idx"], np.cumsum(sizes)[:-1])]
+    skl = [[int(v) for v in row if v >= 0] for row in g["skl"]]
+    return parts, skl
+
+
+@pytest.mark.parametrize("tag", list(PAIR_CONFIGS))
+def test_pair_distance_loss_oracle_matches_reference(tag):
+    """Orientation-adaptive pairwise-distance loss (utils_SH.py:442-478 + train_funcs.py:243-284): the oracle's
+    restatement against numbers produced by the reference's own angle_skl / calc_euclidean_dist_matrix."""
+    g = golden("golden_pair_loss")
+    parts, skl = pair_inputs(g)
+    mode, thr, leaf, rel, use_scale = PAIR_CONFIGS[tag]
+    tx, kps = torch.from_numpy(g["tx"]), torch.from_numpy(g["kps"])
+    rec = torch.from_numpy(g[tag + "_rec"]).requires_grad_(True)
+    loss = so.pair_distance_loss(tx, rec, kps, parts, skl, w_mode=mode, w_threshold=thr, leaf_parts=leaf, relative=rel,
+                                 scale=torch.from_numpy(g["scale"]) if use_scale else None)
+    loss.backward()
+    assert abs(loss.item() - float(g[tag + "_loss"])) < 2e-6
+    assert relerr(rec.grad, g[tag + "_grec"]) < 2e-5
