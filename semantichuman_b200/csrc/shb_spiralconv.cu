@@ -625,7 +625,8 @@ int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SHB_F32) return launch_gather_gemm<float, false>(p, st);
   if (dtype == SHB_BF16) {
-    if (umma_enabled() && umma_gather_gemm_supported(Cin, Cout, S))  // tensor-core path (tcgen05 + TMEM)
+    // tensor-core path (tcgen05 + TMEM); its tile arithmetic is 32-bit, larger problems take the CUDA-core kernel
+    if (umma_enabled() && p.M < (1LL << 31) && umma_gather_gemm_supported(Cin, Cout, S))
       return umma_gather_gemm(x, table, nullptr, nullptr, w, (const float*)bias, y, B, rows_in, rows_out, S, Cin, Cout, act,
                               zero_last_row, src_dummy_zero, false, st);
     return launch_gather_gemm<__nv_bfloat16, false>(p, st);
@@ -770,7 +771,7 @@ int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_
   int rc;
   if (dtype == SHB_F32) rc = launch_gather_gemm<float, true>(p, st);
   else if (dtype == SHB_BF16) {
-    if (umma_enabled() && quads != nullptr && umma_gather_gemm_supported(Cout, Cin, S))
+    if (umma_enabled() && quads != nullptr && p.M < (1LL << 31) && umma_gather_gemm_supported(Cout, Cin, S))
       rc = umma_gather_gemm(gz, (const int32_t*)quads, keyptr, rows, w, nullptr, gx, B, rows_out, rows_in, S, Cout, Cin, SHB_ACT_IDENTITY, 0, 1,
                             true, st);
     else
