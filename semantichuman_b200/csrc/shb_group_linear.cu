@@ -18,48 +18,71 @@ constexpr int GL_MAX = 32;      // widest latent side (L, Lin) the register accu
 constexpr int GL_THREADS = 128;
 
 // ---- gather form, forward (also: scatter form, gradient w.r.t. zz -- same contraction, no bias)
-// grid (G, B).  out[b,k,o] = (bias ? bias_k[o] : 0) + sum_j Wt(o,j) * v[b,j]  where  v[b, p*C+c] = x[b, idx[g0+p], c]  and
-// Wt(o,j) = w_k[o*K + j]  (w_is_KxL == 0)   or   w_k[j*L + o]  (w_is_KxL != 0: the decode weight read transposed).
+// grid (G, ceil(B / BT)).  out[b,k,o] = (bias ? bias_k[o] : 0) + sum_j Wt(o,j) * v[b,j]  where  v[b, p*C+c] = x[b, idx[g0+p], c]
+// and Wt(o,j) = w_k[o*K + j]  (w_is_KxL == 0)   or   w_k[j*L + o]  (w_is_KxL != 0: the decode weight read transposed).
+// A block handles BT samples at once (BT * LM = GL_MAX accumulators per thread) so that a weight element is loaded once per
+// sample tile; L <= LM.
+template <int BT, int LM>
 __global__ void __launch_bounds__(GL_THREADS) gl_contract_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
                                                                  const int32_t* __restrict__ gptr, const float* __restrict__ w,
                                                                  const int64_t* __restrict__ woff, const float* __restrict__ bias,
-                                                                 const int64_t* __restrict__ boff, float* __restrict__ out,
+                                                                 const int64_t* __restrict__ boff, float* __restrict__ out, int B,
                                                                  int rows, int C, int G, int L, int w_is_KxL) {
-  __shared__ float red[GL_THREADS / 32][GL_MAX];
-  const int k = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  __shared__ float red[GL_THREADS / 32][BT][LM];
+  const int k = blockIdx.x, b0 = blockIdx.y * BT, t = threadIdx.x;
+  const int nb = min(BT, B - b0);
   const int g0 = gptr[k], n = gptr[k + 1] - g0, K = n * C;
   const float* wk = w + woff[k];
-  const float* xb = x + (size_t)b * rows * C;
-  float acc[GL_MAX];
+  const size_t xs = (size_t)rows * C;
+  const float* xb = x + (size_t)b0 * xs;
+  float acc[BT][LM];
 #pragma unroll
-  for (int o = 0; o < GL_MAX; ++o) acc[o] = 0.f;
+  for (int u = 0; u < BT; ++u)
+#pragma unroll
+    for (int o = 0; o < LM; ++o) acc[u][o] = 0.f;
   for (int j = t; j < K; j += GL_THREADS) {
     const int p = j / C, c = j - p * C;
-    const float v = xb[(size_t)__ldg(idx + g0 + p) * C + c];
-    if (w_is_KxL) {
+    const size_t col = (size_t)__ldg(idx + g0 + p) * C + c;
+    float v[BT];
 #pragma unroll
-      for (int o = 0; o < GL_MAX; ++o)
-        if (o < L) acc[o] = fmaf(__ldg(wk + (size_t)j * L + o), v, acc[o]);
-    } else {
+    for (int u = 0; u < BT; ++u) v[u] = u < nb ? xb[u * xs + col] : 0.f;
 #pragma unroll
-      for (int o = 0; o < GL_MAX; ++o)
-        if (o < L) acc[o] = fmaf(__ldg(wk + (size_t)o * K + j), v, acc[o]);
+    for (int o = 0; o < LM; ++o) {
+      if (o < L) {
+        const float wv = __ldg(w_is_KxL ? wk + (size_t)j * L + o : wk + (size_t)o * K + j);
+#pragma unroll
+        for (int u = 0; u < BT; ++u) acc[u][o] = fmaf(wv, v[u], acc[u][o]);
+      }
     }
   }
 #pragma unroll
-  for (int o = 0; o < GL_MAX; ++o) {
-    if (o < L) {  // L is uniform across the block
-      const float s = warp_sum(acc[o]);
-      if ((t & 31) == 0) red[t >> 5][o] = s;
+  for (int u = 0; u < BT; ++u)
+#pragma unroll
+    for (int o = 0; o < LM; ++o) {
+      if (o < L) {  // L is uniform across the block
+        const float s = warp_sum(acc[u][o]);
+        if ((t & 31) == 0) red[t >> 5][u][o] = s;
+      }
     }
-  }
   __syncthreads();
-  if (t < L) {
-    float s = bias ? __ldg(bias + boff[k] + t) : 0.f;
+  if (t < nb * L) {
+    const int u = t / L, o = t - u * L;
+    float s = bias ? __ldg(bias + boff[k] + o) : 0.f;
 #pragma unroll
-    for (int q = 0; q < GL_THREADS / 32; ++q) s += red[q][t];
-    out[((size_t)b * G + k) * L + t] = s;
+    for (int q = 0; q < GL_THREADS / 32; ++q) s += red[q][u][o];
+    out[((size_t)(b0 + u) * G + k) * L + o] = s;
   }
+}
+
+static void gl_contract_launch(const float* x, const int32_t* idx, const int32_t* gptr, const float* w, const int64_t* woff,
+                               const float* bias, const int64_t* boff, float* out, int B, int rows, int C, int G, int L,
+                               int w_is_KxL, cudaStream_t st) {
+  if (L <= 8)
+    gl_contract_kernel<4, 8><<<dim3(G, (B + 3) / 4), GL_THREADS, 0, st>>>(x, idx, gptr, w, woff, bias, boff, out, B, rows, C, G, L, w_is_KxL);
+  else if (L <= 16)
+    gl_contract_kernel<2, 16><<<dim3(G, (B + 1) / 2), GL_THREADS, 0, st>>>(x, idx, gptr, w, woff, bias, boff, out, B, rows, C, G, L, w_is_KxL);
+  else
+    gl_contract_kernel<1, 32><<<dim3(G, B), GL_THREADS, 0, st>>>(x, idx, gptr, w, woff, bias, boff, out, B, rows, C, G, L, w_is_KxL);
 }
 
 // ---- scatter form, forward (also: gather form, gradient w.r.t. x -- same expansion, no bias)
@@ -171,7 +194,7 @@ int shb_group_linear_gather_fwd(const float* x, const int32_t* idx, const int32_
   int rc = gl_args_ok(x, idx, gptr, w, woff, B, rows, C, G, L);
   if (rc) return rc;
   if (!z || (bias && !boff)) return SHB_E_ARG;
-  gl_contract_kernel<<<dim3(G, B), GL_THREADS, 0, (cudaStream_t)stream>>>(x, idx, gptr, w, woff, bias, boff, z, rows, C, G, L, 0);
+  gl_contract_launch(x, idx, gptr, w, woff, bias, boff, z, B, rows, C, G, L, 0, (cudaStream_t)stream);
   SHB_LAUNCH_CHECK();
   return 0;
 }
@@ -221,7 +244,7 @@ int shb_group_linear_scatter_bwd(const float* zz, const int32_t* idx, const int3
   if (!gy || max_group_rows <= 0) return SHB_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (gzz) {
-    gl_contract_kernel<<<dim3(G, B), GL_THREADS, 0, st>>>(gy, idx, gptr, w, woff, nullptr, nullptr, gzz, rows, C, G, Lin, 1);
+    gl_contract_launch(gy, idx, gptr, w, woff, nullptr, nullptr, gzz, B, rows, C, G, Lin, 1, st);
     SHB_LAUNCH_CHECK();
   }
   if (gw || gb) {
