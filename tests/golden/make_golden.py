@@ -20,6 +20,7 @@ Fixtures
   golden_multiz_small.npz         reference SpiralAutoencoder_multiz_partkps fwd + losses + bwd.
   golden_pair_loss.npz            reference angle_skl + calc_euclidean_dist_matrix + the pairwise-distance loss lines
                                   of train_funcs.py:243-284 (three weight/normalisation configurations) + d/d rec.
+  golden_skeleton.npz             reference kps2skl / skl2kps (utils_SH.py:26-80), all modes.
   golden_ae_6890.npz              full-size SpiralAutoencoder (default filters, nz=256), B=2, deterministic
                                   weights (semantichuman_b200.synthetic.fill_deterministic_), outputs and
                                   gradient samples.
@@ -323,6 +324,24 @@ def gen_pair_loss():
     np.savez_compressed(os.path.join(HERE, "golden_pair_loss.npz"), **out)
 
 
+def gen_skeleton():
+    """golden_skeleton.npz: the reference's kps2skl / skl2kps (utils_SH.py:26-80) on random keypoints, every mode, for the
+    full (31) and the kept (28) keypoint sets."""
+    import utils_SH  # noqa: E402  (reference)
+
+    g = torch.Generator().manual_seed(5)
+    kps_full = torch.randn(4, 31, 3, generator=g)
+    kps_keep = torch.randn(4, 28, 3, generator=g)
+    out = {"kps_full": kps_full.numpy(), "kps_keep": kps_keep.numpy()}
+    for mode in ["ori_m", "vec_m", "vec", "m"]:
+        out["skl_full_" + mode] = utils_SH.kps2skl(kps_full, mode).numpy()
+        out["skl_keep_" + mode] = utils_SH.kps2skl(kps_keep, mode).numpy()
+    for mode in ["ori_m", "vec_m", "vec"]:
+        out["back_" + mode] = utils_SH.skl2kps(torch.from_numpy(out["skl_keep_" + mode]), mode).numpy()
+    np.savez_compressed(os.path.join(HERE, "golden_skeleton.npz"), **out)
+    print("golden_skeleton", {k: v.shape for k, v in out.items()})
+
+
 def gen_big():
     h, sizes, ssz, spirals, bD, bU = load_hier_for_ref("2222")
     fenc = [[3, 16, 32, 64, 128], [[], [], [], [], []]]
@@ -366,6 +385,7 @@ def main():
         gen_multiz_small()
     if a.only in ("all", "pair"):
         gen_pair_loss()
+        gen_skeleton()
     if a.only in ("all", "big"):
         gen_big()
 
