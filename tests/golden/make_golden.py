@@ -20,6 +20,8 @@ Fixtures
   golden_multiz_small.npz         reference SpiralAutoencoder_multiz_partkps fwd + losses + bwd.
   golden_pair_loss.npz            reference angle_skl + calc_euclidean_dist_matrix + the pairwise-distance loss lines
                                   of train_funcs.py:243-284 (three weight/normalisation configurations) + d/d rec.
+  golden_aux_losses.npz           reference edge regulariser / Edge_loss / cal_volloss (train_funcs.py:22-72), looped over
+                                  the batch as the training loop does.
   golden_skeleton.npz             reference kps2skl / skl2kps (utils_SH.py:26-80), all modes.
   golden_ae_6890.npz              full-size SpiralAutoencoder (default filters, nz=256), B=2, deterministic
                                   weights (semantichuman_b200.synthetic.fill_deterministic_), outputs and
@@ -342,6 +344,57 @@ def gen_skeleton():
     print("golden_skeleton", {k: v.shape for k, v in out.items()})
 
 
+def gen_aux_losses():
+    """golden_aux_losses.npz: the reference's per-sample edge regulariser (get_target + compute_score, train_funcs.py:22-40,
+    looped over the batch as in :137-143), Edge_loss (:42-45) and part-volume loss (cal_volloss :56-72, looped as in
+    :325-333 with the face->part table of :84-89) on the 300-vertex template; values and d/d rec."""
+    import train_funcs  # noqa: E402  (reference)
+
+    h = np.load(os.path.join(HERE, "hier_small.npz"))
+    verts, faces = h["verts0"], h["faces0"].astype(np.int32)
+    V = verts.shape[0]
+    B = 3
+    g = torch.Generator().manual_seed(13)
+    tx = synthetic_meshes(verts, B, seed=31, noise=0.02)[:, :-1, :].contiguous()
+    order = np.argsort(verts[:, 1], kind="stable")
+    parts = np.array_split(order, 4)
+    vdict = {"p%d" % i: np.sort(p).astype(np.int64) for i, p in enumerate(parts)}
+    out = {"tx": tx.numpy(), "faces": faces, "part_sizes": np.asarray([len(p) for p in parts]),
+           "part_idx": np.concatenate([vdict["p%d" % i] for i in range(4)]), "parts_used": np.asarray([0, 2, 3])}
+    # edge regulariser, train_funcs.py:137-143
+    rec = (tx + 0.02 * torch.randn(tx.shape, generator=g)).requires_grad_(True)
+    loss = 0
+    for i in range(B):
+        loss = loss + train_funcs.compute_score(rec[i].unsqueeze(0), faces, train_funcs.get_target(tx[i].numpy(), faces, 1, "cpu"))
+    loss = loss / B
+    loss.backward()
+    out.update(edge_rec=rec.detach().numpy(), edge_loss=loss.detach().numpy(), edge_grec=rec.grad.numpy())
+    # Edge_loss on the unique edges
+    e = np.unique(np.sort(np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [0, 2]]]), axis=1), axis=0)
+    rec = (tx + 0.02 * torch.randn(tx.shape, generator=g)).requires_grad_(True)
+    loss = train_funcs.Edge_loss(tx, rec, torch.from_numpy(e).long())
+    loss.backward()
+    out.update(edges=e, elen_rec=rec.detach().numpy(), elen_loss=loss.detach().numpy(), elen_grec=rec.grad.numpy())
+    # part volumes, train_funcs.py:82-89 tables + :325-333 loop
+    ft = torch.from_numpy(faces)
+    vpi = torch.ones(V)
+    for k, v in enumerate(vdict.values()):
+        vpi[v] = k
+    fpi = torch.ones(len(faces))
+    for k, f in enumerate(ft):
+        fpi[k] = vpi[f[0]] if (vpi[f[0]] == vpi[f[1]] and vpi[f[0]] == vpi[f[2]]) else 100
+    rec = (tx + 0.02 * torch.randn(tx.shape, generator=g)).requires_grad_(True)
+    used = [0, 2, 3]
+    loss = 0
+    for i in range(B):
+        loss = loss + train_funcs.cal_volloss(rec[i], tx[i], ft, vpi, fpi, vdict, used)
+    loss = loss / B
+    loss.backward()
+    out.update(vol_rec=rec.detach().numpy(), vol_loss=loss.detach().numpy(), vol_grec=rec.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, "golden_aux_losses.npz"), **out)
+    print("golden_aux_losses", float(out["edge_loss"]), float(out["elen_loss"]), float(out["vol_loss"]))
+
+
 def gen_big():
     h, sizes, ssz, spirals, bD, bU = load_hier_for_ref("2222")
     fenc = [[3, 16, 32, 64, 128], [[], [], [], [], []]]
@@ -386,6 +439,7 @@ def main():
     if a.only in ("all", "pair"):
         gen_pair_loss()
         gen_skeleton()
+        gen_aux_losses()
     if a.only in ("all", "big"):
         gen_big()
 
