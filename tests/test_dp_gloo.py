@@ -59,7 +59,9 @@ def _worker(rank, world, port, q):
         xs = x[lo:hi]
         (model(xs) - xs).abs().mean().backward()
         sync.finish()
-    q.put((rank, [p.grad.clone() for p in model.parameters()], order, sync.grad_bytes()))
+    # numpy copies, not tensors: a tensor travels through the queue as a file descriptor owned by this process, and the
+    # parent may unpickle it after this process has exited
+    q.put((rank, [p.grad.detach().clone().numpy() for p in model.parameters()], order, sync.grad_bytes()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,11 +84,11 @@ def test_two_rank_average_equals_full_batch():
     full = [p.grad for p in model.parameters()]
     for rank, grads, order, nbytes in got:
         for a, b in zip(grads, full):
-            assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+            assert torch.allclose(torch.from_numpy(a), b, atol=1e-6, rtol=1e-5)
         assert order[:4] == [0, 1, 2, 3]  # decoder convs -> fc_latent_dec -> fc_latent_enc -> encoder convs
         assert nbytes == 4 * sum(p.numel() for p in model.parameters())
     for a, b in zip(got[0][1], got[1][1]):
-        assert torch.equal(a, b)
+        assert (a == b).all()
 
 
 def test_shard_batch():
