@@ -75,7 +75,7 @@ def test_two_rank_average_equals_full_batch():
         p.start()
     got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
     model = _Toy()
     g = torch.Generator().manual_seed(1)
