@@ -204,6 +204,63 @@ int shb_pair_loss_bwd(const float* tx, const float* rec, const float* kps, const
                       const float* gscale, float* grec, const void* workspace, size_t workspace_bytes, int B, int V, int NK,
                       int G, int max_part_rows, void* stream);
 
+/* ==================================================================================================================
+ * Slab layout: the trunks' internal activation format (batch innermost, 128-sample chunks, 8-channel planes).
+ *
+ *   element (r, b, c) of plane p  ->  bf16 index ((((r*NB + b/128)*P + p)*(C/8) + c/8)*128 + b%128)*8 + c%8
+ *   NB = ceil(B/128) (tail chunk zero-padded), C % 8 == 0, P = planes: 1 = bf16 mode, 2 = fp32 mode (bf16 hi + bf16 lo).
+ *
+ * One (row, chunk) pair -- a slab -- is P*C*256 contiguous bytes; what SpiralConv gathers for an output vertex
+ * (x[:, spiral_idx] of models.py:42) is S whole slabs, each moved by one cp.async.bulk (TMA) straight into the UMMA
+ * operand layout.  `rows` always counts the dummy vertex.  The entry points below replace, in this layout, the same
+ * reference call sites as their row-major counterparts above.
+ * ================================================================================================================== */
+size_t shb_slab_tensor_bytes(int rows, int B, int C, int planes);
+
+/* rows <-> slabs (main.py feeds (B, V+1, 3) fp32 tensors; models.py:129,142 reshape to/from the FC layers' (B, rows*C)).
+ * from_rows: src row-major (B, R, Cs) of `src_dtype`; internal row i takes the caller's row perm[i] (perm NULL: identity);
+ *   channels Cs..Cp-1 and samples B..128*NB-1 are written as zeros; if ymul != NULL (slab tensor shaped like dst) the result
+ *   is multiplied by act'(ymul) -- the activation derivative expressed through the layer OUTPUT (act_mul = SHB_ACT_*);
+ *   zero_last zeroes row R-1 (the mask of models.py:48-51 on the gradient path).
+ * to_rows: dst row-major (B, R, Cd), Cd <= Cp; the caller's row perm[i] receives internal row i. */
+int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, void* dst, const void* ymul, int B, int R, int Cs,
+                       int Cp, int act_mul, int zero_last, int planes, void* stream);
+int shb_slab_to_rows(const void* src, const int32_t* perm, void* dst, int dst_dtype, int B, int R, int Cp, int Cd, int planes,
+                     void* stream);
+
+/* Pool (models.py:127,148: torch.matmul(D[i] | U[i], x)) on slab tensors: dst[r] = sum_k vals[k] * src[colidx[k]],
+ * k in rowptr[r]..rowptr[r+1].  Optional epilogue for the gradient path: times act'(ymul[r]) and/or zero the last row. */
+int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx, const float* vals, void* dst, const void* ymul,
+                  int B, int rows_out, int C, int act_mul, int zero_last, int planes, void* stream);
+
+/* Weight operand images of one SpiralConv (nn.Linear weight (Cout, S*Cin) fp32, models.py:16): bf16, un-swizzled UMMA
+ * K-major core-matrix order [plane][N/8][K/8][8][8]; forward image N = pad16(Cout_p), K = S*Cin_p; backward image (per-slot
+ * transpose) N = pad16(Cin_p), K = S*Cout_p.  Cin_p / Cout_p: channel counts of the slab tensors (multiples of 8). */
+size_t shb_slab_weight_image_bytes(int S, int Ck, int Cn, int planes);
+int shb_slab_weight_images(const float* w, void* img_fwd, void* img_bwd, int S, int Cin, int Cout, int Cin_p, int Cout_p,
+                           int planes, void* stream);
+
+/* SpiralConv forward / input gradient (models.py:34-53 and the index_put_(accumulate) + mm of its autograd):
+ *   dst[u] = mask(u) * act'(ymul[u]) * act( bias + sum_{e in ptr[u]..ptr[u+1]} src[entries[e] >> 5] . Wimg[slot entries[e] & 31] )
+ * forward: entries of output row j = (table[j,s] << 5 | s), w_img = forward image, act = the layer's, ymul NULL;
+ * input gradient: entries of source row u = (j << 5 | s) over all (j,s) with table[j,s] == u (fixed order: the sum is
+ * accumulated in list order in TMEM, no atomics), w_img = backward image, bias NULL, act identity, ymul/act_mul = the
+ * PRODUCER layer's output and activation (NULL: none), zero_last = producer's mask.
+ * src (.., B, Cs) and dst (rows_dst, B, Cd) slab tensors; Cd_real = channels `bias` holds. */
+int shb_slab_conv_supported(int S, int Cs, int Cd, int planes);
+int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, const void* w_img, const float* bias, void* dst,
+                  const void* ymul, int B, int rows_dst, int S, int Cs, int Cd, int Cd_real, int act, int act_mul, int zero_last,
+                  int planes, void* stream);
+
+/* SpiralConv weight / bias gradient (the two mm of models.py:45's autograd), K = batch on tcgen05:
+ *   gw[o][s*Cin + c] = sum_{j,b} x[table[j,s]][b][c] * gz[j][b][o],   gb[o] = sum_{j,b} gz[j][b][o]   (gb may be NULL)
+ * x (rows_in, B, Cin_p), gz (rows_out, B, Cout_p) slab tensors; per-CTA partials in `workspace`, added in CTA order. */
+int shb_slab_wgrad_supported(int S, int Cin_p, int Cout_p, int planes);
+size_t shb_slab_wgrad_workspace(int S, int Cin_p, int Cout_p, int planes);
+int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, float* gb, void* workspace,
+                   size_t workspace_bytes, int B, int rows_out, int S, int Cin, int Cin_p, int Cout, int Cout_p, int skip_last,
+                   int planes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

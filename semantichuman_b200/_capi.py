@@ -39,6 +39,17 @@ SIGNATURES = {
     "shb_group_linear_gather_bwd": (c_int, [c_vp] * 10 + [c_int] * 6 + [c_vp]),
     "shb_group_linear_scatter_fwd": (c_int, [c_vp] * 8 + [c_int] * 5 + [c_vp]),
     "shb_group_linear_scatter_bwd": (c_int, [c_vp] * 10 + [c_int] * 6 + [c_vp]),
+    "shb_slab_tensor_bytes": (c_size, [c_int] * 4),
+    "shb_slab_from_rows": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
+    "shb_slab_to_rows": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_slab_pool": (c_int, [c_vp] * 6 + [c_int] * 6 + [c_vp]),
+    "shb_slab_weight_image_bytes": (c_size, [c_int] * 4),
+    "shb_slab_weight_images": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_slab_conv_supported": (c_int, [c_int] * 4),
+    "shb_slab_conv": (c_int, [c_vp] * 7 + [c_int] * 10 + [c_vp]),
+    "shb_slab_wgrad_supported": (c_int, [c_int] * 4),
+    "shb_slab_wgrad_workspace": (c_size, [c_int] * 4),
+    "shb_slab_wgrad": (c_int, [c_vp] * 6 + [c_size] + [c_int] * 9 + [c_vp]),
 }
 
 ACT_ENUM = {"identity": 0, "relu": 1, "elu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5}

@@ -1,0 +1,432 @@
+// SpiralConv forward and input gradient in the slab layout (shb_slab.cuh): one persistent, warp-specialised tcgen05 kernel.
+//
+//   forward (models.py:34-53):   y[j]  = mask * act( sum_s  x[table[j,s]] . W_s^T + b )        entries of j: (table[j,s], s)
+//   input gradient            :  gx[u] = act'(y_prev[u]) * sum_{(j,s): table[j,s]=u} gz[j] . W_s   entries of u: (j, s)
+//
+// Both are "for every destination row: a list of (source row, slot) entries; accumulate  slab(source) x Wop[slot]".
+// A tile is one destination row x one 128-sample batch chunk: M = 128 samples, N = destination channels, and every entry
+// contributes K = source channels.  The source slab arrives with ONE cp.async.bulk (TMA) already in UMMA K-major form, the
+// per-slot weight operands sit in shared memory for the lifetime of the CTA, the sum over entries happens in the TMEM
+// accumulator in list order -- fixed order, fp32, no atomics, no register gather-sum -- and the epilogue (bias, activation or
+// activation derivative, dummy-row mask, bf16 / hi-lo split) writes 512 contiguous bytes per warp and channel chunk.
+//
+// Roles: warp 0 = TMA producer (entry lists -> bulk copies into a ring of stages), warp 1 = MMA issuer (one thread),
+// warps 2-5 = epilogue (TMEM -> registers -> HBM), double-buffered accumulator.
+#include "shb_common.cuh"
+#include "shb_internal.h"
+#include "shb_slab.cuh"
+
+namespace shb {
+
+using namespace umma;
+using namespace slab;
+
+constexpr int SC_THREADS = 192;
+constexpr int SC_MAX_STAGES = 24;
+constexpr int SC_MAX_SPS = 4;  // slabs per ring stage (narrow slabs are batched so that a stage is >= 8 KB)
+
+struct SlabConvParams {
+  const uint8_t* src;      // slab tensor, CS channels, P planes
+  const int32_t* ptr;      // (rows_dst + 1) entry ranges
+  const int32_t* ent;      // (source row << 5) | slot
+  const uint8_t* w_img;    // this pass's weight operand image(s): [P][NP/8][Q][8 n][8 k] bf16 (plane stride img_plane_stride)
+  const float* bias;       // fp32, already offset to this pass's first channel; or null
+  uint8_t* dst;            // slab tensor, Cd channels, P planes
+  const uint8_t* ymul;     // slab tensor shaped like dst or null: dst = act'(ymul) * acc
+  uint32_t img_plane_stride;
+  int NB, rows_dst;
+  int CS, Q, NP;           // source channels; S*CS/8; accumulator columns of this pass (multiple of 16)
+  int n0, ncols, Cd;       // first destination channel of this pass, channels written (multiple of 8), destination channels
+  int nbias;               // entries of `bias` that exist from n0 on
+  int act, act_mul, zero_last;
+  int P;
+  int nstage, SPS;
+  int num_tiles;
+  uint32_t tmem_cols;
+};
+
+template <int P>
+__global__ void __launch_bounds__(SC_THREADS, 1) slab_conv_kernel(const SlabConvParams p) {
+  extern __shared__ __align__(1024) uint8_t dyn_smem[];
+  __shared__ __align__(8) uint64_t full_bar[SC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[SC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t img_bar;
+  __shared__ uint32_t meta_s[SC_MAX_STAGES];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t img_bytes1 = (uint32_t)p.NP * p.Q * 16;            // one plane
+  const uint32_t img_region = ((P * img_bytes1 + 128 + 1023) / 1024) * 1024;  // + 128 B zero pad, ring 1024-aligned
+  const uint32_t slab_b = (uint32_t)P * p.CS * 256;
+  const uint32_t stage_b = slab_b * p.SPS;
+  const uint32_t smem0 = smem_u32(dyn_smem);
+  const uint32_t ring0 = smem0 + img_region;
+  const uint32_t zero0 = ring0 + (uint32_t)p.nstage * stage_b;     // 2 KB of zeros (8-channel sources only)
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+
+  // ---------------------------------------------------------------- prologue
+  for (int i = tid; i < 128 / 16; i += SC_THREADS) *reinterpret_cast<uint4*>(dyn_smem + P * img_bytes1 + i * 16) = make_uint4(0, 0, 0, 0);
+  if (p.CS == 8)
+    for (int i = tid; i < PLANE_STRIDE / 16; i += SC_THREADS)
+      *reinterpret_cast<uint4*>(dyn_smem + img_region + (size_t)p.nstage * stage_b + i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 256; i += SC_THREADS) bias_s[i] = (p.bias != nullptr && i < p.nbias) ? __ldg(p.bias + i) : 0.f;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    for (int i = 0; i < p.nstage; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_init(&img_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ================================================================ producer: entry lists -> bulk copies
+    if (lane == 0) {  // weight operand image(s): resident for the whole kernel
+      mbar_expect_tx(smem_u32(&img_bar), P * img_bytes1);
+      for (int pl = 0; pl < P; ++pl)
+        for (uint32_t off = 0; off < img_bytes1; off += 32768) {
+          const uint32_t n = img_bytes1 - off < 32768 ? img_bytes1 - off : 32768;
+          bulk_load(smem0 + pl * img_bytes1 + off, p.w_img + (size_t)pl * p.img_plane_stride + off, n, smem_u32(&img_bar));
+        }
+    }
+    uint32_t slot = 0, ph = 0;
+    int t = blockIdx.x;
+    int u = t / p.NB, q = t - u * p.NB;
+    int e0 = 0, e1 = 0;
+    if (t < p.num_tiles) { e0 = __ldg(p.ptr + u); e1 = __ldg(p.ptr + u + 1); }
+    while (t < p.num_tiles) {
+      // next tile's range is fetched now, a whole tile ahead of its use
+      const int tn = t + gridDim.x;
+      const int un = tn / p.NB, qn = tn - un * p.NB;
+      int e0n = 0, e1n = 0;
+      if (tn < p.num_tiles) { e0n = __ldg(p.ptr + un); e1n = __ldg(p.ptr + un + 1); }
+      const uint8_t* srcq = p.src + (size_t)q * slab_b;
+      const size_t row_stride = (size_t)p.NB * slab_b;
+      if (e0 == e1) {  // no entries: the epilogue writes act(bias) / zeros; the MMA thread still hands the buffer over
+        if (lane == 0) {
+          mbar_wait(empty0 + slot * 8, ph ^ 1);
+          meta_s[slot] = 3u;
+          mbar_arrive(full0 + slot * 8);
+        }
+        if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
+      }
+      for (int base = e0; base < e1; base += 32) {
+        const int cnt = e1 - base < 32 ? e1 - base : 32;
+        const int mine = lane < cnt ? __ldg(p.ent + base + lane) : 0;
+        for (int i = 0; i < cnt; i += p.SPS) {
+          const int ns = cnt - i < p.SPS ? cnt - i : p.SPS;
+          uint32_t m = (base + i == e0 ? 1u : 0u) | (base + i + ns == e1 ? 2u : 0u) | ((uint32_t)ns << 2);
+          int ev[SC_MAX_SPS];
+#pragma unroll
+          for (int k = 0; k < SC_MAX_SPS; ++k) {
+            ev[k] = __shfl_sync(0xFFFFFFFFu, mine, (i + k) & 31);
+            if (k < ns) m |= (uint32_t)(ev[k] & 31) << (5 + 5 * k);
+          }
+          if (lane == 0) {
+            mbar_wait(empty0 + slot * 8, ph ^ 1);
+            meta_s[slot] = m;
+            mbar_expect_tx(full0 + slot * 8, (uint32_t)ns * slab_b);
+            const uint32_t dst = ring0 + slot * stage_b;
+#pragma unroll
+            for (int k = 0; k < SC_MAX_SPS; ++k)
+              if (k < ns) bulk_load(dst + k * slab_b, srcq + (size_t)(ev[k] >> 5) * row_stride, slab_b, full0 + slot * 8);
+          }
+          if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
+        }
+      }
+      t = tn; u = un; q = qn; e0 = e0n; e1 = e1n;
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(CHUNK, p.NP, 0, 0);
+      const uint64_t hi_b = ((uint64_t)(((uint32_t)p.Q * 128) >> 4) << 32) | ((uint64_t)1 << 46);       // SBO = Q*128
+      const uint64_t hi_a = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);                         // SBO = 128
+      const uint32_t lo_b0 = (smem0 >> 4) | ((128u >> 4) << 16);                                         // LBO = 128
+      const uint32_t nk = p.CS >= 16 ? (uint32_t)p.CS / 16 : 1u;   // MMAs (K = 16) per slab and plane
+      const uint32_t chunks_per_slot = (uint32_t)p.CS / 8;
+      mbar_wait(smem_u32(&img_bar), 0);
+      uint32_t slot = 0, ph = 0;
+      int tcount = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait_sleep(smem_u32(&tempty_bar[buf]), ((tcount >> 1) & 1) ^ 1, 32);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.NP);
+        uint32_t acc = 0;
+        for (;;) {
+          mbar_wait_sleep(full0 + slot * 8, ph, 20);
+          const uint32_t m = meta_s[slot];
+          tc_fence_after();
+          const uint32_t ns = (m >> 2) & 7u;
+          const uint32_t a_stage = ring0 + slot * stage_b;
+          for (uint32_t k = 0; k < ns; ++k) {
+            const uint32_t s = (m >> (5 + 5 * k)) & 31u;
+            const uint32_t a_slab = a_stage + k * slab_b;
+            // A: K-major, SBO = 128 (next 8 samples), LBO = 2048 (next 8 channels); 8-channel sources pair the slab with zeros
+            const uint32_t lbo_a = p.CS >= 16 ? (uint32_t)PLANE_STRIDE : zero0 - a_slab;
+            const uint32_t lo_a = ((a_slab & 0x3FFFFu) >> 4) | ((lbo_a >> 4) << 16);
+            // second plane (fp32 mode): its own distance to the zero block when the source has 8 channels
+            const uint32_t a_slab1 = a_slab + (uint32_t)p.CS * 256;
+            const uint32_t lbo_a1 = p.CS >= 16 ? (uint32_t)PLANE_STRIDE : zero0 - a_slab1;
+            const uint32_t lo_a1 = ((a_slab1 & 0x3FFFFu) >> 4) | ((lbo_a1 >> 4) << 16);
+            const uint32_t lo_b = lo_b0 + s * chunks_per_slot * 8;  // 128 B per core matrix >> 4
+            for (uint32_t kk = 0; kk < nk; ++kk) {
+              const uint32_t la = lo_a + kk * (2 * PLANE_STRIDE >> 4), lb = lo_b + kk * 16;
+              mma_bf16(tmem_d, hi_a | la, hi_b | lb, idesc, acc);
+              acc = 1;
+              if (P == 2) {  // x ~ xh + xl, w ~ wh + wl:  xh.wh + xl.wh + xh.wl  (xl.wl ~ 2^-18 relative: dropped)
+                const uint32_t plane_b = img_bytes1 >> 4;
+                mma_bf16(tmem_d, hi_a | (lo_a1 + kk * (2 * PLANE_STRIDE >> 4)), hi_b | lb, idesc, 1);
+                mma_bf16(tmem_d, hi_a | la, hi_b | (lb + plane_b), idesc, 1);
+              }
+            }
+          }
+          mma_commit_u32(empty0 + slot * 8);  // stage reusable once these MMAs have read it
+          if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
+          if (m & 2u) break;
+        }
+        mma_commit_u32(smem_u32(&tfull_bar[buf]));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ epilogue warps: TMEM -> bias / act / act' / mask -> HBM
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int b = quarter * 32 + lane;       // sample within the chunk
+    const size_t dslab = slab_bytes(p.Cd, P);
+    const uint32_t plane_d = (uint32_t)(p.Cd / 8) * PLANE_STRIDE;
+    int tcount = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      const int u = t / p.NB, q = t - u * p.NB;
+      const bool empty_tile = __ldg(p.ptr + u) == __ldg(p.ptr + u + 1);
+      const bool zero = p.zero_last && u == p.rows_dst - 1;
+      const size_t off = ((size_t)u * p.NB + q) * dslab + (size_t)(p.n0 / 8) * PLANE_STRIDE + (size_t)b * 16;
+      uint8_t* drow = p.dst + off;
+      const uint8_t* yrow = p.ymul != nullptr ? p.ymul + off : nullptr;
+      mbar_wait_sleep(smem_u32(&tfull_bar[buf]), (tcount >> 1) & 1, 64);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NP) + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.ncols) {  // accumulator fully read: hand the buffer back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (c0 + 8 * h >= p.ncols) break;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            v[i] = act_fwd((empty_tile ? 0.f : __uint_as_float(r[8 * h + i])) + bias_s[c0 + 8 * h + i], p.act);
+          const size_t coff = (size_t)(c0 / 8 + h) * PLANE_STRIDE;
+          if (yrow != nullptr) {
+            float y[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(yrow + coff)), y);
+            if (P == 2) {
+              float yl[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(yrow + coff + plane_d)), yl);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] += yl[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_out(y[i], p.act_mul);
+          }
+          if (zero) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          }
+          if (P == 1) {
+            *reinterpret_cast<uint4*>(drow + coff) = pack8(v);
+          } else {
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            *reinterpret_cast<uint4*>(drow + coff) = hi;
+            *reinterpret_cast<uint4*>(drow + coff + plane_d) = lo;
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight operand images
+// nn.Linear weight (Cout, S*Cin) fp32  ->  bf16 operand images in the un-swizzled K-major core-matrix layout
+//   [plane][N/8][Q][8 n][8 k],  Q = K/8:
+//   forward : N = pad16(Cout_p), K = S*Cin_p,   img[n][s*Cin_p + c]  = W[n][s*Cin + c]
+//   backward: N = pad16(Cin_p),  K = S*Cout_p,  img[n][s*Cout_p + o] = W[o][s*Cin + n]      (per-slot transpose)
+// Padded channels are zero.  planes == 2 adds the lo image (w - bf16(w)) behind the hi image.
+__global__ void slab_weight_image_kernel(const float* __restrict__ w, uint8_t* __restrict__ img_f, uint8_t* __restrict__ img_b,
+                                         int S, int Cin, int Cout, int Cin_p, int Cout_p, int planes) {
+  const int Nf = (Cout_p + 15) / 16 * 16, Qf = S * Cin_p / 8, Nb = (Cin_p + 15) / 16 * 16, Qb = S * Cout_p / 8;
+  const int nf = Nf * Qf, nb = Nb * Qb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += gridDim.x * blockDim.x) {
+    const bool fwd = i < nf;
+    const int c = fwd ? i : i - nf;
+    const int Q = fwd ? Qf : Qb, N = fwd ? Nf : Nb;
+    const int n = c / Q, q = c - n * Q;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = q * 8 + e;
+      float x = 0.f;
+      if (fwd) {
+        const int s = k / Cin_p, ci = k - s * Cin_p;
+        if (n < Cout && ci < Cin) x = __ldg(w + (size_t)n * S * Cin + s * Cin + ci);
+      } else {
+        const int s = k / Cout_p, o = k - s * Cout_p;
+        if (n < Cin && o < Cout) x = __ldg(w + (size_t)o * S * Cin + s * Cin + n);
+      }
+      v[e] = x;
+    }
+    uint8_t* img = fwd ? img_f : img_b;
+    const size_t off = (((size_t)(n >> 3) * Q + q) * 8 + (n & 7)) * 16;
+    if (planes == 1) {
+      *reinterpret_cast<uint4*>(img + off) = pack8(v);
+    } else {
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(img + off) = hi;
+      *reinterpret_cast<uint4*>(img + (size_t)N * Q * 16 + off) = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+constexpr size_t SC_SMEM_MAX = 227 * 1024 - 3072;  // dynamic budget: leave room for the static part (barriers, bias)
+
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+struct SlabConvPlan { int NP, nstage, SPS; size_t smem; };
+
+// Columns per pass (all of them unless the weight image would not leave room for a 3-stage ring), ring depth, smem bytes.
+static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
+  const int Q = S * CS / 8;
+  const size_t slab_b = (size_t)P * CS * 256;
+  int SPS = 1;
+  while (SPS < SC_MAX_SPS && slab_b * SPS < 8192) SPS *= 2;
+  const size_t stage_b = slab_b * SPS, zero_b = CS == 8 ? PLANE_STRIDE : 0;
+  for (int NP = NPt > 256 ? 256 : NPt; NP >= 16; NP -= 16) {
+    if (NPt % NP != 0 && NP != NPt) continue;  // equal passes
+    const size_t img_region = (((size_t)P * NP * Q * 16 + 128 + 1023) / 1024) * 1024;
+    if (img_region + zero_b + 2 * stage_b > SC_SMEM_MAX) continue;
+    size_t n = (SC_SMEM_MAX - img_region - zero_b) / stage_b;
+    if (n < 3 && NP > 16) continue;  // prefer a narrower pass with a deeper ring
+    if (n > SC_MAX_STAGES) n = SC_MAX_STAGES;
+    out->NP = NP; out->nstage = (int)n; out->SPS = SPS; out->smem = img_region + zero_b + n * stage_b;
+    return true;
+  }
+  return false;
+}
+
+static int slab_conv_launch(const SlabConvParams& p, size_t smem, cudaStream_t st) {
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[p.P]) {
+    cudaError_t e = p.P == 1 ? cudaFuncSetAttribute(slab_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX)
+                             : cudaFuncSetAttribute(slab_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[p.P] = true;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  if (p.P == 1) slab_conv_kernel<1><<<grid, SC_THREADS, smem, st>>>(p);
+  else slab_conv_kernel<2><<<grid, SC_THREADS, smem, st>>>(p);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+size_t shb_slab_tensor_bytes(int rows, int B, int C, int planes) {
+  if (rows <= 0 || B <= 0 || C <= 0 || (C & 7) || planes < 1 || planes > 2) return 0;
+  return slab::tensor_bytes(rows, B, C, planes);
+}
+
+size_t shb_slab_weight_image_bytes(int S, int Ck, int Cn, int planes) {
+  if (S <= 0 || Ck <= 0 || Cn <= 0 || (Ck & 7) || (Cn & 7) || planes < 1 || planes > 2) return 0;
+  return (size_t)planes * pad16(Cn) * (S * Ck / 8) * 16;
+}
+
+int shb_slab_weight_images(const float* w, void* img_fwd, void* img_bwd, int S, int Cin, int Cout, int Cin_p, int Cout_p, int planes,
+                           void* stream) {
+  if (!w || !img_fwd || !img_bwd || S <= 0 || S > 32 || Cin <= 0 || Cout <= 0 || Cin_p < Cin || Cout_p < Cout || (Cin_p & 7) ||
+      (Cout_p & 7) || planes < 1 || planes > 2)
+    return SHB_E_ARG;
+  const int total = pad16(Cout_p) * (S * Cin_p / 8) + pad16(Cin_p) * (S * Cout_p / 8);
+  int grid = ceil_div(total, 256);
+  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+  slab_weight_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)img_fwd, (uint8_t*)img_bwd, S, Cin, Cout, Cin_p,
+                                                                  Cout_p, planes);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_slab_conv_supported(int S, int Cs, int Cd, int planes) {
+  SlabConvPlan plan;
+  if (S <= 0 || S > 32 || planes < 1 || planes > 2) return 0;
+  if (!(Cs == 8 || (Cs % 16 == 0 && Cs <= 256)) || (Cd & 7) || Cd <= 0 || Cd > 1024) return 0;
+  return slab_conv_plan(S, Cs, pad16(Cd), planes, &plan) ? 1 : 0;
+}
+
+int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, const void* w_img, const float* bias, void* dst,
+                  const void* ymul, int B, int rows_dst, int S, int Cs, int Cd, int Cd_real, int act, int act_mul, int zero_last,
+                  int planes, void* stream) {
+  if (!src || !ptr || !entries || !w_img || !dst || B <= 0 || rows_dst <= 0) return SHB_E_ARG;
+  if (!shb_slab_conv_supported(S, Cs, Cd, planes)) return SHB_E_UNSUPPORTED;
+  SlabConvPlan plan;
+  const int NPt = pad16(Cd);
+  slab_conv_plan(S, Cs, NPt, planes, &plan);
+  SlabConvParams p{};
+  p.src = (const uint8_t*)src; p.ptr = ptr; p.ent = entries; p.dst = (uint8_t*)dst; p.ymul = (const uint8_t*)ymul;
+  p.NB = slab::num_chunks(B); p.rows_dst = rows_dst;
+  p.CS = Cs; p.Q = S * Cs / 8; p.Cd = Cd;
+  p.act = act; p.act_mul = act_mul; p.zero_last = zero_last; p.P = planes;
+  p.nstage = plan.nstage; p.SPS = plan.SPS;
+  p.num_tiles = rows_dst * p.NB;
+  p.img_plane_stride = (uint32_t)NPt * p.Q * 16;
+  for (int n0 = 0; n0 < NPt; n0 += plan.NP) {
+    if (n0 >= Cd) break;
+    p.NP = plan.NP; p.n0 = n0;
+    p.ncols = Cd - n0 < plan.NP ? Cd - n0 : plan.NP;
+    p.w_img = (const uint8_t*)w_img + (size_t)(n0 / 8) * p.Q * 128;
+    p.bias = bias ? bias + n0 : nullptr;
+    p.nbias = Cd_real - n0 < p.ncols ? (Cd_real - n0 > 0 ? Cd_real - n0 : 0) : p.ncols;  // bias holds Cd_real entries
+    uint32_t cols = 32;
+    while (cols < 2u * p.NP) cols <<= 1;
+    p.tmem_cols = cols;
+    int rc = slab_conv_launch(p, plan.smem, (cudaStream_t)stream);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -171,6 +171,9 @@ class PoolMatrix:
         # structural fact the fused conv+down-pool relies on (mesh_sampling.py:214-227): one 1.0 per row
         self.is_selection = bool(self.nnz == rows and (counts == 1).all() and (vals == 1.0).all())
         self.selection_cols = colidx.copy() if self.is_selection else None
+        # last row == e_dummy (main.py:190-191): the pooled tensor's dummy row is the input's dummy row, nothing else
+        self.dummy_preserving = bool(rows > 0 and counts[-1] == 1 and colidx[rowptr[rows - 1]] == cols - 1
+                                     and vals[rowptr[rows - 1]] == 1.0)
         t_rowptr, t_colidx, t_vals = csr_transpose(rowptr, colidx, vals, rows, cols)
         self.device = torch.device(device)
         dev = self.device

@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functions as fn
+from . import slab
 from ._capi import ACT_ENUM
 from .indexing import PoolMatrix, SpiralGeometry, locality_order, normalise_spiral
 
@@ -161,20 +162,27 @@ class _SpiralTrunk(nn.Module):
             self._pD = [self._pD[i].permuted(full[i + 1], full[i]) for i in range(n_levels)]
             self._pU = [self._pU[i].permuted(full[i], full[i + 1]) for i in range(n_levels)]
             self._io_perm = PoolMatrix.from_permutation(full[0], dev)
-        geoms = [SpiralGeometry(tables[i], tables[i].shape[0], dev, dummy_row_grad=False) for i in range(n_levels)]
+        self._perm_dev = None if self._perm is None else torch.as_tensor(full[0], dtype=torch.int32, device=dev)
+        # a pool keeps the dummy row zero only if its last row is exactly e_dummy (main.py:190-191 builds it that way)
+        d_ok = [pm.dummy_preserving for pm in self._pD]
+        u_ok = [pm.dummy_preserving for pm in self._pU]
+        geoms = [slab.SlabGeometry(tables[i], tables[i].shape[0], dev, dummy_row_grad=False) for i in range(n_levels)]
         # encoder plan: (conv index, geometry, pool-after or None)
         self._enc_plan = []
         for j, lvl in enumerate(self._enc_lvl):
             last_at_level = (j + 1 == len(self._enc_lvl)) or (self._enc_lvl[j + 1] != lvl)
             # conv 0 reads the caller's tensor (its dummy row is zero only by the dataset's convention); every later
             # encoder conv reads a masked conv output, possibly through a pool that maps dummy -> dummy
-            geoms[lvl] = geoms[lvl].with_flags(src_dummy_zero=(j > 0))
+            first_at_level = (j == 0) or (self._enc_lvl[j - 1] != lvl)
+            # input dummy row known zero: a masked conv output, directly or through a dummy-preserving pool / selection
+            src_zero = (j > 0) and (not first_at_level or d_ok[lvl - 1])
+            geoms[lvl] = geoms[lvl].with_flags(src_dummy_zero=src_zero, dummy_row_grad=not src_zero and j > 0)
             if not last_at_level:
                 self._enc_plan.append((j, geoms[lvl], None))
             elif fuse_pool and sel_rows[lvl] is not None and sel_rows[lvl][-1] == geoms[lvl].rows_in - 1:
                 # D is a row selection: evaluate the conv only at the kept vertices (+ dummy)
-                self._enc_plan.append((j, geoms[lvl].restricted(sel_rows[lvl], dummy_row_grad=False,
-                                                                src_dummy_zero=(j > 0)), None))
+                self._enc_plan.append((j, geoms[lvl].restricted(sel_rows[lvl], dummy_row_grad=geoms[lvl].dummy_row_grad,
+                                                                src_dummy_zero=src_zero), None))
             else:
                 self._enc_plan.append((j, geoms[lvl], self._pD[lvl]))
         # decoder plan: (conv index, geometry, pool-before or None); only the very first decoder conv can see a live
@@ -183,8 +191,8 @@ class _SpiralTrunk(nn.Module):
         for j, lvl in enumerate(self._dec_lvl):
             first_at_level = (j == 0) or (self._dec_lvl[j - 1] != lvl)
             # decoder conv 0 sees the live FC row; all later decoder convs read masked outputs (through U: dummy -> dummy)
-            g = geoms[lvl].with_flags(dummy_row_grad=True, src_dummy_zero=False) if j == 0 else \
-                geoms[lvl].with_flags(src_dummy_zero=True)
+            src_zero = j > 0 and (not first_at_level or u_ok[lvl])
+            g = geoms[lvl].with_flags(dummy_row_grad=not src_zero, src_dummy_zero=src_zero)
             self._dec_plan.append((j, g, self._pU[lvl] if first_at_level else None))
         self.compute_dtype = torch.float32
 
@@ -207,9 +215,13 @@ class _SpiralTrunk(nn.Module):
                 perm.append(locality_order(tables[l + 1]))
         return perm
 
+    def _planes(self):
+        return 1 if self.compute_dtype == torch.bfloat16 else 2
+
     def set_compute_dtype(self, dtype):
-        """torch.float32 (default; exact-fp32 kernels, 1e-4 parity) or torch.bfloat16 (bf16 activations and
-        operands, fp32 accumulation, fp32 master weights; 2e-2 parity)."""
+        """torch.float32 (default; every operand split into bf16 hi + lo, three tensor-core products per term, fp32
+        accumulation: 1e-4 parity) or torch.bfloat16 (bf16 activations and operands, fp32 accumulation, fp32 master
+        weights; 2e-2 parity)."""
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError("compute dtype must be float32 or bfloat16")
         self.compute_dtype = dtype
@@ -218,24 +230,24 @@ class _SpiralTrunk(nn.Module):
     def _encode_trunk(self, x):
         if not x.is_cuda:
             raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
-        if self._io_perm is not None:
-            x = fn.pool(x.contiguous(), self._io_perm)  # caller's vertex order -> internal order (row gather)
+        s = slab.from_rows(x, self._perm_dev, self._planes())  # caller's vertex order -> internal order, slab layout
         for j, geom, pm in self._enc_plan:
-            x = self.conv[j](x, geom, self.compute_dtype)  # the first conv casts (and pads) its fp32 input itself
+            c = self.conv[j]
+            s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name)
             if pm is not None:
-                x = fn.pool(x, pm)
-        return x
+                s = slab.pool(s, pm)
+        return slab.to_rows(s, None, self.compute_dtype)  # last level: caller's order (FC layout of models.py:128)
 
     def _decode_trunk(self, x):
-        x = x.to(self.compute_dtype)
+        if not x.is_cuda:
+            raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
+        s = slab.from_rows(x, None, self._planes())
         for j, geom, pm in self._dec_plan:
             if pm is not None:
-                x = fn.pool(x, pm)
-            x = self.dconv[j](x, geom)
-        x = x.float()
-        if self._io_perm is not None:
-            x = fn.PoolFn.apply(x, self._io_perm, True)  # internal order -> caller's order (the inverse gather)
-        return x
+                s = slab.pool(s, pm)
+            c = self.dconv[j]
+            s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name)
+        return slab.to_rows(s, self._perm_dev, torch.float32)  # internal order -> caller's order
 
 
 class SpiralAutoencoder(_SpiralTrunk):

@@ -1,0 +1,320 @@
+"""Slab-layout trunk operators: the autograd layer over libshb200's shb_slab_* entry points.
+
+Inside the model trunks activations live batch-innermost in 128-sample chunks ("slab layout", csrc/shb_slab.cuh):
+what SpiralConv gathers for one output vertex (``x[:, spiral_idx]``, models.py:42) is then S contiguous slabs, each
+moved by one TMA bulk copy straight into tensor-core operand form; Pool (models.py:127,148) is a weighted sum of whole
+slabs.  A :class:`Slab` wraps one such tensor together with what its consumers need to know about its producer.
+
+Gradient convention inside a trunk (private to this module): the gradient that flows back INTO a slab tensor is the
+gradient w.r.t. the producer's *pre-activation*.  Every consumer's backward kernel multiplies by act'(y) of the producer
+(read from the saved output y) and applies the producer's dummy-row mask in its epilogue, so no stand-alone
+activation-derivative pass over the gradients exists.  ``from_rows`` / ``to_rows`` are the only ways in and out, and they
+translate between this convention and ordinary autograd gradients.
+
+planes = 1: bf16 activations and operands (bf16 mode, 2e-2 parity).  planes = 2: every activation and weight is the
+sum of two bf16 numbers (hi + lo, ~16 mantissa bits) and every product runs as three tensor-core MMAs
+(hi.hi + lo.hi + hi.lo, fp32 accumulation) -- the fp32 mode, 1e-4 parity (hard part 1).
+"""
+import numpy as np
+import torch
+
+from . import functions as fn
+from ._capi import ACT_ENUM, BF16, F32, lib
+from .functions import _call, _count, _cuda, _p, _stream
+
+CHUNK = 128
+
+
+def pad_channels(c):
+    """Channel count of the slab tensor that carries c channels: 8, 16, 32, 64, 128, 256 (zeros above c)."""
+    for p in (8, 16, 32, 64, 128, 256):
+        if c <= p:
+            return p
+    raise ValueError(f"slab kernels support at most 256 channels per layer, got {c}")
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+class Slab:
+    """A slab tensor plus what the consumers of its gradient need: the activation that produced it (its derivative is taken
+    through the stored output) and whether the producer zeroed the dummy row (models.py:48-51)."""
+
+    __slots__ = ("t", "rows", "B", "C", "Cp", "planes", "act", "masked")
+
+    def __init__(self, t, rows, B, C, Cp, planes, act=0, masked=False):
+        self.t, self.rows, self.B, self.C, self.Cp, self.planes, self.act, self.masked = t, rows, B, C, Cp, planes, act, masked
+
+    @staticmethod
+    def shape_for(rows, B, Cp, planes):
+        return (rows, (B + CHUNK - 1) // CHUNK, planes, Cp // 8, CHUNK, 8)
+
+    @staticmethod
+    def empty(rows, B, C, Cp, planes, device, act=0, masked=False):
+        t = torch.empty(Slab.shape_for(rows, B, Cp, planes), dtype=torch.bfloat16, device=device)
+        return Slab(t, rows, B, C, Cp, planes, act, masked)
+
+    def like(self, t):
+        return Slab(t, self.rows, self.B, self.C, self.Cp, self.planes, self.act, self.masked)
+
+    @property
+    def esize_bytes(self):
+        return 2 * self.planes
+
+
+class SlabGeometry:
+    """Entry lists of one SpiralConv call shape, resident on the device.
+
+    forward : for every output row j the entries (table[j,s] << 5 | s); entries reading the source's dummy row are dropped
+              when that row is known to be zero.
+    backward: for every source row u the entries (j << 5 | s) with table[j,s] == u, ascending in (j, s) -- the fixed
+              summation order of the input gradient; rows whose gz is zero by the mask are dropped, and the
+              dummy source row gets no entries unless its gradient is wanted.
+    """
+
+    def __init__(self, table, rows_in, device, zero_last_row=True, dummy_row_grad=True, src_dummy_zero=False):
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        self.rows_out, self.S = int(table.shape[0]), int(table.shape[1])
+        self.rows_in = int(rows_in)
+        if self.S > 32:
+            raise ValueError("slab kernels support spiral lengths up to 32")
+        if table.min() < 0 or table.max() >= rows_in:
+            raise ValueError("spiral index out of range")
+        self.zero_last_row, self.dummy_row_grad, self.src_dummy_zero = bool(zero_last_row), bool(dummy_row_grad), bool(src_dummy_zero)
+        self.table_host = table
+        self.device = torch.device(device)
+        S = self.S
+        slots = np.tile(np.arange(S, dtype=np.int64), self.rows_out)
+        flat = table.reshape(-1).astype(np.int64)
+        # forward lists
+        keep = np.ones(flat.shape, bool) if not self.src_dummy_zero else flat != self.rows_in - 1
+        counts = keep.reshape(self.rows_out, S).sum(1)
+        self.ptr_f = self._dev(np.concatenate([[0], np.cumsum(counts)]))
+        self.ent_f = self._dev(((flat << 5) | slots)[keep])
+        # backward lists: stable sort of the flattened table by source row == ascending (j, s) within a row
+        j_of = np.repeat(np.arange(self.rows_out, dtype=np.int64), S)
+        live = np.ones(flat.shape, bool)
+        if self.zero_last_row:
+            live &= j_of != self.rows_out - 1
+        if not self.dummy_row_grad:
+            live &= flat != self.rows_in - 1
+        order = np.argsort(flat[live], kind="stable")
+        counts_b = np.bincount(flat[live], minlength=self.rows_in)
+        self.ptr_b = self._dev(np.concatenate([[0], np.cumsum(counts_b)]))
+        self.ent_b = self._dev(((j_of[live] << 5) | slots[live])[order])
+        self.table = torch.from_numpy(table).to(self.device)
+        self.n_fwd_entries, self.n_bwd_entries = int(counts.sum()), int(counts_b.sum())
+
+    def _dev(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        if a.size and a.max() >= 2 ** 31:
+            raise ValueError("table too large for 32-bit entry lists")
+        if a.size == 0:
+            a = np.zeros(1, np.int64)
+        return torch.from_numpy(a.astype(np.int32)).to(self.device)
+
+    def _flags(self, kw):
+        f = dict(zero_last_row=self.zero_last_row, dummy_row_grad=self.dummy_row_grad, src_dummy_zero=self.src_dummy_zero)
+        f.update({k: bool(v) for k, v in kw.items()})
+        return f
+
+    def restricted(self, out_rows, **kw):
+        """Geometry that evaluates only `out_rows` (source-vertex ids, dummy last)."""
+        out_rows = np.asarray(out_rows, dtype=np.int64)
+        return SlabGeometry(self.table_host[out_rows], self.rows_in, self.device, **self._flags(kw))
+
+    def with_flags(self, **kw):
+        """Same table, different promises about the dummy rows (the entry lists depend on them)."""
+        f = self._flags(kw)
+        if all(getattr(self, k) == v for k, v in f.items()):
+            return self
+        return SlabGeometry(self.table_host, self.rows_in, self.device, **f)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"semantichuman_b200 supports float32 and bfloat16 tensors, got {t.dtype}")
+
+
+def _from_rows_raw(x, perm, Cp, planes, ymul=None, act_mul=0, zero_last=False):
+    B, R, Cs = x.shape
+    out = torch.empty(Slab.shape_for(R, B, Cp, planes), dtype=torch.bfloat16, device=x.device)
+    _call(f"slab_from_rows[{R}x{Cs}>{Cp}]", {"bytes": float(B) * R * (Cs * x.element_size() + Cp * 2 * planes)},
+          lib.shb_slab_from_rows, _p(x), _dt(x), _p(perm), _p(out), _p(ymul), B, R, Cs, Cp, int(act_mul), int(bool(zero_last)),
+          planes, _stream())
+    _count()
+    return out
+
+
+def _to_rows_raw(t, perm, B, R, Cp, Cd, planes, dtype):
+    out = torch.empty((B, R, Cd), dtype=dtype, device=t.device)
+    _call(f"slab_to_rows[{R}x{Cp}>{Cd}]", {"bytes": float(B) * R * (Cd * out.element_size() + Cp * 2 * planes)},
+          lib.shb_slab_to_rows, _p(t), _p(perm), _p(out), _dt(out), B, R, Cp, Cd, planes, _stream())
+    _count()
+    return out
+
+
+class FromRowsFn(torch.autograd.Function):
+    """Caller layout (B, rows, C) -> slab layout (vertex permutation, channel padding, dtype conversion in one pass)."""
+
+    @staticmethod
+    def forward(ctx, x, perm, Cp, planes):
+        _cuda(x)
+        x = x.contiguous()
+        ctx.perm, ctx.meta, ctx.xdtype = perm, (x.shape[0], x.shape[1], x.shape[2], Cp, planes), x.dtype
+        return _from_rows_raw(x, perm, Cp, planes)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, R, Cs, Cp, planes = ctx.meta
+        return _to_rows_raw(g.contiguous(), ctx.perm, B, R, Cp, Cs, planes, ctx.xdtype), None, None, None
+
+
+class ToRowsFn(torch.autograd.Function):
+    """Slab layout -> caller layout (B, rows, C).  Backward re-enters the trunk's gradient convention: the incoming
+    gradient is multiplied by act'(y) of the slab's producer and masked."""
+
+    @staticmethod
+    def forward(ctx, t, perm, meta, dtype):
+        rows, B, C, Cp, planes, act, masked = meta
+        ctx.perm, ctx.meta = perm, meta
+        ctx.save_for_backward(t)
+        return _to_rows_raw(t, perm, B, rows, Cp, C, planes, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (t,) = ctx.saved_tensors
+        rows, B, C, Cp, planes, act, masked = ctx.meta
+        g = g.contiguous()
+        ymul = t if act != 0 else None
+        return _from_rows_raw(g, ctx.perm, Cp, planes, ymul, act, masked), None, None, None
+
+
+def from_rows(x, perm=None, planes=1, Cp=None):
+    """(B, rows, C) float32/bfloat16 CUDA tensor -> Slab (internal row i = caller's row perm[i])."""
+    B, R, C = x.shape
+    Cp = pad_channels(C) if Cp is None else Cp
+    return Slab(FromRowsFn.apply(x, perm, Cp, planes), R, B, C, Cp, planes, 0, False)
+
+
+def to_rows(s, perm=None, dtype=torch.float32):
+    return ToRowsFn.apply(s.t, perm, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked), dtype)
+
+
+class SlabPoolFn(torch.autograd.Function):
+    """y[r] = sum_k P[r,k] x[k] over whole slabs (models.py:127,148); backward = P^T, times act' of x's producer."""
+
+    @staticmethod
+    def forward(ctx, t, pm, meta):
+        rows, B, C, Cp, planes, act, masked = meta
+        if rows != pm.rows_in:
+            raise ValueError(f"pool expects {pm.rows_in} rows, got {rows}")
+        ctx.pm, ctx.meta = pm, meta
+        ctx.save_for_backward(t)
+        y = torch.empty(Slab.shape_for(pm.rows_out, B, Cp, planes), dtype=torch.bfloat16, device=t.device)
+        _call(f"slab_pool[{pm.rows_in}>{pm.rows_out}x{C}]", fn._pool_meta(B, pm, Cp, 2 * planes, False), lib.shb_slab_pool, _p(t),
+              _p(pm.rowptr), _p(pm.colidx), _p(pm.vals), _p(y), None, B, pm.rows_out, Cp, 0, 0, planes, _stream())
+        _count()
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (t,) = ctx.saved_tensors
+        pm = ctx.pm
+        rows, B, C, Cp, planes, act, masked = ctx.meta
+        gx = torch.empty_like(t)
+        _call(f"slab_pool_bwd[{pm.rows_out}>{pm.rows_in}x{C}]", fn._pool_meta(B, pm, Cp, 2 * planes, True), lib.shb_slab_pool,
+              _p(g.contiguous()), _p(pm.t_rowptr), _p(pm.t_colidx), _p(pm.t_vals), _p(gx), _p(t) if act != 0 else None, B,
+              pm.rows_in, Cp, act, int(masked), planes, _stream())
+        _count()
+        return gx, None, None
+
+
+def pool(s, pm):
+    t = SlabPoolFn.apply(s.t, pm, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked))
+    return Slab(t, pm.rows_out, s.B, s.C, s.Cp, s.planes, 0, False)
+
+
+class SlabConvFn(torch.autograd.Function):
+    """y = mask * act(W . gather(x) + b) (models.py:34-53) on slab tensors.
+
+    forward : weight-image kernel + ONE fused gather-GEMM kernel (TMA slabs -> tcgen05 -> bias/act/mask epilogue).
+    backward: weight/bias gradient kernel (+ fixed-order reduce) and the input-gradient kernel, which also applies act' and
+              the mask of x's producer.  The incoming gradient is already w.r.t. this layer's pre-activation (see module
+              docstring)."""
+
+    @staticmethod
+    def forward(ctx, t, weight, bias, geom, act, meta, want_gx):
+        rows, B, C, Cp, planes, xact, xmasked = meta
+        _cuda(t, weight, bias)
+        cout, k = weight.shape
+        S = geom.S
+        if rows != geom.rows_in or k != S * C:
+            raise ValueError(f"shape mismatch: x rows {rows} channels {C}, weight {tuple(weight.shape)}, geometry "
+                             f"rows_in={geom.rows_in} S={S}")
+        if geom.table.device != t.device:
+            raise RuntimeError("spiral tables live on a different device than x")
+        cout_p = pad_channels(cout)
+        if not lib.shb_slab_conv_supported(S, Cp, cout_p, planes) or not lib.shb_slab_conv_supported(S, cout_p, Cp, planes) \
+                or not lib.shb_slab_wgrad_supported(S, Cp, cout_p, planes):
+            raise NotImplementedError(f"SpiralConv shape S={S}, {C}->{cout} channels is outside what the slab kernels support")
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        dev = t.device
+        img_f = torch.empty(lib.shb_slab_weight_image_bytes(S, Cp, cout_p, planes), dtype=torch.uint8, device=dev)
+        img_b = torch.empty(lib.shb_slab_weight_image_bytes(S, cout_p, Cp, planes), dtype=torch.uint8, device=dev)
+        _call("slab_weight_images", {"bytes": 4.0 * w32.numel() + img_f.numel() + img_b.numel()}, lib.shb_slab_weight_images,
+              _p(w32), _p(img_f), _p(img_b), S, C, cout, Cp, cout_p, planes, _stream())
+        y = torch.empty(Slab.shape_for(geom.rows_out, B, cout_p, planes), dtype=torch.bfloat16, device=dev)
+        tag = f"[{rows}>{geom.rows_out}x{S}x{C}>{cout}]"
+        cmeta = fn._conv_meta(B, rows, geom.rows_out, S, C, cout, 2 * planes)
+        _call("slabconv_fwd" + tag, cmeta, lib.shb_slab_conv, _p(t), _p(geom.ptr_f), _p(geom.ent_f), _p(img_f), _p(b32), _p(y),
+              None, B, geom.rows_out, S, Cp, cout_p, cout, act, 0, int(geom.zero_last_row), planes, _stream())
+        _count(2)
+        ctx.save_for_backward(t, img_b)
+        ctx.geom, ctx.meta, ctx.tag, ctx.cmeta = geom, meta, tag, cmeta
+        ctx.dims = (cout, cout_p, bias is not None, weight.dtype, bool(want_gx))
+        return y
+
+    @staticmethod
+    def backward(ctx, gz):
+        t, img_b = ctx.saved_tensors
+        geom = ctx.geom
+        rows, B, C, Cp, planes, xact, xmasked = ctx.meta
+        cout, cout_p, has_bias, wdtype, want_gx = ctx.dims
+        S = geom.S
+        gz = gz.contiguous()
+        dev = t.device
+        gw = gb = gx = None
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            nbytes = lib.shb_slab_wgrad_workspace(S, Cp, cout_p, planes)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            gw = torch.empty((cout, S * C), dtype=torch.float32, device=dev)
+            gb = torch.empty((cout,), dtype=torch.float32, device=dev) if (has_bias and ctx.needs_input_grad[2]) else None
+            _call("slabconv_wgrad" + ctx.tag, ctx.cmeta, lib.shb_slab_wgrad, _p(t), _p(geom.table), _p(gz), _p(gw), _p(gb),
+                  _p(ws), nbytes, B, geom.rows_out, S, C, Cp, cout, cout_p, int(geom.zero_last_row), planes, _stream())
+            _count(2)
+            if wdtype != torch.float32:
+                gw = gw.to(wdtype)
+            if not ctx.needs_input_grad[1]:
+                gw = None
+        if want_gx and ctx.needs_input_grad[0]:
+            gx = torch.empty_like(t)
+            _call("slabconv_dgrad" + ctx.tag, ctx.cmeta, lib.shb_slab_conv, _p(gz), _p(geom.ptr_b), _p(geom.ent_b), _p(img_b), None,
+                  _p(gx), _p(t) if xact != 0 else None, B, rows, S, cout_p, Cp, C, 0, xact, int(xmasked), planes, _stream())
+            _count()
+        return gx, gw, gb, None, None, None, None
+
+
+def spiral_conv(s, weight, bias, geom, activation="elu", want_gx=True):
+    """Slab in, Slab out.  `want_gx=False` skips the input gradient (first layer of an encoder fed with data)."""
+    if activation not in ACT_ENUM:
+        raise NotImplementedError(activation)
+    act = ACT_ENUM[activation]
+    t = SlabConvFn.apply(s.t, weight, bias, geom, act, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked), want_gx)
+    cout = weight.shape[0]
+    return Slab(t, geom.rows_out, s.B, cout, pad_channels(cout), s.planes, act, geom.zero_last_row)
