@@ -112,8 +112,8 @@ def base_config(args, world):
 def cpu_reference_run(steps, warmup, batch=16, threads=None):
     """The reference algorithm (oracle port of models.py + train_funcs.py:495-510) on the host cores."""
     from oracle import spiral_oracle as so
-    from semantichuman_b200.assets import Hierarchy
-    from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+    from tests.golden.loader import Hierarchy
+    from tests.golden.synthetic import fill_deterministic_, synthetic_meshes
 
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -180,8 +180,8 @@ def run_own(args):
 
     import semantichuman_b200 as shb
     from semantichuman_b200 import functions as fn
-    from semantichuman_b200.assets import Hierarchy
-    from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+    from tests.golden.loader import Hierarchy
+    from tests.golden.synthetic import fill_deterministic_, synthetic_meshes
     from semantichuman_b200.train import TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import semantichuman_b200 as shb
 from semantichuman_b200 import functions as fn
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 
 lvl, cin, cout = (int(v) for v in os.environ.get("LAYER", "0,32,16").split(","))
 B = int(os.environ.get("B", "256")); reps = int(os.environ.get("REPS", "5"))

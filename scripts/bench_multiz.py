@@ -10,8 +10,8 @@ import numpy as np
 import torch
 import semantichuman_b200 as shb
 from semantichuman_b200 import functions as fn
-from semantichuman_b200.assets import Hierarchy
-from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+from tests.golden.loader import Hierarchy
+from tests.golden.synthetic import fill_deterministic_, synthetic_meshes
 from tests.golden.constants import KPS_INDEX_LIST, PART_LIST
 
 dev = "cuda:0"

@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import semantichuman_b200 as shb
-from semantichuman_b200.assets import Hierarchy
-from semantichuman_b200.synthetic import synthetic_meshes
+from tests.golden.loader import Hierarchy
+from tests.golden.synthetic import synthetic_meshes
 
 dev = "cuda:0"; B = 256
 h = Hierarchy("2222")

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import semantichuman_b200 as shb
 from semantichuman_b200 import functions as fn
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 dev = "cuda:0"; B = 256
 dt = torch.bfloat16 if os.environ.get("DT", "bf16") == "bf16" else torch.float32
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6555.2

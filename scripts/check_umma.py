@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import semantichuman_b200 as shb
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 from tests.helpers import relerr
 
 B = int(os.environ.get("B", "5"))

@@ -3,8 +3,8 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import semantichuman_b200 as shb
-from semantichuman_b200.assets import Hierarchy
-from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+from tests.golden.loader import Hierarchy
+from tests.golden.synthetic import fill_deterministic_, synthetic_meshes
 from semantichuman_b200.train import TrainStep
 import bench
 dev = torch.device("cuda", 0)

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import semantichuman_b200 as shb
 from semantichuman_b200 import functions as fn
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 from semantichuman_b200.indexing import locality_order, normalise_spiral
 
 ap = argparse.ArgumentParser()

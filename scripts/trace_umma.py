@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import semantichuman_b200 as shb
 from semantichuman_b200 import _capi
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 lvl, cin, cout = (int(v) for v in os.environ.get("LAYER", "0,32,16").split(","))
 dev = "cuda:0"; B = 256
 h = Hierarchy("2222")

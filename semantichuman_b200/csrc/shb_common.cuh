@@ -77,6 +77,18 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
     default: return v;
   }
 }
+// Epilogue version: ELU / sigmoid through ex2.approx (absolute error ~2e-7 on outputs of O(1): far inside the 1e-4 budget of
+// the fp32 mode).  expm1f / expf cost ~40 dependent instructions per value, which made the epilogue warps the bottleneck.
+__device__ __forceinline__ float act_fwd_fast(float v, int act) {
+  switch (act) {
+    case SHB_ACT_RELU: return v > 0.f ? v : 0.f;
+    case SHB_ACT_ELU: return v > 0.f ? v : __expf(v) - 1.f;
+    case SHB_ACT_LEAKY_RELU: return v > 0.f ? v : 0.02f * v;
+    case SHB_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-v));
+    case SHB_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
 // derivative expressed through the OUTPUT y = act(v)
 __device__ __forceinline__ float act_bwd_from_out(float y, int act) {
   switch (act) {

@@ -59,6 +59,28 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
     __nanosleep(ns);
   }
 }
+// Wait with a hardware suspend-time hint: the thread is parked (no polling instructions competing for the shared-memory
+// pipe with the producer / MMA threads) until the phase completes or `hint_ns` elapse.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (ok == 0);
+}
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, code under this predicate keeps warp-uniform values in the
+// uniform datapath, which is what the single-thread tcgen05 / bulk-copy instructions take their operands from.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit_u32(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -12,6 +12,8 @@
 //
 // Roles: warp 0 = TMA producer (entry lists -> bulk copies into a ring of stages), warp 1 = MMA issuer (one thread),
 // warps 2-5 = epilogue (TMEM -> registers -> HBM), double-buffered accumulator.
+#include <stdlib.h>
+
 #include "shb_common.cuh"
 #include "shb_internal.h"
 #include "shb_slab.cuh"
@@ -21,9 +23,9 @@ namespace shb {
 using namespace umma;
 using namespace slab;
 
-constexpr int SC_THREADS = 192;
+constexpr int SC_MAX_THREADS = 64 + 4 * 128;  // producer warp, MMA warp, up to four groups of four epilogue warps
 constexpr int SC_MAX_STAGES = 24;
-constexpr int SC_MAX_SPS = 4;  // slabs per ring stage (narrow slabs are batched so that a stage is >= 8 KB)
+constexpr int SC_MAX_SPS = 8;  // slabs per ring stage: a stage is up to 32 KB behind one barrier round trip
 
 struct SlabConvParams {
   const uint8_t* src;      // slab tensor, CS channels, P planes
@@ -41,19 +43,38 @@ struct SlabConvParams {
   int act, act_mul, zero_last;
   int P;
   int nstage, SPS;
+  int cpw, EG;             // accumulator columns per epilogue warp (8/16/32), epilogue groups (threads = 64 + 128*EG)
   int num_tiles;
   uint32_t tmem_cols;
 };
 
+// Debug timeline (build with SHB_NVCC_FLAGS=-DSHB_SLAB_TRACE): per CTA, cycles each role spends waiting / working.
+//   [0] producer wait-empty  [1] producer total   [2] MMA wait-full  [3] MMA wait-tmem  [4] MMA total
+//   [5] epilogue wait-accumulator (warp 2)  [6] epilogue total (warp 2)  [7] tiles
+#ifdef SHB_SLAB_TRACE
+__device__ long long g_slab_trace[kNumSMs * 8];
+#define SC_T0(var) const long long var = clock64()
+#define SC_ACC(idx, t0) trace_acc[idx] += clock64() - (t0)
+#else
+#define SC_T0(var) do { } while (0)
+#define SC_ACC(idx, t0) do { } while (0)
+#endif
+
 template <int P>
-__global__ void __launch_bounds__(SC_THREADS, 1) slab_conv_kernel(const SlabConvParams p) {
+__global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const SlabConvParams p) {
+#ifdef SHB_SLAB_TRACE
+  long long trace_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long trace_start = clock64();
+#endif
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[SC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[SC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t img_bar;
-  __shared__ uint32_t meta_s[SC_MAX_STAGES];
+  __shared__ uint32_t hdr_s[SC_MAX_STAGES];                       // per stage: first/last-of-tile flags, slab count
+  __shared__ __align__(16) uint32_t lb_s[SC_MAX_STAGES * SC_MAX_SPS];  // per slab: B-descriptor low word of its slot
+  __shared__ uint32_t tile_empty_s[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
 
@@ -68,11 +89,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) slab_conv_kernel(const SlabConv
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
 
   // ---------------------------------------------------------------- prologue
-  for (int i = tid; i < 128 / 16; i += SC_THREADS) *reinterpret_cast<uint4*>(dyn_smem + P * img_bytes1 + i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128 / 16; i += blockDim.x) *reinterpret_cast<uint4*>(dyn_smem + P * img_bytes1 + i * 16) = make_uint4(0, 0, 0, 0);
   if (p.CS == 8)
-    for (int i = tid; i < PLANE_STRIDE / 16; i += SC_THREADS)
+    for (int i = tid; i < PLANE_STRIDE / 16; i += blockDim.x)
       *reinterpret_cast<uint4*>(dyn_smem + img_region + (size_t)p.nstage * stage_b + i * 16) = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 256; i += SC_THREADS) bias_s[i] = (p.bias != nullptr && i < p.nbias) ? __ldg(p.bias + i) : 0.f;
+  for (int i = tid; i < 256; i += blockDim.x) bias_s[i] = (p.bias != nullptr && i < p.nbias) ? __ldg(p.bias + i) : 0.f;
   fence_proxy_async_smem();
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) {
@@ -81,7 +102,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) slab_conv_kernel(const SlabConv
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * p.EG);
     }
     mbar_init(&img_bar, 1);
     fence_mbar_init();
@@ -94,6 +115,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) slab_conv_kernel(const SlabConv
 
   if (warp == 0) {
     // ================================================================ producer: entry lists -> bulk copies
+    // One thread's mbarrier / bulk-copy instructions cost ~50 cycles each back to back (measured, tests/cuda/slab_probe.cu:
+    // 200 cycles per wait + expect_tx + copy), so a ring stage carries up to SPS slabs behind ONE wait and ONE expect_tx.
     if (lane == 0) {  // weight operand image(s): resident for the whole kernel
       mbar_expect_tx(smem_u32(&img_bar), P * img_bytes1);
       for (int pl = 0; pl < P; ++pl)
@@ -103,170 +126,234 @@ __global__ void __launch_bounds__(SC_THREADS, 1) slab_conv_kernel(const SlabConv
         }
     }
     uint32_t slot = 0, ph = 0;
+    const size_t row_stride = (size_t)p.NB * slab_b;
+    const uint32_t lo_b0 = (smem0 >> 4) | ((128u >> 4) << 16);          // B descriptor low word of slot 0 (LBO = 128)
+    const uint32_t b_step = (uint32_t)p.CS;                             // (CS/8 chunks) * 128 B >> 4 per slot
+    const int sps_shift = p.SPS == 8 ? 3 : (p.SPS == 4 ? 2 : (p.SPS == 2 ? 1 : 0));
+    const int kpos = lane & (p.SPS - 1), sidx_of_lane = lane >> sps_shift;
     int t = blockIdx.x;
     int u = t / p.NB, q = t - u * p.NB;
-    int e0 = 0, e1 = 0;
-    if (t < p.num_tiles) { e0 = __ldg(p.ptr + u); e1 = __ldg(p.ptr + u + 1); }
+    int e0 = 0, e1 = 0, mine = 0;
+    if (t < p.num_tiles) {
+      e0 = __ldg(p.ptr + u);
+      e1 = __ldg(p.ptr + u + 1);
+      if (e0 + lane < e1) mine = __ldg(p.ent + e0 + lane);
+    }
+    // two tiles ahead: entry range; one tile ahead: range + first 32 entries (registers)
+    int t1 = t + gridDim.x, u1 = t1 / p.NB, q1 = t1 - u1 * p.NB, f0 = 0, f1 = 0;
+    if (t1 < p.num_tiles) { f0 = __ldg(p.ptr + u1); f1 = __ldg(p.ptr + u1 + 1); }
     while (t < p.num_tiles) {
-      // next tile's range is fetched now, a whole tile ahead of its use
-      const int tn = t + gridDim.x;
-      const int un = tn / p.NB, qn = tn - un * p.NB;
-      int e0n = 0, e1n = 0;
-      if (tn < p.num_tiles) { e0n = __ldg(p.ptr + un); e1n = __ldg(p.ptr + un + 1); }
+      int mine_n = 0;
+      if (f0 + lane < f1) mine_n = __ldg(p.ent + f0 + lane);
+      const int t2 = t1 + gridDim.x, u2 = t2 / p.NB, q2 = t2 - u2 * p.NB;
+      int g0 = 0, g1 = 0;
+      if (t2 < p.num_tiles) { g0 = __ldg(p.ptr + u2); g1 = __ldg(p.ptr + u2 + 1); }
       const uint8_t* srcq = p.src + (size_t)q * slab_b;
-      const size_t row_stride = (size_t)p.NB * slab_b;
       if (e0 == e1) {  // no entries: the epilogue writes act(bias) / zeros; the MMA thread still hands the buffer over
         if (lane == 0) {
           mbar_wait(empty0 + slot * 8, ph ^ 1);
-          meta_s[slot] = 3u;
+          hdr_s[slot] = 3u;
           mbar_arrive(full0 + slot * 8);
         }
         if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
       }
+      // Lane L of the warp owns entry L of the current block of 32: it computes its own addresses and B-descriptor word and
+      // issues its own bulk copy; lane 0 does the barrier round trip of each stage (one wait + one expect_tx per <= SPS slabs).
       for (int base = e0; base < e1; base += 32) {
         const int cnt = e1 - base < 32 ? e1 - base : 32;
-        const int mine = lane < cnt ? __ldg(p.ent + base + lane) : 0;
-        for (int i = 0; i < cnt; i += p.SPS) {
-          const int ns = cnt - i < p.SPS ? cnt - i : p.SPS;
-          uint32_t m = (base + i == e0 ? 1u : 0u) | (base + i + ns == e1 ? 2u : 0u) | ((uint32_t)ns << 2);
-          int ev[SC_MAX_SPS];
-#pragma unroll
-          for (int k = 0; k < SC_MAX_SPS; ++k) {
-            ev[k] = __shfl_sync(0xFFFFFFFFu, mine, (i + k) & 31);
-            if (k < ns) m |= (uint32_t)(ev[k] & 31) << (5 + 5 * k);
-          }
+        if (base > e0) mine = lane < cnt ? __ldg(p.ent + base + lane) : 0;  // long lists: the rest is fetched in place
+        const uint8_t* my_src = srcq + (size_t)(mine >> 5) * row_stride;
+        const uint32_t my_lb = lo_b0 + (uint32_t)(mine & 31) * b_step;
+        const int nstg = (cnt + p.SPS - 1) >> sps_shift;
+        for (int sidx = 0; sidx < nstg; ++sidx) {
+          const int ns = cnt - (sidx << sps_shift) < p.SPS ? cnt - (sidx << sps_shift) : p.SPS;
+          const bool active = sidx_of_lane == sidx && lane < cnt;
           if (lane == 0) {
+            SC_T0(tw);
             mbar_wait(empty0 + slot * 8, ph ^ 1);
-            meta_s[slot] = m;
-            mbar_expect_tx(full0 + slot * 8, (uint32_t)ns * slab_b);
-            const uint32_t dst = ring0 + slot * stage_b;
-#pragma unroll
-            for (int k = 0; k < SC_MAX_SPS; ++k)
-              if (k < ns) bulk_load(dst + k * slab_b, srcq + (size_t)(ev[k] >> 5) * row_stride, slab_b, full0 + slot * 8);
+            SC_ACC(0, tw);
+            hdr_s[slot] = (base + (sidx << sps_shift) == e0 ? 1u : 0u) | (base + (sidx << sps_shift) + ns == e1 ? 2u : 0u) |
+                          ((uint32_t)ns << 2);
           }
+          __syncwarp();
+          if (active) lb_s[slot * SC_MAX_SPS + kpos] = my_lb;
+          __syncwarp();
+          if (lane == 0) mbar_expect_tx(full0 + slot * 8, (uint32_t)ns * slab_b);
+          __syncwarp();
+          if (active) bulk_load(ring0 + slot * stage_b + kpos * slab_b, my_src, slab_b, full0 + slot * 8);
           if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
         }
       }
-      t = tn; u = un; q = qn; e0 = e0n; e1 = e1n;
+      t = t1; u = u1; q = q1; e0 = f0; e1 = f1; mine = mine_n;
+      t1 = t2; u1 = u2; q1 = q2; f0 = g0; f1 = g1;
     }
+#ifdef SHB_SLAB_TRACE
+    if (lane == 0) {
+      g_slab_trace[blockIdx.x * 8 + 0] = trace_acc[0];
+      g_slab_trace[blockIdx.x * 8 + 1] = clock64() - trace_start;
+    }
+#endif
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
+    // tcgen05.commit only tracks the issuing thread's MMAs, so one thread issues them all; what it executes per entry is cut
+    // to the bone (every instruction of this dependent chain costs ~5 cycles): the B-descriptor word comes ready-made from the
+    // producer, the A-descriptor word advances by a constant.
+    if (elect_one()) {
       const uint32_t idesc = idesc_bf16_f32(CHUNK, p.NP, 0, 0);
       const uint64_t hi_b = ((uint64_t)(((uint32_t)p.Q * 128) >> 4) << 32) | ((uint64_t)1 << 46);       // SBO = Q*128
       const uint64_t hi_a = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);                         // SBO = 128
-      const uint32_t lo_b0 = (smem0 >> 4) | ((128u >> 4) << 16);                                         // LBO = 128
       const uint32_t nk = p.CS >= 16 ? (uint32_t)p.CS / 16 : 1u;   // MMAs (K = 16) per slab and plane
-      const uint32_t chunks_per_slot = (uint32_t)p.CS / 8;
+      const uint32_t slab16 = slab_b >> 4;
+      // A: K-major, SBO = 128 (next 8 samples), LBO = 2048 (next 8 channels).  8-channel sources pair the slab with a block of
+      // zeros through LBO = zero0 - slab: moving to the next slab adds slab16 to the address field and takes it off the LBO field
+      const uint32_t a_step = p.CS >= 16 ? slab16 : slab16 - (slab16 << 16);
+      const uint32_t plane_a = p.CS >= 16 ? ((uint32_t)p.CS * 256) >> 4 : (((uint32_t)p.CS * 256) >> 4) - ((((uint32_t)p.CS * 256) >> 4) << 16);
+      const uint32_t plane_b = img_bytes1 >> 4;
       mbar_wait(smem_u32(&img_bar), 0);
       uint32_t slot = 0, ph = 0;
       int tcount = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
-        mbar_wait_sleep(smem_u32(&tempty_bar[buf]), ((tcount >> 1) & 1) ^ 1, 32);
+        SC_T0(tw3);
+        mbar_wait_parked(smem_u32(&tempty_bar[buf]), ((tcount >> 1) & 1) ^ 1, 1000);
+        SC_ACC(3, tw3);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.NP);
         uint32_t acc = 0;
         for (;;) {
-          mbar_wait_sleep(full0 + slot * 8, ph, 20);
-          const uint32_t m = meta_s[slot];
+          SC_T0(tw2);
+          mbar_wait_parked(full0 + slot * 8, ph, 1000);
+          SC_ACC(2, tw2);
+          const uint32_t hdr = hdr_s[slot];
+          const uint4 w0 = *reinterpret_cast<const uint4*>(&lb_s[slot * SC_MAX_SPS]);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(&lb_s[slot * SC_MAX_SPS + 4]);
+          const uint32_t lbs[SC_MAX_SPS] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           tc_fence_after();
-          const uint32_t ns = (m >> 2) & 7u;
-          const uint32_t a_stage = ring0 + slot * stage_b;
-          for (uint32_t k = 0; k < ns; ++k) {
-            const uint32_t s = (m >> (5 + 5 * k)) & 31u;
-            const uint32_t a_slab = a_stage + k * slab_b;
-            // A: K-major, SBO = 128 (next 8 samples), LBO = 2048 (next 8 channels); 8-channel sources pair the slab with zeros
-            const uint32_t lbo_a = p.CS >= 16 ? (uint32_t)PLANE_STRIDE : zero0 - a_slab;
-            const uint32_t lo_a = ((a_slab & 0x3FFFFu) >> 4) | ((lbo_a >> 4) << 16);
-            // second plane (fp32 mode): its own distance to the zero block when the source has 8 channels
-            const uint32_t a_slab1 = a_slab + (uint32_t)p.CS * 256;
-            const uint32_t lbo_a1 = p.CS >= 16 ? (uint32_t)PLANE_STRIDE : zero0 - a_slab1;
-            const uint32_t lo_a1 = ((a_slab1 & 0x3FFFFu) >> 4) | ((lbo_a1 >> 4) << 16);
-            const uint32_t lo_b = lo_b0 + s * chunks_per_slot * 8;  // 128 B per core matrix >> 4
-            for (uint32_t kk = 0; kk < nk; ++kk) {
-              const uint32_t la = lo_a + kk * (2 * PLANE_STRIDE >> 4), lb = lo_b + kk * 16;
-              mma_bf16(tmem_d, hi_a | la, hi_b | lb, idesc, acc);
-              acc = 1;
-              if (P == 2) {  // x ~ xh + xl, w ~ wh + wl:  xh.wh + xl.wh + xh.wl  (xl.wl ~ 2^-18 relative: dropped)
-                const uint32_t plane_b = img_bytes1 >> 4;
-                mma_bf16(tmem_d, hi_a | (lo_a1 + kk * (2 * PLANE_STRIDE >> 4)), hi_b | lb, idesc, 1);
-                mma_bf16(tmem_d, hi_a | la, hi_b | (lb + plane_b), idesc, 1);
+          const uint32_t ns = (hdr >> 2) & 15u;
+          const uint32_t a_slab = ring0 + slot * stage_b;
+          const uint32_t lbo_a = p.CS >= 16 ? (uint32_t)PLANE_STRIDE : zero0 - a_slab;
+          uint32_t la0 = ((a_slab & 0x3FFFFu) >> 4) | ((lbo_a >> 4) << 16);
+#pragma unroll
+          for (uint32_t k = 0; k < (uint32_t)SC_MAX_SPS; ++k) {
+            if (k < ns) {
+              uint32_t la = la0, lb = lbs[k];
+              for (uint32_t kk = 0; kk < nk; ++kk) {
+                mma_bf16(tmem_d, hi_a | la, hi_b | lb, idesc, acc);
+                acc = 1;
+                if (P == 2) {  // x ~ xh + xl, w ~ wh + wl: all four partial products (the tensor pipe is far from the bound)
+                  mma_bf16(tmem_d, hi_a | (la + plane_a), hi_b | lb, idesc, 1);
+                  mma_bf16(tmem_d, hi_a | la, hi_b | (lb + plane_b), idesc, 1);
+                  mma_bf16(tmem_d, hi_a | (la + plane_a), hi_b | (lb + plane_b), idesc, 1);
+                }
+                la += 2 * PLANE_STRIDE >> 4;
+                lb += 16;
               }
+              la0 += a_step;
             }
           }
           mma_commit_u32(empty0 + slot * 8);  // stage reusable once these MMAs have read it
           if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
-          if (m & 2u) break;
+          if (hdr & 2u) {
+            tile_empty_s[buf] = ns == 0 ? 1u : 0u;
+            break;
+          }
         }
+        __threadfence_block();
         mma_commit_u32(smem_u32(&tfull_bar[buf]));  // accumulator complete
       }
+#ifdef SHB_SLAB_TRACE
+      g_slab_trace[blockIdx.x * 8 + 2] = trace_acc[2];
+      g_slab_trace[blockIdx.x * 8 + 3] = trace_acc[3];
+      g_slab_trace[blockIdx.x * 8 + 4] = clock64() - trace_start;
+#endif
     }
     __syncwarp();
   } else {
     // ================================================================ epilogue warps: TMEM -> bias / act / act' / mask -> HBM
+    // EG groups of 4 warps; a group owns `cpw` consecutive accumulator columns (a warp can only read its own TMEM lane
+    // quarter, warp_id % 4).  The instruction stream of a warp is one dependent chain (~5 cycles per instruction) and a global
+    // load issued next to a saturated TMA ring takes ~2000 cycles, so: many narrow warps, and the act' operands are requested
+    // before the wait on the accumulator.
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;         // column group
     const int b = quarter * 32 + lane;       // sample within the chunk
+    const int cpw = p.cpw, ngr = cpw >> 3;   // columns per warp (8, 16 or 32), 8-column vectors per warp
+    const int col0 = grp * cpw;
     const size_t dslab = slab_bytes(p.Cd, P);
     const uint32_t plane_d = (uint32_t)(p.Cd / 8) * PLANE_STRIDE;
     int tcount = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
       const int u = t / p.NB, q = t - u * p.NB;
-      const bool empty_tile = __ldg(p.ptr + u) == __ldg(p.ptr + u + 1);
       const bool zero = p.zero_last && u == p.rows_dst - 1;
-      const size_t off = ((size_t)u * p.NB + q) * dslab + (size_t)(p.n0 / 8) * PLANE_STRIDE + (size_t)b * 16;
+      const size_t off = ((size_t)u * p.NB + q) * dslab + (size_t)((p.n0 + col0) / 8) * PLANE_STRIDE + (size_t)b * 16;
       uint8_t* drow = p.dst + off;
-      const uint8_t* yrow = p.ymul != nullptr ? p.ymul + off : nullptr;
-      mbar_wait_sleep(smem_u32(&tfull_bar[buf]), (tcount >> 1) & 1, 64);
+      uint4 yv[4][P];
+      if (p.ymul != nullptr) {
+        const uint8_t* yrow = p.ymul + off;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g < ngr) {
+            yv[g][0] = __ldg(reinterpret_cast<const uint4*>(yrow + (size_t)g * PLANE_STRIDE));
+            if (P == 2) yv[g][P - 1] = __ldg(reinterpret_cast<const uint4*>(yrow + (size_t)g * PLANE_STRIDE + plane_d));
+          }
+      }
+      SC_T0(tw5);
+      mbar_wait_parked(smem_u32(&tfull_bar[buf]), (tcount >> 1) & 1, 2000);
+      SC_ACC(5, tw5);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NP) + ((uint32_t)(quarter * 32) << 16);
-      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (c0 + 16 >= p.ncols) {  // accumulator fully read: hand the buffer back before the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      const bool empty_tile = tile_empty_s[buf] != 0;
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NP + col0) + ((uint32_t)(quarter * 32) << 16);
+      uint32_t r[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < ngr) tmem_ld8(taddr + g * 8, r[g]);
+      tmem_ld_wait();
+      tc_fence_before();   // accumulator columns of this warp are in registers: hand the buffer back before the math
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g >= ngr) break;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = act_fwd_fast((empty_tile ? 0.f : __uint_as_float(r[g][i])) + bias_s[col0 + 8 * g + i], p.act);
+        if (p.ymul != nullptr) {
+          float y[8];
+          unpack8(yv[g][0], y);
+          if (P == 2) {
+            float yl[8];
+            unpack8(yv[g][P - 1], yl);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] += yl[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_out(y[i], p.act_mul);
         }
+        if (zero) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (c0 + 8 * h >= p.ncols) break;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            v[i] = act_fwd((empty_tile ? 0.f : __uint_as_float(r[8 * h + i])) + bias_s[c0 + 8 * h + i], p.act);
-          const size_t coff = (size_t)(c0 / 8 + h) * PLANE_STRIDE;
-          if (yrow != nullptr) {
-            float y[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(yrow + coff)), y);
-            if (P == 2) {
-              float yl[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(yrow + coff + plane_d)), yl);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] += yl[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_out(y[i], p.act_mul);
-          }
-          if (zero) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-          }
-          if (P == 1) {
-            *reinterpret_cast<uint4*>(drow + coff) = pack8(v);
-          } else {
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(drow + coff) = hi;
-            *reinterpret_cast<uint4*>(drow + coff + plane_d) = lo;
-          }
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        if (P == 1) {
+          *reinterpret_cast<uint4*>(drow + (size_t)g * PLANE_STRIDE) = pack8(v);
+        } else {
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(drow + (size_t)g * PLANE_STRIDE) = hi;
+          *reinterpret_cast<uint4*>(drow + (size_t)g * PLANE_STRIDE + plane_d) = lo;
         }
       }
     }
   }
 
+#ifdef SHB_SLAB_TRACE
+  if (tid == 64) {
+    g_slab_trace[blockIdx.x * 8 + 5] = trace_acc[5];
+    g_slab_trace[blockIdx.x * 8 + 6] = clock64() - trace_start;
+    g_slab_trace[blockIdx.x * 8 + 7] = (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  }
+#endif
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
@@ -330,7 +417,7 @@ static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
   const int Q = S * CS / 8;
   const size_t slab_b = (size_t)P * CS * 256;
   int SPS = 1;
-  while (SPS < SC_MAX_SPS && slab_b * SPS < 8192) SPS *= 2;
+  while (SPS < SC_MAX_SPS && slab_b * SPS * 2 <= 32768) SPS *= 2;
   const size_t stage_b = slab_b * SPS, zero_b = CS == 8 ? PLANE_STRIDE : 0;
   for (int NP = NPt > 256 ? 256 : NPt; NP >= 16; NP -= 16) {
     if (NPt % NP != 0 && NP != NPt) continue;  // equal passes
@@ -354,8 +441,9 @@ static int slab_conv_launch(const SlabConvParams& p, size_t smem, cudaStream_t s
     attr_set[p.P] = true;
   }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  if (p.P == 1) slab_conv_kernel<1><<<grid, SC_THREADS, smem, st>>>(p);
-  else slab_conv_kernel<2><<<grid, SC_THREADS, smem, st>>>(p);
+  const int threads = 64 + 128 * p.EG;
+  if (p.P == 1) slab_conv_kernel<1><<<grid, threads, smem, st>>>(p);
+  else slab_conv_kernel<2><<<grid, threads, smem, st>>>(p);
   SHB_LAUNCH_CHECK();
   return 0;
 }
@@ -363,6 +451,12 @@ static int slab_conv_launch(const SlabConvParams& p, size_t smem, cudaStream_t s
 }  // namespace shb
 
 using namespace shb;
+
+#ifdef SHB_SLAB_TRACE
+extern "C" int shb_slab_trace_read(long long* host_out) {  // debug builds only: not part of the ABI
+  return (int)cudaMemcpyFromSymbol(host_out, g_slab_trace, sizeof(long long) * kNumSMs * 8);
+}
+#endif
 
 extern "C" {
 
@@ -418,6 +512,12 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
     p.NP = plan.NP; p.n0 = n0;
     p.ncols = Cd - n0 < plan.NP ? Cd - n0 : plan.NP;
     p.w_img = (const uint8_t*)w_img + (size_t)(n0 / 8) * p.Q * 128;
+    p.cpw = p.ncols >= 128 ? 32 : (p.ncols >= 64 ? 16 : 8);
+    p.EG = p.ncols / p.cpw;
+    {
+      static const int eg_cap = [] { const char* e = getenv("SHB_SLAB_EG"); return e ? atoi(e) : 4; }();  // tuning knob
+      while (p.EG > eg_cap && p.cpw < 32) { p.cpw *= 2; p.EG /= 2; }
+    }
     p.bias = bias ? bias + n0 : nullptr;
     p.nbias = Cd_real - n0 < p.ncols ? (Cd_real - n0 > 0 ? Cd_real - n0 : 0) : p.ncols;  // bias holds Cd_real entries
     uint32_t cols = 32;

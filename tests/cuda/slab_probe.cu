@@ -209,9 +209,10 @@ __global__ void __launch_bounds__(64) stream_kernel(const __grid_constant__ CUte
     for (int t = t0; t < t1; t += tstep) {
       const int chunk = rr ? (t % nchunk) : t / R, j = rr ? t / nchunk : t - chunk * R;
       for (int s = 0; s < S; ++s) {
-        int r = j + offs[(j * S + s) & 4095];
+        int r = j + ((mode & 4) ? ((j * 7 + s * 13) % 161) - 80 : offs[(j * S + s) & 4095]);
         r = r < 0 ? 0 : (r >= R ? R - 1 : r);
-        mbar_wait(smem_u32(&empty[slot]), ph ^ 1);
+        if (mode & 8) mbar_wait(smem_u32(&full[slot]), ph ^ 1);   // self-consume: the previous load into this slot has landed
+        else mbar_wait(smem_u32(&empty[slot]), ph ^ 1);
         mbar_expect_tx(smem_u32(&full[slot]), stage_bytes);
         if (mode & 1)
           bulk_load(smem_u32(smem) + slot * stage_bytes, base_ptr + ((size_t)r * nchunk + chunk) * stage_bytes, stage_bytes, smem_u32(&full[slot]));
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(64) stream_kernel(const __grid_constant__ CUte
         if (++slot == (uint32_t)nst) { slot = 0; ph ^= 1; }
       }
     }
-  } else if (tid == 32) {
+  } else if (tid == 32 && !(mode & 8)) {
     uint32_t slot = 0, ph = 0;
     for (int t = t0; t < t1; t += tstep)
       for (int s = 0; s < S; ++s) {
@@ -261,6 +262,109 @@ __global__ void __launch_bounds__(64) timeline_kernel(const uint8_t* __restrict_
       my[32 + i] = clock64() - c0;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------- part 4: steady-state timeline
+// One thread issues n bulk copies through a ring of nst slots, waiting for the previous load of a slot before reusing it.
+// Stamps: [i][0] before the wait, [i][1] after the wait, [i][2] after the issue.
+__global__ void __launch_bounds__(64) ring_timeline_kernel(const uint8_t* __restrict__ base_ptr, uint32_t bytes, int n, int nst,
+                                                           size_t stride, long long* stamps /* [grid][n][3] */) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[32];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < nst; ++i) mbar_init(smem_u32(&full[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  long long* my = stamps + (size_t)blockIdx.x * n * 3;
+  if (tid == 0) {
+    const long long c0 = clock64();
+    uint32_t slot = 0, ph = 0;
+    for (int i = 0; i < n; ++i) {
+      const long long a = clock64();
+      mbar_wait(smem_u32(&full[slot]), ph ^ 1);
+      const long long b = clock64();
+      mbar_expect_tx(smem_u32(&full[slot]), bytes);
+      bulk_load(smem_u32(smem) + slot * bytes, base_ptr + ((size_t)blockIdx.x * 97 + (size_t)i * 5) % 30000 * stride, bytes, smem_u32(&full[slot]));
+      const long long c = clock64();
+      my[i * 3 + 0] = a - c0; my[i * 3 + 1] = b - c0; my[i * 3 + 2] = c - c0;
+      if (++slot == (uint32_t)nst) { slot = 0; ph ^= 1; }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------- part 5: MMA issue/execute rate
+// One thread issues `n` tcgen05.mma (M=128, K=16) with the given descriptors (operand contents irrelevant), alternating
+// between `nacc` accumulators, then commits and waits.  Reports cycles per MMA.
+__global__ void __launch_bounds__(128) mma_rate_kernel(uint64_t da, uint64_t db, uint32_t idesc, int n, int nacc, int ncols,
+                                                       uint32_t a_step, int a_wrap, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 200 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint64_t add = (uint64_t)((smem_u32(smem) & 0x3FFFFu) >> 4);
+    const long long c0 = clock64();
+    for (int i = 0; i < n; ++i)
+      mma_bf16(tmem + (uint32_t)((i % nacc) * ncols), da + add + (uint64_t)((i % a_wrap) * (a_step >> 4)), db + add, idesc, i >= nacc ? 1u : 0u);
+    const long long c1 = clock64();
+    mma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long c2 = clock64();
+    out[0] = c1 - c0; out[1] = c2 - c0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+
+// part 5b: same measurement with a fully unrolled issue sequence (no per-MMA arithmetic at all)
+__global__ void __launch_bounds__(128) mma_rate_unrolled_kernel(uint64_t da, uint64_t db, uint32_t idesc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 200 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint64_t add = (uint64_t)((smem_u32(smem) & 0x3FFFFu) >> 4);
+    const uint64_t a = da + add, b = db + add;
+    const long long c0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 64; ++i) mma_bf16(tmem, a, b, idesc, 1u);
+    const long long c1 = clock64();
+    mma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long c2 = clock64();
+    out[0] = c1 - c0; out[1] = c2 - c0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 int main() {
@@ -408,8 +512,8 @@ int main() {
       CK(cudaMemset(dX, 0, n * 2));
       const CUtensorMap map = make_map(dX, Rr, Bb, C, cbox);
       const uint32_t box_bytes = 128u * cbox * 2, stage = box_bytes * nbox;
-      for (int mode = 0; mode < 4; ++mode)
-      for (int nst_bytes : {64 * 1024, 128 * 1024, 200 * 1024}) {
+      for (int mode : {3, 7, 15})
+      for (int nst_bytes : {32 * 1024, 128 * 1024, 200 * 1024}) {
         const int nst = nst_bytes / (int)stage > 32 ? 32 : nst_bytes / (int)stage;
         if (nst < 2) continue;
         if (C == 8 && !(mode & 1)) continue;
@@ -425,7 +529,7 @@ int main() {
         CK(cudaEventElapsedTime(&ms, e0, e1));
         const double bytes = (double)Rr * 2 * S * stage;
         printf("stream[%s,%s]: rows of %3d B, %2d stages of %5u B in flight per SM: %.3f ms, %.0f GB/s L2->SM fill (%.1f B/clk/SM at 1.965 GHz), tensor %.0f MB\n",
-               (mode & 1) ? "bulk" : "tmap", (mode & 2) ? "round-robin" : "ranges", C * 2, nst, stage, ms, bytes / ms / 1e6, bytes / ms / 1e6 / 148 / 1.965, n * 2 / 1e6);
+               (mode & 1) ? "bulk" : "tmap", (mode & 8) ? "rr,arith,self-consume" : (mode & 4) ? "rr,arith" : "rr,table", C * 2, nst, stage, ms, bytes / ms / 1e6, bytes / ms / 1e6 / 148 / 1.965, n * 2 / 1e6);
       }
       CK(cudaFree(dX));
     }
@@ -455,6 +559,82 @@ int main() {
           printf(" | done");
           for (int i = 0; i < n; i += 1) printf(" %lld", st[32 + i]);
           printf("\n");
+        }
+  }
+
+  // ---------------------------------------------------------------- steady-state ring timeline
+  {
+    uint8_t* d;
+    const size_t total = (size_t)512 << 20;
+    CK(cudaMalloc(&d, total));
+    CK(cudaMemset(d, 0, total));
+    const int n = 120;
+    long long* d_st;
+    CK(cudaMalloc(&d_st, 148 * n * 3 * 8));
+    CK(cudaFuncSetAttribute(ring_timeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    for (int grid : {1, 148})
+      for (uint32_t bytes : {2048u, 8192u})
+        for (int nst : {4, 16}) {
+          for (int rep = 0; rep < 2; ++rep) {
+            ring_timeline_kernel<<<grid, 64, nst * bytes>>>(d, bytes, n, nst, 16384, d_st);
+            CK(cudaDeviceSynchronize());
+          }
+          std::vector<long long> st(n * 3);
+          CK(cudaMemcpy(st.data(), d_st, n * 3 * 8, cudaMemcpyDeviceToHost));
+          printf("ring grid=%d bytes=%u nst=%d: (before-wait, after-wait, after-issue) ops 0..3:", grid, bytes, nst);
+          for (int i = 0; i < 4; ++i) printf(" (%lld %lld %lld)", st[i * 3], st[i * 3 + 1], st[i * 3 + 2]);
+          printf(" ... ops 100..107:");
+          for (int i = 100; i < 108; ++i) printf(" (%lld %lld %lld)", st[i * 3], st[i * 3 + 1], st[i * 3 + 2]);
+          printf("  => %.0f cycles/op over ops 40..119\n", (double)(st[119 * 3 + 2] - st[40 * 3 + 2]) / 79.0);
+        }
+  }
+
+  // ---------------------------------------------------------------- MMA rate per operand layout
+  {
+    long long* d_out;
+    CK(cudaMalloc(&d_out, 16));
+    CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    struct L { const char* name; uint32_t layout, lbo, sbo, step; };
+    // K-major A operand, 128 rows: un-swizzled slab planes (LBO 2048, SBO 128); SW32/64/128 row-major tiles
+    const L la[] = {{"A none(LBO2048,SBO128)", 0, 2048, 128, 4096}, {"A SW32 ", 6, 0, 256, 4096}, {"A SW64 ", 4, 0, 512, 32},
+                    {"A SW128", 2, 0, 1024, 32}};
+    for (const L& a : la)
+      for (int bsw = 0; bsw < 2; ++bsw)
+        for (int N : {16, 32, 64, 128, 256})
+          for (int nacc : {1, 2}) {
+            if (nacc * N > 512) continue;
+            const int n = 256;
+            const uint64_t da = make_desc(0, a.lbo, a.sbo, a.layout);
+            // B: N rows x K=16: un-swizzled image (LBO 128, SBO 256) or SW128 rows of 128 B
+            const uint64_t db = bsw ? make_desc(IMG, 0, 1024, 2) : make_desc(IMG, 128, 256, 0);
+            long long h[2];
+            for (int rep = 0; rep < 2; ++rep) {
+              mma_rate_kernel<<<1, 128, 200 * 1024>>>(da, db, make_idesc(128, N, 0, 0), n, nacc, N, a.step, a.step == 32 ? 2 : 8, d_out);
+              CK(cudaDeviceSynchronize());
+            }
+            CK(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+            printf("mma rate: %s, B %s, N=%3d, %d accumulator(s): issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %.1f)\n", a.name,
+                   bsw ? "SW128" : "none ", N, nacc, (double)h[0] / n, (double)h[1] / n, 128.0 * N * 16 * 2 / 8192.0);
+          }
+  }
+
+  {
+    long long* d_out;
+    CK(cudaMalloc(&d_out, 16));
+    CK(cudaFuncSetAttribute(mma_rate_unrolled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int M : {128, 64})
+      for (int sw = 0; sw < 2; ++sw)
+        for (int N : {16, 32, 64, 128, 256}) {
+          const uint64_t da = sw ? make_desc(0, 0, 1024, 2) : make_desc(0, 2048, 128, 0);
+          const uint64_t db = sw ? make_desc(IMG, 0, 1024, 2) : make_desc(IMG, 128, 256, 0);
+          long long h[2];
+          for (int rep = 0; rep < 2; ++rep) {
+            mma_rate_unrolled_kernel<<<1, 128, 200 * 1024>>>(da, db, make_idesc(M, N, 0, 0), d_out);
+            CK(cudaDeviceSynchronize());
+          }
+          CK(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+          printf("mma unrolled: M=%d %s N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %.1f)\n", M, sw ? "SW128" : "none ", N,
+                 (double)h[0] / 64, (double)h[1] / 64, (double)M * N * 16 * 2 / 8192.0);
         }
   }
   printf("descriptor cases failed (K-major): %d\n", failures);

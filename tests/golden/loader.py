@@ -1,7 +1,7 @@
 """Loader for the hierarchy fixtures (tests/golden/hier_*.npz): template, D/U, spirals.
 
 The fixtures are produced by the reference's own mesh_sampling.py / utils_spiral.py (tests/golden/make_golden.py);
-this module only unpacks them into the constructor arguments of the models -- either exactly as main.py:183-205
+this module (test infrastructure, like the fixtures it reads) only unpacks them into the constructor arguments of the models -- either exactly as main.py:183-205
 builds them (dense padded D/U, (1, V+1, S) int64 spirals) or in the sparse form the product accepts directly.
 """
 import os
@@ -10,7 +10,7 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
 
 
 class Hierarchy:

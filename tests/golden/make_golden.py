@@ -24,7 +24,7 @@ Fixtures
                                   the batch as the training loop does.
   golden_skeleton.npz             reference kps2skl / skl2kps (utils_SH.py:26-80), all modes.
   golden_ae_6890.npz              full-size SpiralAutoencoder (default filters, nz=256), B=2, deterministic
-                                  weights (semantichuman_b200.synthetic.fill_deterministic_), outputs and
+                                  weights (tests.golden.synthetic.fill_deterministic_), outputs and
                                   gradient samples.
 """
 import argparse
@@ -48,7 +48,7 @@ import models as ref_models  # noqa: E402  (reference)
 import utils_spiral  # noqa: E402  (reference)
 from _ref_stubs import Mesh  # noqa: E402
 
-from semantichuman_b200.synthetic import (fill_deterministic_, make_open_template, make_template,  # noqa: E402
+from tests.golden.synthetic import (fill_deterministic_, make_open_template, make_template,  # noqa: E402
                                           synthetic_meshes)
 
 DEFAULT_STEPS = [2, 2, 1, 1, 1]

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import torch
 
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import spiral_oracle as so
 from semantichuman_b200 import _capi, indexing
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -164,7 +164,7 @@ def test_locality_order_and_permuted_pool_matrices():
     """Host logic of the internal vertex re-ordering: the order is a permutation that shrinks the per-tile gather
     footprint, and PoolMatrix.permuted / from_permutation are exact relabellings (checked against dense algebra)."""
     import scipy.sparse as sp
-    from semantichuman_b200.assets import Hierarchy
+    from tests.golden.loader import Hierarchy
     from semantichuman_b200.indexing import PoolMatrix, locality_order, normalise_spiral
 
     h = Hierarchy("2222")

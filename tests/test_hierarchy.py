@@ -10,7 +10,7 @@ import scipy.sparse as sp
 
 from semantichuman_b200 import hierarchy as hy
 from semantichuman_b200 import spirals as spr
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 
 
 @pytest.mark.parametrize("tag", ["small", "open", "2222", "4444"])

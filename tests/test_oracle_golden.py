@@ -10,7 +10,7 @@ import torch
 from tests.helpers import (DEFAULT_FDEC, DEFAULT_FENC, filters_from_golden, golden, grads_from_golden, params_from_golden,
                      ref_args, relerr)
 from oracle import spiral_oracle as so
-from semantichuman_b200.synthetic import fill_deterministic_, synthetic_meshes
+from tests.golden.synthetic import fill_deterministic_, synthetic_meshes
 
 TIGHT = 2e-6  # same ATen ops in a different call structure: fp32 rounding only
 

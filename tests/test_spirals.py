@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from semantichuman_b200 import spirals as sp
-from semantichuman_b200.assets import Hierarchy
+from tests.golden.loader import Hierarchy
 
 CONFIGS = {"A": ([2, 2, 1, 1, 1], [2, 2, 1, 1, 1]), "B": ([1] * 5, [1] * 5)}
 
