@@ -49,11 +49,11 @@ for spec in layers.split(";"):
         import ctypes
         from semantichuman_b200._capi import lib as _lib
         raw = ctypes.CDLL(_lib._name)
-        buf = (ctypes.c_longlong * (148 * 8))()
+        buf = (ctypes.c_longlong * (148 * 16))()
         torch.cuda.synchronize()
         raw.shb_slab_trace_read(buf)
-        a = np.array(buf[:]).reshape(148, 8).astype(np.float64)
-        names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-tmem", "mma total", "epi wait-acc", "epi total", "tiles"]
+        a = np.array(buf[:]).reshape(148, 16).astype(np.float64)
+        names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-tmem", "mma total", "epi wait-acc", "epi total", "tiles", "prod lb+sync", "prod expect", "prod bulk", "mma issue", "mma commit", "epi tmem-ld", "epi fence+arrive", "epi math+store"]
         print("  trace of the LAST slab_conv launch, mean over CTAs, cycles per tile:")
         for i, n in enumerate(names):
-            print(f"    {n:18s} {a[:, i].mean() / max(a[:, 7].mean(), 1):10.0f}" if i < 7 else f"    {n:18s} {a[:, i].mean():10.1f}")
+            print(f"    {n:18s} {a[:, i].mean() / max(a[:, 7].mean(), 1):10.0f}" if i != 7 else f"    {n:18s} {a[:, i].mean():10.1f}")

@@ -23,8 +23,9 @@ namespace shb {
 using namespace umma;
 using namespace slab;
 
-constexpr int SC_MAX_THREADS = 64 + 4 * 128;  // producer warp, MMA warp, up to four groups of four epilogue warps
-constexpr int SC_MAX_STAGES = 24;
+constexpr int SC_LEAD_WARPS = 3;                // two producer warps (even / odd ring stages) and the MMA warp
+constexpr int SC_MAX_THREADS = SC_LEAD_WARPS * 32 + 4 * 128;  // + up to four groups of four epilogue warps
+constexpr int SC_MAX_STAGES = 12;
 constexpr int SC_MAX_SPS = 8;  // slabs per ring stage: a stage is up to 32 KB behind one barrier round trip
 
 struct SlabConvParams {
@@ -43,7 +44,8 @@ struct SlabConvParams {
   int act, act_mul, zero_last;
   int P;
   int nstage, SPS;
-  int cpw, EG;             // accumulator columns per epilogue warp (8/16/32), epilogue groups (threads = 64 + 128*EG)
+  int dbg;                 // trace builds only: 1 = skip epilogue stores, 2 = skip activation math
+  int cpw, EG;             // accumulator columns per epilogue warp (8/16/32), epilogue groups (threads = 96 + 128*EG)
   int num_tiles;
   uint32_t tmem_cols;
 };
@@ -52,7 +54,7 @@ struct SlabConvParams {
 //   [0] producer wait-empty  [1] producer total   [2] MMA wait-full  [3] MMA wait-tmem  [4] MMA total
 //   [5] epilogue wait-accumulator (warp 2)  [6] epilogue total (warp 2)  [7] tiles
 #ifdef SHB_SLAB_TRACE
-__device__ long long g_slab_trace[kNumSMs * 8];
+__device__ long long g_slab_trace[kNumSMs * 16];
 #define SC_T0(var) const long long var = clock64()
 #define SC_ACC(idx, t0) trace_acc[idx] += clock64() - (t0)
 #else
@@ -60,10 +62,10 @@ __device__ long long g_slab_trace[kNumSMs * 8];
 #define SC_ACC(idx, t0) do { } while (0)
 #endif
 
-template <int P>
+template <int P, int NK>
 __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const SlabConvParams p) {
 #ifdef SHB_SLAB_TRACE
-  long long trace_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long trace_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long trace_start = clock64();
 #endif
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t img_bar;
+  __shared__ __align__(16) unsigned long long src_s[SC_MAX_STAGES * SC_MAX_SPS];  // per slab: global source address
   __shared__ uint32_t hdr_s[SC_MAX_STAGES];                       // per stage: first/last-of-tile flags, slab count
   __shared__ __align__(16) uint32_t lb_s[SC_MAX_STAGES * SC_MAX_SPS];  // per slab: B-descriptor low word of its slot
   __shared__ uint32_t tile_empty_s[2];
@@ -80,7 +83,8 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t img_bytes1 = (uint32_t)p.NP * p.Q * 16;            // one plane
-  const uint32_t img_region = ((P * img_bytes1 + 128 + 1023) / 1024) * 1024;  // + 128 B zero pad, ring 1024-aligned
+  // 8-channel sources read one core matrix past their slot's (see the MMA issuer): 128 B of zeros behind the image
+  const uint32_t img_region = ((P * img_bytes1 + (p.CS == 8 ? 128u : 0u) + 1023) / 1024) * 1024;
   const uint32_t slab_b = (uint32_t)P * p.CS * 256;
   const uint32_t stage_b = slab_b * p.SPS;
   const uint32_t smem0 = smem_u32(dyn_smem);
@@ -89,10 +93,11 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
 
   // ---------------------------------------------------------------- prologue
-  for (int i = tid; i < 128 / 16; i += blockDim.x) *reinterpret_cast<uint4*>(dyn_smem + P * img_bytes1 + i * 16) = make_uint4(0, 0, 0, 0);
-  if (p.CS == 8)
+  if (p.CS == 8) {
+    for (int i = tid; i < 128 / 16; i += blockDim.x) *reinterpret_cast<uint4*>(dyn_smem + P * img_bytes1 + i * 16) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < PLANE_STRIDE / 16; i += blockDim.x)
       *reinterpret_cast<uint4*>(dyn_smem + img_region + (size_t)p.nstage * stage_b + i * 16) = make_uint4(0, 0, 0, 0);
+  }
   for (int i = tid; i < 256; i += blockDim.x) bias_s[i] = (p.bias != nullptr && i < p.nbias) ? __ldg(p.bias + i) : 0.f;
   fence_proxy_async_smem();
   if (tid == 0) {
@@ -107,17 +112,21 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
     mbar_init(&img_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  if (warp == 2) tmem_alloc(&tmem_base_s, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
-    // ================================================================ producer: entry lists -> bulk copies
+  if (warp < 2) {
+    // ================================================================ producers: entry lists -> bulk copies
+    // Two warps run the same walk over tiles and stages; warp w does the serial part (barrier round trip, bulk-copy issue) of
+    // the stages whose running number is w mod 2 -- that part is a dependent instruction chain of ~1000 cycles per stage-triple.
+    const uint32_t pw = (uint32_t)warp;
+    uint32_t stage_no = 0;
     // One thread's mbarrier / bulk-copy instructions cost ~50 cycles each back to back (measured, tests/cuda/slab_probe.cu:
     // 200 cycles per wait + expect_tx + copy), so a ring stage carries up to SPS slabs behind ONE wait and ONE expect_tx.
-    if (lane == 0) {  // weight operand image(s): resident for the whole kernel
+    if (warp == 0 && lane == 0) {  // weight operand image(s): resident for the whole kernel
       mbar_expect_tx(smem_u32(&img_bar), P * img_bytes1);
       for (int pl = 0; pl < P; ++pl)
         for (uint32_t off = 0; off < img_bytes1; off += 32768) {
@@ -131,6 +140,8 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
     const uint32_t b_step = (uint32_t)p.CS;                             // (CS/8 chunks) * 128 B >> 4 per slot
     const int sps_shift = p.SPS == 8 ? 3 : (p.SPS == 4 ? 2 : (p.SPS == 2 ? 1 : 0));
     const int kpos = lane & (p.SPS - 1), sidx_of_lane = lane >> sps_shift;
+    // tile -> (row u, chunk q) without divisions: a tile step adds gridDim.x = gdiv * NB + gmod
+    const int gdiv = (int)gridDim.x / p.NB, gmod = (int)gridDim.x - gdiv * p.NB;
     int t = blockIdx.x;
     int u = t / p.NB, q = t - u * p.NB;
     int e0 = 0, e1 = 0, mine = 0;
@@ -140,47 +151,68 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
       if (e0 + lane < e1) mine = __ldg(p.ent + e0 + lane);
     }
     // two tiles ahead: entry range; one tile ahead: range + first 32 entries (registers)
-    int t1 = t + gridDim.x, u1 = t1 / p.NB, q1 = t1 - u1 * p.NB, f0 = 0, f1 = 0;
+    int t1 = t + gridDim.x, u1 = u + gdiv, q1 = q + gmod, f0 = 0, f1 = 0;
+    if (q1 >= p.NB) { q1 -= p.NB; ++u1; }
     if (t1 < p.num_tiles) { f0 = __ldg(p.ptr + u1); f1 = __ldg(p.ptr + u1 + 1); }
     while (t < p.num_tiles) {
       int mine_n = 0;
       if (f0 + lane < f1) mine_n = __ldg(p.ent + f0 + lane);
-      const int t2 = t1 + gridDim.x, u2 = t2 / p.NB, q2 = t2 - u2 * p.NB;
+      const int t2 = t1 + gridDim.x;
+      int u2 = u1 + gdiv, q2 = q1 + gmod;
+      if (q2 >= p.NB) { q2 -= p.NB; ++u2; }
       int g0 = 0, g1 = 0;
       if (t2 < p.num_tiles) { g0 = __ldg(p.ptr + u2); g1 = __ldg(p.ptr + u2 + 1); }
       const uint8_t* srcq = p.src + (size_t)q * slab_b;
       if (e0 == e1) {  // no entries: the epilogue writes act(bias) / zeros; the MMA thread still hands the buffer over
-        if (lane == 0) {
+        if (lane == 0 && (stage_no & 1u) == pw) {
           mbar_wait(empty0 + slot * 8, ph ^ 1);
           hdr_s[slot] = 3u;
           mbar_arrive(full0 + slot * 8);
         }
+        ++stage_no;
         if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
       }
-      // Lane L of the warp owns entry L of the current block of 32: it computes its own addresses and B-descriptor word and
-      // issues its own bulk copy; lane 0 does the barrier round trip of each stage (one wait + one expect_tx per <= SPS slabs).
+      // Lane L of the warp owns entry L of the current block of 32: it computes its own source address and B-descriptor word
+      // (vector code, all lanes at once) and parks them in shared memory; ONE elected lane then does the barrier round trip of
+      // the stage and issues the <= SPS bulk copies from warp-uniform operands (a per-lane issue costs ~100 cycles per copy).
       for (int base = e0; base < e1; base += 32) {
         const int cnt = e1 - base < 32 ? e1 - base : 32;
         if (base > e0) mine = lane < cnt ? __ldg(p.ent + base + lane) : 0;  // long lists: the rest is fetched in place
-        const uint8_t* my_src = srcq + (size_t)(mine >> 5) * row_stride;
+        const unsigned long long my_src = (unsigned long long)(srcq + (size_t)(mine >> 5) * row_stride);
         const uint32_t my_lb = lo_b0 + (uint32_t)(mine & 31) * b_step;
         const int nstg = (cnt + p.SPS - 1) >> sps_shift;
         for (int sidx = 0; sidx < nstg; ++sidx) {
+          if (((stage_no++) & 1u) != pw) {  // the other producer warp's stage
+            if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
+            continue;
+          }
           const int ns = cnt - (sidx << sps_shift) < p.SPS ? cnt - (sidx << sps_shift) : p.SPS;
           const bool active = sidx_of_lane == sidx && lane < cnt;
-          if (lane == 0) {
+          const uint32_t hdr = (base + (sidx << sps_shift) == e0 ? 1u : 0u) | (base + (sidx << sps_shift) + ns == e1 ? 2u : 0u) |
+                               ((uint32_t)ns << 2);
+          if (elect_one()) {
             SC_T0(tw);
             mbar_wait(empty0 + slot * 8, ph ^ 1);
             SC_ACC(0, tw);
-            hdr_s[slot] = (base + (sidx << sps_shift) == e0 ? 1u : 0u) | (base + (sidx << sps_shift) + ns == e1 ? 2u : 0u) |
-                          ((uint32_t)ns << 2);
+            hdr_s[slot] = hdr;
           }
           __syncwarp();
-          if (active) lb_s[slot * SC_MAX_SPS + kpos] = my_lb;
+          if (active) {
+            lb_s[slot * SC_MAX_SPS + kpos] = my_lb;
+            src_s[slot * SC_MAX_SPS + kpos] = my_src;
+          }
           __syncwarp();
-          if (lane == 0) mbar_expect_tx(full0 + slot * 8, (uint32_t)ns * slab_b);
-          __syncwarp();
-          if (active) bulk_load(ring0 + slot * stage_b + kpos * slab_b, my_src, slab_b, full0 + slot * 8);
+          if (elect_one()) {
+            SC_T0(tc);
+            const uint32_t bar = full0 + slot * 8;
+            mbar_expect_tx(bar, (uint32_t)ns * slab_b);
+            const uint32_t dst = ring0 + slot * stage_b;
+            const unsigned long long* sp = &src_s[slot * SC_MAX_SPS];
+#pragma unroll
+            for (int k = 0; k < SC_MAX_SPS; ++k)
+              if (k < ns) bulk_load(dst + k * slab_b, reinterpret_cast<const void*>(sp[k]), slab_b, bar);
+            SC_ACC(10, tc);
+          }
           if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
         }
       }
@@ -188,12 +220,15 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
       t1 = t2; u1 = u2; q1 = q2; f0 = g0; f1 = g1;
     }
 #ifdef SHB_SLAB_TRACE
-    if (lane == 0) {
-      g_slab_trace[blockIdx.x * 8 + 0] = trace_acc[0];
-      g_slab_trace[blockIdx.x * 8 + 1] = clock64() - trace_start;
+    if (lane == 0 && warp == 0) {
+      g_slab_trace[blockIdx.x * 16 + 0] = trace_acc[0];
+      g_slab_trace[blockIdx.x * 16 + 1] = clock64() - trace_start;
+      g_slab_trace[blockIdx.x * 16 + 8] = trace_acc[8];
+      g_slab_trace[blockIdx.x * 16 + 9] = trace_acc[9];
+      g_slab_trace[blockIdx.x * 16 + 10] = trace_acc[10];
     }
 #endif
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // ================================================================ MMA issuer (one thread)
     // tcgen05.commit only tracks the issuing thread's MMAs, so one thread issues them all; what it executes per entry is cut
     // to the bone (every instruction of this dependent chain costs ~5 cycles): the B-descriptor word comes ready-made from the
@@ -202,7 +237,6 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
       const uint32_t idesc = idesc_bf16_f32(CHUNK, p.NP, 0, 0);
       const uint64_t hi_b = ((uint64_t)(((uint32_t)p.Q * 128) >> 4) << 32) | ((uint64_t)1 << 46);       // SBO = Q*128
       const uint64_t hi_a = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);                         // SBO = 128
-      const uint32_t nk = p.CS >= 16 ? (uint32_t)p.CS / 16 : 1u;   // MMAs (K = 16) per slab and plane
       const uint32_t slab16 = slab_b >> 4;
       // A: K-major, SBO = 128 (next 8 samples), LBO = 2048 (next 8 channels).  8-channel sources pair the slab with a block of
       // zeros through LBO = zero0 - slab: moving to the next slab adds slab16 to the address field and takes it off the LBO field
@@ -230,6 +264,7 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
           const uint32_t lbs[SC_MAX_SPS] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           tc_fence_after();
           const uint32_t ns = (hdr >> 2) & 15u;
+          SC_T0(ti);
           const uint32_t a_slab = ring0 + slot * stage_b;
           const uint32_t lbo_a = p.CS >= 16 ? (uint32_t)PLANE_STRIDE : zero0 - a_slab;
           uint32_t la0 = ((a_slab & 0x3FFFFu) >> 4) | ((lbo_a >> 4) << 16);
@@ -237,7 +272,8 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
           for (uint32_t k = 0; k < (uint32_t)SC_MAX_SPS; ++k) {
             if (k < ns) {
               uint32_t la = la0, lb = lbs[k];
-              for (uint32_t kk = 0; kk < nk; ++kk) {
+#pragma unroll
+              for (uint32_t kk = 0; kk < (uint32_t)NK; ++kk) {
                 mma_bf16(tmem_d, hi_a | la, hi_b | lb, idesc, acc);
                 acc = 1;
                 if (P == 2) {  // x ~ xh + xl, w ~ wh + wl: all four partial products (the tensor pipe is far from the bound)
@@ -251,7 +287,10 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
               la0 += a_step;
             }
           }
+          SC_ACC(11, ti);
+          SC_T0(tj);
           mma_commit_u32(empty0 + slot * 8);  // stage reusable once these MMAs have read it
+          SC_ACC(12, tj);
           if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
           if (hdr & 2u) {
             tile_empty_s[buf] = ns == 0 ? 1u : 0u;
@@ -262,9 +301,11 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
         mma_commit_u32(smem_u32(&tfull_bar[buf]));  // accumulator complete
       }
 #ifdef SHB_SLAB_TRACE
-      g_slab_trace[blockIdx.x * 8 + 2] = trace_acc[2];
-      g_slab_trace[blockIdx.x * 8 + 3] = trace_acc[3];
-      g_slab_trace[blockIdx.x * 8 + 4] = clock64() - trace_start;
+      g_slab_trace[blockIdx.x * 16 + 2] = trace_acc[2];
+      g_slab_trace[blockIdx.x * 16 + 3] = trace_acc[3];
+      g_slab_trace[blockIdx.x * 16 + 4] = clock64() - trace_start;
+      g_slab_trace[blockIdx.x * 16 + 11] = trace_acc[11];
+      g_slab_trace[blockIdx.x * 16 + 12] = trace_acc[12];
 #endif
     }
     __syncwarp();
@@ -275,16 +316,17 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
     // load issued next to a saturated TMA ring takes ~2000 cycles, so: many narrow warps, and the act' operands are requested
     // before the wait on the accumulator.
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-    const int grp = (warp - 2) >> 2;         // column group
+    const int grp = (warp - SC_LEAD_WARPS) >> 2;  // column group
     const int b = quarter * 32 + lane;       // sample within the chunk
     const int cpw = p.cpw, ngr = cpw >> 3;   // columns per warp (8, 16 or 32), 8-column vectors per warp
     const int col0 = grp * cpw;
     const size_t dslab = slab_bytes(p.Cd, P);
     const uint32_t plane_d = (uint32_t)(p.Cd / 8) * PLANE_STRIDE;
     int tcount = 0;
+    const int gdiv = (int)gridDim.x / p.NB, gmod = (int)gridDim.x - gdiv * p.NB;
+    int u = (int)blockIdx.x / p.NB, q = (int)blockIdx.x - u * p.NB;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
-      const int u = t / p.NB, q = t - u * p.NB;
       const bool zero = p.zero_last && u == p.rows_dst - 1;
       const size_t off = ((size_t)u * p.NB + q) * dslab + (size_t)((p.n0 + col0) / 8) * PLANE_STRIDE + (size_t)b * 16;
       uint8_t* drow = p.dst + off;
@@ -305,20 +347,28 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
       const bool empty_tile = tile_empty_s[buf] != 0;
       const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NP + col0) + ((uint32_t)(quarter * 32) << 16);
       uint32_t r[4][8];
+      SC_T0(te1);
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         if (g < ngr) tmem_ld8(taddr + g * 8, r[g]);
       tmem_ld_wait();
+      SC_ACC(13, te1);
+      SC_T0(te2);
       tc_fence_before();   // accumulator columns of this warp are in registers: hand the buffer back before the math
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      SC_ACC(14, te2);
+      SC_T0(te3);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (g >= ngr) break;
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          v[i] = act_fwd_fast((empty_tile ? 0.f : __uint_as_float(r[g][i])) + bias_s[col0 + 8 * g + i], p.act);
+        for (int i = 0; i < 8; ++i) v[i] = (empty_tile ? 0.f : __uint_as_float(r[g][i])) + bias_s[col0 + 8 * g + i];
+#ifdef SHB_SLAB_TRACE
+        if (!(p.dbg & 2))
+#endif
+          act_fwd8(v, p.act);
         if (p.ymul != nullptr) {
           float y[8];
           unpack8(yv[g][0], y);
@@ -328,13 +378,15 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] += yl[i];
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_out(y[i], p.act_mul);
+          act_bwd8(v, y, p.act_mul);
         }
         if (zero) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = 0.f;
         }
+#ifdef SHB_SLAB_TRACE
+        if ((p.dbg & 1) && v[0] != 12345.678f) continue;
+#endif
         if (P == 1) {
           *reinterpret_cast<uint4*>(drow + (size_t)g * PLANE_STRIDE) = pack8(v);
         } else {
@@ -344,20 +396,26 @@ __global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const Slab
           *reinterpret_cast<uint4*>(drow + (size_t)g * PLANE_STRIDE + plane_d) = lo;
         }
       }
+      SC_ACC(15, te3);
+      u += gdiv; q += gmod;
+      if (q >= p.NB) { q -= p.NB; ++u; }
     }
   }
 
 #ifdef SHB_SLAB_TRACE
-  if (tid == 64) {
-    g_slab_trace[blockIdx.x * 8 + 5] = trace_acc[5];
-    g_slab_trace[blockIdx.x * 8 + 6] = clock64() - trace_start;
-    g_slab_trace[blockIdx.x * 8 + 7] = (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  if (tid == SC_LEAD_WARPS * 32) {
+    g_slab_trace[blockIdx.x * 16 + 5] = trace_acc[5];
+    g_slab_trace[blockIdx.x * 16 + 6] = clock64() - trace_start;
+    g_slab_trace[blockIdx.x * 16 + 7] = (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    g_slab_trace[blockIdx.x * 16 + 13] = trace_acc[13];
+    g_slab_trace[blockIdx.x * 16 + 14] = trace_acc[14];
+    g_slab_trace[blockIdx.x * 16 + 15] = trace_acc[15];
   }
 #endif
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -406,7 +464,7 @@ __global__ void slab_weight_image_kernel(const float* __restrict__ w, uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-constexpr size_t SC_SMEM_MAX = 227 * 1024 - 3072;  // dynamic budget: leave room for the static part (barriers, bias)
+constexpr size_t SC_SMEM_MAX = 227 * 1024 - 3072;  // dynamic budget: leave room for the static part (barriers, tables, bias)
 
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 
@@ -421,7 +479,7 @@ static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
   const size_t stage_b = slab_b * SPS, zero_b = CS == 8 ? PLANE_STRIDE : 0;
   for (int NP = NPt > 256 ? 256 : NPt; NP >= 16; NP -= 16) {
     if (NPt % NP != 0 && NP != NPt) continue;  // equal passes
-    const size_t img_region = (((size_t)P * NP * Q * 16 + 128 + 1023) / 1024) * 1024;
+    const size_t img_region = (((size_t)P * NP * Q * 16 + (CS == 8 ? 128 : 0) + 1023) / 1024) * 1024;
     if (img_region + zero_b + 2 * stage_b > SC_SMEM_MAX) continue;
     size_t n = (SC_SMEM_MAX - img_region - zero_b) / stage_b;
     if (n < 3 && NP > 16) continue;  // prefer a narrower pass with a deeper ring
@@ -435,15 +493,38 @@ static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
 static int slab_conv_launch(const SlabConvParams& p, size_t smem, cudaStream_t st) {
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[p.P]) {
-    cudaError_t e = p.P == 1 ? cudaFuncSetAttribute(slab_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX)
-                             : cudaFuncSetAttribute(slab_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX);
+    cudaError_t e = cudaSuccess;
+#define SHB_SC_ATTR(PL, K) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(slab_conv_kernel<PL, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX)
+    if (p.P == 1) { SHB_SC_ATTR(1, 1); SHB_SC_ATTR(1, 2); SHB_SC_ATTR(1, 4); SHB_SC_ATTR(1, 8); SHB_SC_ATTR(1, 16); }
+    else { SHB_SC_ATTR(2, 1); SHB_SC_ATTR(2, 2); SHB_SC_ATTR(2, 4); SHB_SC_ATTR(2, 8); }
+#undef SHB_SC_ATTR
     if (e != cudaSuccess) return (int)e;
     attr_set[p.P] = true;
   }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  const int threads = 64 + 128 * p.EG;
-  if (p.P == 1) slab_conv_kernel<1><<<grid, threads, smem, st>>>(p);
-  else slab_conv_kernel<2><<<grid, threads, smem, st>>>(p);
+  const int threads = SC_LEAD_WARPS * 32 + 128 * p.EG;
+  const int nk = p.CS >= 16 ? p.CS / 16 : 1;  // MMAs (K = 16) per slab and plane
+#define SHB_SC_GO(PL, K) slab_conv_kernel<PL, K><<<grid, threads, smem, st>>>(p)
+  if (p.P == 1) {
+    switch (nk) {
+      case 1: SHB_SC_GO(1, 1); break;
+      case 2: SHB_SC_GO(1, 2); break;
+      case 4: SHB_SC_GO(1, 4); break;
+      case 8: SHB_SC_GO(1, 8); break;
+      case 16: SHB_SC_GO(1, 16); break;
+      default: return SHB_E_UNSUPPORTED;
+    }
+  } else {
+    switch (nk) {
+      case 1: SHB_SC_GO(2, 1); break;
+      case 2: SHB_SC_GO(2, 2); break;
+      case 4: SHB_SC_GO(2, 4); break;
+      case 8: SHB_SC_GO(2, 8); break;
+      default: return SHB_E_UNSUPPORTED;
+    }
+  }
+#undef SHB_SC_GO
   SHB_LAUNCH_CHECK();
   return 0;
 }
@@ -454,7 +535,7 @@ using namespace shb;
 
 #ifdef SHB_SLAB_TRACE
 extern "C" int shb_slab_trace_read(long long* host_out) {  // debug builds only: not part of the ABI
-  return (int)cudaMemcpyFromSymbol(host_out, g_slab_trace, sizeof(long long) * kNumSMs * 8);
+  return (int)cudaMemcpyFromSymbol(host_out, g_slab_trace, sizeof(long long) * kNumSMs * 16);
 }
 #endif
 
@@ -487,7 +568,9 @@ int shb_slab_weight_images(const float* w, void* img_fwd, void* img_bwd, int S, 
 int shb_slab_conv_supported(int S, int Cs, int Cd, int planes) {
   SlabConvPlan plan;
   if (S <= 0 || S > 32 || planes < 1 || planes > 2) return 0;
-  if (!(Cs == 8 || (Cs % 16 == 0 && Cs <= 256)) || (Cd & 7) || Cd <= 0 || Cd > 1024) return 0;
+  if (!(Cs == 8 || Cs == 16 || Cs == 32 || Cs == 64 || Cs == 128 || (Cs == 256 && planes == 1)) || (Cd & 7) || Cd <= 0 ||
+      Cd > 1024)
+    return 0;
   return slab_conv_plan(S, Cs, pad16(Cd), planes, &plan) ? 1 : 0;
 }
 
@@ -512,6 +595,7 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
     p.NP = plan.NP; p.n0 = n0;
     p.ncols = Cd - n0 < plan.NP ? Cd - n0 : plan.NP;
     p.w_img = (const uint8_t*)w_img + (size_t)(n0 / 8) * p.Q * 128;
+    { static const int dbg = [] { const char* e = getenv("SHB_SLAB_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
     p.cpw = p.ncols >= 128 ? 32 : (p.ncols >= 64 ? 16 : 8);
     p.EG = p.ncols / p.cpw;
     {

@@ -57,8 +57,7 @@ __global__ void __launch_bounds__(256) slab_pool_kernel(const uint8_t* __restric
 #pragma unroll
             for (int i = 0; i < 8; ++i) yy[i] += l[i];
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] *= act_bwd_from_out(yy[i], act_mul);
+          act_bwd8(acc, yy, act_mul);
         }
       }
       if (P == 1) {
@@ -115,8 +114,7 @@ __global__ void __launch_bounds__(256) slab_from_rows_kernel(const T* __restrict
 #pragma unroll
           for (int e = 0; e < 8; ++e) y[e] += l[e];
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= act_bwd_from_out(y[e], act_mul);
+        act_bwd8(v, y, act_mul);
       }
     }
     if (P == 1) {

@@ -83,11 +83,19 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
 
   if (warp == 0) {
     // ================================================================ producer
+    // Lane L owns piece L of a stage (<= 16 pieces of 128/PPG channels): it picks its source row out of the tile's table row
+    // (held one entry per lane, fetched a tile ahead) and issues its own bulk copies; lane 0 does the barrier round trips.
     uint32_t slot = 0, ph = 0;
     int tcount = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+    const int pps_shift = p.PPS == 2 ? 1 : 0;
+    int t = blockIdx.x;
+    int mine = 0;
+    if (t < p.num_tiles && lane < p.S) mine = __ldg(p.table + (size_t)(t / p.NB) * p.S + lane);
+    for (; t < p.num_tiles; t += gridDim.x, ++tcount) {
       const int j = t / p.NB, q = t - j * p.NB;
-      const int mine = lane < p.S ? __ldg(p.table + (size_t)j * p.S + lane) : 0;
+      const int tn = t + gridDim.x;
+      int mine_n = 0;
+      if (tn < p.num_tiles && lane < p.S) mine_n = __ldg(p.table + (size_t)(tn / p.NB) * p.S + lane);
       const int buf = tcount & 1;
       if (lane == 0) {
         mbar_wait(gempty0 + buf * 8, ((tcount >> 1) & 1) ^ 1);
@@ -99,26 +107,26 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
       for (int gi = 0; gi < p.Gp; ++gi) {
         const int pi0 = (p.g0 + gi) * p.PPG;
         const int np = pieces_total - pi0 < p.PPG ? pieces_total - pi0 : p.PPG;
+        const int pi = pi0 + lane, s = pi >> pps_shift, h = pi & (p.PPS - 1);
+        const int row = __shfl_sync(0xFFFFFFFFu, mine, s & 31);
         if (lane == 0) {
           mbar_wait(empty0 + slot * 8, ph ^ 1);
           mbar_expect_tx(full0 + slot * 8, (uint32_t)np * P * piece_b);
         }
-        for (int k = 0; k < np; ++k) {
-          const int pi = pi0 + k, s = pi / p.PPS, h = pi - s * p.PPS;
-          const int row = __shfl_sync(0xFFFFFFFFu, mine, s);
-          if (lane == 0) {
-            const uint8_t* src = p.x + ((size_t)row * p.NB + q) * xslab + (size_t)h * SW_GROUP_BYTES;
-            for (int pl = 0; pl < P; ++pl)
-              bulk_load(smem0 + slot * stage_b + pl * SW_GROUP_BYTES + k * piece_b, src + (size_t)pl * p.Cin * 256, piece_b,
-                        full0 + slot * 8);
-          }
+        __syncwarp();
+        if (lane < np) {
+          const uint8_t* src = p.x + ((size_t)row * p.NB + q) * xslab + (size_t)h * SW_GROUP_BYTES;
+          for (int pl = 0; pl < P; ++pl)
+            bulk_load(smem0 + slot * stage_b + pl * SW_GROUP_BYTES + lane * piece_b, src + (size_t)pl * p.Cin * 256, piece_b,
+                      full0 + slot * 8);
         }
         if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
       }
+      mine = mine_n;
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
+    // ================================================================ MMA issuer (one elected thread: warp-uniform operands)
+    if (elect_one()) {
       const uint32_t idesc = idesc_bf16_f32(CHUNK, p.N, 1, 1);
       // MN-major, un-swizzled: LBO = 128 B (next 8 samples), SBO = 2048 B (next 8 channels)
       const uint64_t hi = ((uint64_t)((uint32_t)PLANE_STRIDE >> 4) << 32) | ((uint64_t)1 << 46);
@@ -127,10 +135,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
       int tcount = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
-        mbar_wait_sleep(gfull0 + buf * 8, (tcount >> 1) & 1, 20);
+        mbar_wait_parked(gfull0 + buf * 8, (tcount >> 1) & 1, 1000);
         const uint32_t lo_g = (((gz0 + buf * gz_buf_b) & 0x3FFFFu) >> 4) | lbo;
         for (int gi = 0; gi < p.Gp; ++gi) {
-          mbar_wait_sleep(full0 + slot * 8, ph, 20);
+          mbar_wait_parked(full0 + slot * 8, ph, 1000);
           tc_fence_after();
           const uint32_t lo_a = (((smem0 + slot * stage_b) & 0x3FFFFu) >> 4) | lbo;
           const uint32_t tmem_d = tmem_base + (uint32_t)(gi * p.N);
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
       const int nchunk = p.ncols_gz / 8;  // 8-channel chunks of gz in this pass
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
-        mbar_wait_sleep(gfull0 + buf * 8, (tcount >> 1) & 1, 64);
+        mbar_wait_parked(gfull0 + buf * 8, (tcount >> 1) & 1, 2000);
         const uint8_t* g = dyn_smem + (size_t)p.nstage * stage_b + (size_t)buf * gz_buf_b;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
