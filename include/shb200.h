@@ -261,6 +261,19 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
                    size_t workspace_bytes, int B, int rows_out, int S, int Cin, int Cin_p, int Cout, int Cout_p, int skip_last,
                    int planes, void* stream);
 
+/* ---- Optimizer step (main.py:262: torch.optim.Adam(params, lr, weight_decay), defaults betas (0.9, 0.999), eps 1e-8):
+ * g += weight_decay * p;  m = lerp(m, g, 1-beta1);  v = beta2 v + (1-beta2) g^2;
+ * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps),   t = *step (device scalar, advanced by shb_adam_tick
+ * BEFORE the step so that the pair replays inside a CUDA graph).  `count` tensors, HOST arrays of DEVICE pointers (16-byte
+ * aligned) and element counts; shadow[k] != NULL receives bf16(p) of the updated weights (the operand of the bf16-mode FC
+ * GEMMs), so the step contains no separate weight cast.  shb_cast_bf16 is that cast on its own (initialisation, or after an
+ * update by a foreign optimizer). */
+int shb_adam_tick(float* step, void* stream);
+int shb_adam_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v, void* const* shadow,
+                  const int64_t* numel, const float* step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  void* stream);
+int shb_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,24 +19,54 @@ template <int P>
 __global__ void __launch_bounds__(256) slab_pool_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                         uint8_t* __restrict__ dst, const uint8_t* __restrict__ ymul, int NB,
-                                                        int rows_out, int C, int act_mul, int zero_last) {
+                                                        int rows_out, int C, int act_mul, int zero_last, int nslice) {
   const int nvec = C * 16;                  // 16-byte vectors per plane of a slab
+  const int vper = (nvec + nslice - 1) / nslice;   // a (row, chunk) unit is cut into nslice vector ranges when rows are few
   const size_t slab_b = slab_bytes(C, P);
-  const int units = rows_out * NB;
+  const int units = rows_out * NB * nslice;
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    const int r = unit / NB, q = unit - r * NB;
+    const int rq = unit / nslice, sl = unit - rq * nslice;
+    const int r = rq / NB, q = rq - r * NB;
     const int k0 = __ldg(rowptr + r), k1 = __ldg(rowptr + r + 1);
     const bool zero = zero_last && r == rows_out - 1;
     uint8_t* d = dst + ((size_t)r * NB + q) * slab_b;
     const uint8_t* y = ymul != nullptr ? ymul + ((size_t)r * NB + q) * slab_b : nullptr;
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int v1 = (sl + 1) * vper < nvec ? (sl + 1) * vper : nvec;
+    for (int v = sl * vper + threadIdx.x; v < v1; v += blockDim.x) {
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
       if (!zero) {
-        for (int k = k0; k < k1; ++k) {
+        const uint8_t* sv = src + (size_t)q * slab_b + (size_t)v * 16;
+        const size_t rstride = (size_t)NB * slab_b;
+        int k = k0;
+        for (; k + 4 <= k1; k += 4) {  // four independent loads in flight per thread; accumulation stays in CSR order
+          uint4 raw[4][P];
+          float w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint8_t* s = sv + (size_t)__ldg(colidx + k + j) * rstride;
+            w[j] = __ldg(vals + k + j);
+            raw[j][0] = __ldg(reinterpret_cast<const uint4*>(s));
+            if (P == 2) raw[j][P - 1] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)C * 256));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x[8];
+            unpack8(raw[j][0], x);
+            if (P == 2) {
+              float l[8];
+              unpack8(raw[j][P - 1], l);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] += l[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[j], x[i], acc[i]);
+          }
+        }
+        for (; k < k1; ++k) {
           const float w = __ldg(vals + k);
-          const uint8_t* s = src + ((size_t)__ldg(colidx + k) * NB + q) * slab_b + (size_t)v * 16;
+          const uint8_t* s = sv + (size_t)__ldg(colidx + k) * rstride;
           float x[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>(s)), x);
           if (P == 2) {
@@ -183,16 +213,20 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
                   int B, int rows_out, int C, int act_mul, int zero_last, int planes, void* stream) {
   if (!src || !rowptr || !colidx || !vals || !dst || B <= 0 || rows_out <= 0 || C <= 0 || (C & 7)) return SHB_E_ARG;
   if (planes < 1 || planes > 2) return SHB_E_ARG;
-  const int NB = slab::num_chunks(B), units = rows_out * NB;
-  const int threads = C * 16 < 256 ? 128 : 256;
+  const int NB = slab::num_chunks(B), nvec = C * 16;
+  int nslice = 1;  // few, long rows (the per-slot sums of the dummy-row gradient): spread a unit's vectors over several CTAs
+  while (rows_out * NB * nslice < 4 * kNumSMs && nvec / (nslice * 2) >= 32) nslice *= 2;
+  const int units = rows_out * NB * nslice;
+  const int per = nvec / nslice;
+  const int threads = per >= 256 ? 256 : (per >= 128 ? 128 : (per >= 64 ? 64 : 32));
   int grid = units < kNumSMs * 8 ? units : kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 1)
     slab_pool_kernel<1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
-                                                  NB, rows_out, C, act_mul, zero_last);
+                                                  NB, rows_out, C, act_mul, zero_last, nslice);
   else
     slab_pool_kernel<2><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
-                                                  NB, rows_out, C, act_mul, zero_last);
+                                                  NB, rows_out, C, act_mul, zero_last, nslice);
   SHB_LAUNCH_CHECK();
   return 0;
 }

@@ -10,7 +10,8 @@
 // layout.  The bias gradient is summed from the gz slab in shared memory by the four warps that otherwise only run the final
 // TMEM read-out.
 //
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = gz column sums + final read-out.
+// Roles: warps 0-1 = TMA producers (alternate ring stages), warp 2 = MMA issuer (one elected thread), warps 3-6 = gz column
+// sums + final read-out.
 #include "shb_common.cuh"
 #include "shb_internal.h"
 #include "shb_slab.cuh"
@@ -20,7 +21,7 @@ namespace shb {
 using namespace umma;
 using namespace slab;
 
-constexpr int SW_THREADS = 192;
+constexpr int SW_THREADS = 224;  // two producer warps, the MMA warp, four column-sum / read-out warps
 constexpr int SW_MAX_STAGES = 8;
 constexpr uint32_t SW_GROUP_BYTES = 32768;  // one plane of one stage: 128 channels x 128 samples x 2 B
 
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  if (warp == 2) tmem_alloc(&tmem_base_s, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -81,8 +82,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
   const uint32_t piece_b = (uint32_t)p.PC * 256;
   const size_t xslab = slab_bytes(p.Cin, P), gslab = slab_bytes(p.Cout_p, P);
 
-  if (warp == 0) {
-    // ================================================================ producer
+  if (warp < 2) {
+    // ================================================================ producers (warp w: stages with running number w mod 2)
+    const uint32_t pw = (uint32_t)warp;
+    uint32_t stage_no = 0;
     // Lane L owns piece L of a stage (<= 16 pieces of 128/PPG channels): it picks its source row out of the tile's table row
     // (held one entry per lane, fetched a tile ahead) and issues its own bulk copies; lane 0 does the barrier round trips.
     uint32_t slot = 0, ph = 0;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
       int mine_n = 0;
       if (tn < p.num_tiles && lane < p.S) mine_n = __ldg(p.table + (size_t)(tn / p.NB) * p.S + lane);
       const int buf = tcount & 1;
-      if (lane == 0) {
+      if (lane == 0 && warp == 0) {
         mbar_wait(gempty0 + buf * 8, ((tcount >> 1) & 1) ^ 1);
         mbar_expect_tx(gfull0 + buf * 8, P * gz_load_b);
         const uint8_t* g = p.gz + ((size_t)j * p.NB + q) * gslab + (size_t)(p.n0 / 8) * PLANE_STRIDE;
@@ -105,6 +108,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
           bulk_load(gz0 + buf * gz_buf_b + pl * gz_plane_b, g + (size_t)pl * p.Cout_p * 256, gz_load_b, gfull0 + buf * 8);
       }
       for (int gi = 0; gi < p.Gp; ++gi) {
+        if (((stage_no++) & 1u) != pw) {  // the other producer warp's stage
+          if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
+          continue;
+        }
         const int pi0 = (p.g0 + gi) * p.PPG;
         const int np = pieces_total - pi0 < p.PPG ? pieces_total - pi0 : p.PPG;
         const int pi = pi0 + lane, s = pi >> pps_shift, h = pi & (p.PPS - 1);
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
       }
       mine = mine_n;
     }
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // ================================================================ MMA issuer (one elected thread: warp-uniform operands)
     if (elect_one()) {
       const uint32_t idesc = idesc_bf16_f32(CHUNK, p.N, 1, 1);
@@ -161,8 +168,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
     }
     __syncwarp();
   } else {
-    // ================================================================ warps 2-5: bias column sums, then the read-out
-    const int ew = warp - 2;          // 0..3: column-sum work split; TMEM quarter is warp & 3
+    // ================================================================ warps 3-6: bias column sums, then the read-out
+    const int ew = warp - 3;          // 0..3: column-sum work split; TMEM quarter is warp & 3
     float bsum[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) bsum[i] = 0.f;
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgr
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -249,13 +256,30 @@ __global__ void slab_wgrad_reduce_kernel(const float* __restrict__ partial, cons
       const int piece = s * PPS + c / PC;
       const int row = (piece / PPG) * 128 + (piece % PPG) * PC + c % PC;
       const float* src = partial + (size_t)row * NPt + o;
+      // CTA order, eight loads in flight (a plain dependent loop over 148 strided partials took 22 us per launch)
       float acc = 0.f;
-      for (int q = 0; q < nparts; ++q) acc += src[(size_t)q * pstride];
+      int q = 0;
+      for (; q + 8 <= nparts; q += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)(q + j) * pstride);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      for (; q < nparts; ++q) acc += __ldg(src + (size_t)q * pstride);
       gw[(size_t)o * K + k] = acc;
     } else if (gb != nullptr && bias_partial != nullptr) {
       const int o = i - total;
       float acc = 0.f;
-      for (int q = 0; q < nparts; ++q) acc += bias_partial[(size_t)q * NPt + o];
+      int q = 0;
+      for (; q + 8 <= nparts; q += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(bias_partial + (size_t)(q + j) * NPt + o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      for (; q < nparts; ++q) acc += __ldg(bias_partial + (size_t)q * NPt + o);
       gb[o] = acc;
     }
   }

@@ -507,6 +507,40 @@ def group_linear_scatter(zz, layers, extra, lay):
     return GroupLinearScatterFn.apply(zz, w, b, extra, lay)
 
 
+def cast_bf16(src, dst):
+    """dst (bfloat16) = src (float32), one kernel; used for the FC weight shadows of the bf16 mode."""
+    _cuda(src, dst)
+    if src.dtype != torch.float32 or dst.dtype != torch.bfloat16 or src.numel() != dst.numel():
+        raise TypeError("cast_bf16: float32 source and bfloat16 destination of equal size")
+    _call("cast_bf16", {"bytes": 6.0 * src.numel()}, lib.shb_cast_bf16, _p(src.contiguous()), _p(dst), src.numel(), _stream())
+    _count()
+    return dst
+
+
+class LinearShadowFn(torch.autograd.Function):
+    """y = x W^T + b with bf16 operands taken from the weight SHADOWS (kept current by optim.Adam), gradients delivered to
+    the fp32 master parameters in fp32 (cuBLAS accumulates in fp32 anyway; no bf16 gradient tensor, no cast kernels).
+    The GEMMs are plain library GEMMs (models.py:129,142: nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, w_sh, b_sh):
+        ctx.save_for_backward(x, w_sh)
+        ctx.has_bias = b is not None
+        return torch.addmm(b_sh, x, w_sh.t()) if b is not None else torch.mm(x, w_sh.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w_sh = ctx.saved_tensors
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(g, w_sh)
+        if ctx.needs_input_grad[1]:
+            gw = torch.mm(g.t(), x, out_dtype=torch.float32)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = torch.sum(g, 0, dtype=torch.float32)
+        return gx, gw, gb, None, None
+
+
 def spiral_conv(x, weight, bias, geom, activation="elu", compute_dtype=None):
     """compute_dtype: storage/operand dtype of this layer (default: x.dtype); a differing input is cast (and, in
     bf16 mode, channel-padded) by one fused kernel."""

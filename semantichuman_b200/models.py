@@ -218,6 +218,30 @@ class _SpiralTrunk(nn.Module):
     def _planes(self):
         return 1 if self.compute_dtype == torch.bfloat16 else 2
 
+    def _shadow_of(self, p):
+        """bf16 copy of a master parameter, re-made only when the parameter changed (its autograd version) or moved.
+        optim.Adam writes the shadows itself, in the same pass as the update."""
+        if not hasattr(self, "_shadows"):
+            self._shadows = {}
+        ent = self._shadows.get(p)
+        if ent is None or ent[0].device != p.device or ent[0].shape != p.shape:
+            ent = [torch.empty_like(p, dtype=torch.bfloat16), -1]
+            self._shadows[p] = ent
+        if ent[1] != p._version:
+            fn.cast_bf16(p.detach(), ent[0])
+            ent[1] = p._version
+        return ent[0]
+
+    def shadow_map(self):
+        """{parameter: [bf16 shadow, version]} of the parameters the bf16 mode reads through shadows (the FC layers), for
+        optim.Adam(shadows=...)."""
+        if not hasattr(self, "_shadows"):
+            self._shadows = {}
+        for name, p in self.named_parameters():
+            if name.startswith("fc_latent_enc.") or name.startswith("fc_latent_dec."):
+                self._shadow_of(p)
+        return self._shadows
+
     def set_compute_dtype(self, dtype):
         """torch.float32 (default; every operand split into bf16 hi + lo, three tensor-core products per term, fp32
         accumulation: 1e-4 parity) or torch.bfloat16 (bf16 activations and operands, fp32 accumulation, fp32 master
@@ -269,7 +293,7 @@ class SpiralAutoencoder(_SpiralTrunk):
     def _linear(self, layer, v):
         if self.compute_dtype == torch.float32:
             return layer(v)
-        return F.linear(v, layer.weight.to(self.compute_dtype), layer.bias.to(self.compute_dtype))
+        return fn.LinearShadowFn.apply(v, layer.weight, layer.bias, self._shadow_of(layer.weight), self._shadow_of(layer.bias))
 
     def encode(self, x, VAE_flag):
         bsize = x.size(0)

@@ -100,19 +100,19 @@ class SlabGeometry:
         if not self.dummy_row_grad:
             live &= flat != self.rows_in - 1
         # A live dummy source row (the FC row under the first decoder conv) is referenced by every padded spiral entry:
-        # thousands of entries in ONE list.  Its gradient is taken in two steps instead -- per slot, sum the gz slabs that
-        # reference it (a Pool over a (S x rows_out) 0/1 matrix), then one S-entry tile: sum_s T[s] . W_s.
-        self.dummy_pool = None
+        # hundreds of entries in ONE list, i.e. one tile that a single CTA would grind through.  Its list is cut into
+        # sub-lists that run as ordinary tiles into a scratch tensor (one partial row each); a Pool row then adds the
+        # partials in order and applies the producer's activation derivative.
+        self.dummy_split = None
         to_dummy = live & (flat == self.rows_in - 1)
-        if self.dummy_row_grad and int(to_dummy.sum()) > 4 * S:
+        n_dummy = int(to_dummy.sum())
+        if self.dummy_row_grad and n_dummy > 4 * S:
             live &= flat != self.rows_in - 1
-            js, ss = j_of[to_dummy], slots[to_dummy]
-            o2 = np.lexsort((js, ss))  # by slot, then ascending row: the fixed summation order
-            cnt_s = np.bincount(ss, minlength=S)
-            used = np.nonzero(cnt_s)[0]
-            self.dummy_pool = (self._dev(np.concatenate([[0], np.cumsum(cnt_s)])), self._dev(js[o2]),
-                               torch.ones(int(to_dummy.sum()), dtype=torch.float32, device=self.device),
-                               self._dev(np.array([0, len(used)])), self._dev((used << 5) | used))
+            ents = ((j_of[to_dummy] << 5) | slots[to_dummy])  # ascending (j, s): the fixed summation order
+            T = (n_dummy + 47) // 48
+            bounds = (np.arange(T + 1, dtype=np.int64) * n_dummy) // T
+            self.dummy_split = (T, self._dev(bounds), self._dev(ents), self._dev(np.array([0, T])), self._dev(np.arange(T)),
+                                torch.ones(T, dtype=torch.float32, device=self.device))
         order = np.argsort(flat[live], kind="stable")
         counts_b = np.bincount(flat[live], minlength=self.rows_in)
         self.ptr_b = self._dev(np.concatenate([[0], np.cumsum(counts_b)]))
@@ -321,15 +321,15 @@ class SlabConvFn(torch.autograd.Function):
             _call("slabconv_dgrad" + ctx.tag, ctx.cmeta, lib.shb_slab_conv, _p(gz), _p(geom.ptr_b), _p(geom.ent_b), _p(img_b), None,
                   _p(gx), _p(t) if xact != 0 else None, B, rows, S, cout_p, Cp, C, 0, xact, int(xmasked), planes, _stream())
             _count()
-            if geom.dummy_pool is not None and not xmasked:
-                rowptr, colidx, vals, dptr, dent = geom.dummy_pool
-                tsum = torch.empty(Slab.shape_for(S, B, cout_p, planes), dtype=torch.bfloat16, device=dev)
-                _call("slabconv_dgrad_dummy_sum" + ctx.tag, {"bytes": 2.0 * planes * vals.numel() * cout_p * B}, lib.shb_slab_pool,
-                      _p(gz), _p(rowptr), _p(colidx), _p(vals), _p(tsum), None, B, S, cout_p, 0, 0, planes, _stream())
+            if geom.dummy_split is not None and not xmasked:
+                T, sptr, sent, prow, pcol, pval = geom.dummy_split
+                part = torch.empty(Slab.shape_for(T, B, Cp, planes), dtype=torch.bfloat16, device=dev)
+                _call("slabconv_dgrad_dummy" + ctx.tag, {"bytes": 2.0 * planes * sent.numel() * cout_p * B}, lib.shb_slab_conv,
+                      _p(gz), _p(sptr), _p(sent), _p(img_b), None, _p(part), None, B, T, S, cout_p, Cp, C, 0, 0, 0, planes, _stream())
                 off = (rows - 1) * gx[0].numel() * 2  # byte offset of the dummy row's slabs
-                _call("slabconv_dgrad_dummy" + ctx.tag, {"bytes": 0.0}, lib.shb_slab_conv, _p(tsum), _p(dptr), _p(dent), _p(img_b),
-                      None, _p(gx) + off, (_p(t) + off) if xact != 0 else None, B, 1, S, cout_p, Cp, C, 0, xact, 0, planes,
-                      _stream())
+                _call("slabconv_dgrad_dummy_sum" + ctx.tag, {"bytes": 2.0 * planes * (T + 1) * Cp * B}, lib.shb_slab_pool,
+                      _p(part), _p(prow), _p(pcol), _p(pval), _p(gx) + off, (_p(t) + off) if xact != 0 else None, B, 1, Cp, xact,
+                      0, planes, _stream())
                 _count(2)
         return gx, gw, gb, None, None, None, None
 

@@ -13,6 +13,7 @@ import torch
 
 from . import functions as fn
 from .dp import GradSync
+from .optim import Adam
 
 
 class TrainStep:
@@ -20,8 +21,9 @@ class TrainStep:
         self.model = model
         self.sync = GradSync(model)
         self.graph_enabled = bool(graph)
-        self.optim = (torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
-                                       capturable=self.graph_enabled) if optimizer else None)
+        # own multi-tensor Adam (device-side step count: replayable; writes the bf16 weight shadows in the same pass)
+        shadows = model.shadow_map() if hasattr(model, "shadow_map") else None
+        self.optim = Adam(model.parameters(), lr=lr, weight_decay=weight_decay, shadows=shadows) if optimizer else None
         self._copy_stream = None
         self._staged = None
         self._graph = None
@@ -42,7 +44,7 @@ class TrainStep:
     def capture(self, example_x, warmup=3):
         """Capture one whole step into a CUDA graph (static input buffer; later calls copy into it and replay)."""
         if not self.graph_enabled:
-            raise RuntimeError("construct TrainStep(graph=True) to capture (Adam must be built capturable)")
+            raise RuntimeError("construct TrainStep(graph=True) to capture")
         self._gx = example_x.clone()
         # warm-up and capture share one side stream: autograd's AccumulateGrad nodes (kept alive by the bucket hooks in
         # multi-process runs) remember the stream they were created on, and a mismatch would make the engine
