@@ -270,7 +270,7 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
  * update by a foreign optimizer). */
 int shb_adam_tick(float* step, void* stream);
 int shb_adam_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v, void* const* shadow,
-                  const int64_t* numel, const float* step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  const int64_t* numel, const float* step, double lr, double beta1, double beta2, float eps, float weight_decay,
                   void* stream);
 int shb_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -25,12 +25,19 @@ struct AdamTable {
 
 __global__ void adam_tick_kernel(float* step) { step[0] += 1.f; }
 
-__global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const float* __restrict__ step, float lr, float b1, float b2,
-                                                   float eps, float wd) {
-  // torch.optim.Adam (single-tensor formula): step_size = lr / (1 - b1^t); denom = sqrt(v) / sqrt(1 - b2^t) + eps
-  const float tt = __ldg(step);
-  const float bc1 = 1.f - powf(b1, tt), bc2_sqrt = sqrtf(1.f - powf(b2, tt));
-  const float step_size = lr / bc1;
+__global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const float* __restrict__ step, double lr_d, double b1_d,
+                                                   double b2_d, float eps, float wd) {
+  // torch.optim.Adam: step_size = lr / (1 - b1^t); denom = sqrt(v) / sqrt(1 - b2^t) + eps.  torch evaluates the bias
+  // corrections in Python doubles; in fp32, 1 - 0.999f^t loses five digits for small t (0.999f != 0.999), so: doubles here too
+  __shared__ float bc_s[2];
+  if (threadIdx.x == 0) {
+    const double tt = (double)__ldg(step);
+    bc_s[0] = (float)(lr_d / (1.0 - pow(b1_d, tt)));
+    bc_s[1] = (float)sqrt(1.0 - pow(b2_d, tt));
+  }
+  __syncthreads();
+  const float step_size = bc_s[0], bc2_sqrt = bc_s[1];
+  const float b1 = (float)b1_d, b2 = (float)b2_d;
   const int total_chunks = t.chunk_start[t.count];
   for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
     int ti = 0;
@@ -102,7 +109,7 @@ int shb_adam_tick(float* step, void* stream) {
 }
 
 int shb_adam_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v, void* const* shadow,
-                  const int64_t* numel, const float* step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  const int64_t* numel, const float* step, double lr, double beta1, double beta2, float eps, float weight_decay,
                   void* stream) {
   if (count <= 0 || !p || !g || !m || !v || !numel || !step) return SHB_E_ARG;
   for (int base = 0; base < count; base += AD_MAX_TENSORS) {
@@ -120,7 +127,7 @@ int shb_adam_step(int count, float* const* p, const float* const* g, float* cons
     }
     int grid = t.chunk_start[t.count];
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, step, lr, beta1, beta2, eps, weight_decay);
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, step, (double)lr, (double)beta1, (double)beta2, eps, weight_decay);
     SHB_LAUNCH_CHECK();
   }
   return 0;
