@@ -14,9 +14,9 @@
  *     (a cudaStream_t passed as void*).  The caller owns every buffer, including workspaces.
  *   - return value: 0 = ok; negative = argument error (SHB_E_*); positive = a cudaError_t from the launch.
  *     shb_error_string() renders either.  The Python host raises RuntimeError on any non-zero code.
- *   - activations are row-major (B, rows, C): batch-major, channel fastest -- the reference's own layout
- *     (models.py:37,48).  `dtype` selects the storage type of activations/weights/gradients; accumulation
- *     is always fp32.
+ *   - callers hand over row-major (B, rows, C) tensors (batch-major, channel fastest -- the reference's own layout,
+ *     models.py:37,48); inside the trunks activations live in the SLAB layout described further down, and
+ *     shb_slab_from_rows / shb_slab_to_rows convert.  Accumulation is always fp32.
  *   - "table": the spiral index table restricted to the rows this call produces, int32, (rows_out, S),
  *     values in [0, rows_in): the reference's -1 (models.py:42, Python negative index -> dummy row) is
  *     normalised to rows_in-1 on the host (semantichuman_b200/indexing.py).
@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SHB_ABI_VERSION 1
+#define SHB_ABI_VERSION 2
 
 /* activation enum == the strings models.py:19-32 accepts */
 enum { SHB_ACT_IDENTITY = 0, SHB_ACT_RELU = 1, SHB_ACT_ELU = 2, SHB_ACT_LEAKY_RELU = 3, SHB_ACT_SIGMOID = 4,
@@ -53,17 +53,6 @@ const char* shb_error_string(int code);
 int shb_build_inverse_spiral_csr(const int32_t* table, int rows_out, int S, int rows_in, int32_t* rowptr,
                                  int32_t* slots);
 
-/* Same relation keyed by (u, s): for key u*S+s the ascending list of output rows j with table[j,s]==u.
- * This is the layout the input-gradient kernel consumes (one weight slice per key).
- *   HOST keyptr (rows_in*S+1), HOST rows (rows_out*S). */
-int shb_build_inverse_spiral_by_slot(const int32_t* table, int rows_out, int S, int rows_in, int32_t* keyptr,
-                                     int32_t* rows);
-
-/* Inline form of the (u,s)-keyed relation: quads[u,s,0..3] = the first four output rows of the key as uint16
- * (0xFFFF = none).  A key with five or more entries stores three rows and 0xFFFE in the fourth position: entries 3..
- * continue in the CSR.  Row ids must be <= 0xFFFD.  HOST keyptr/rows as produced above, HOST quads (rows_in*S*4). */
-int shb_build_inverse_spiral_quads(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, uint16_t* quads);
-
 /* Dense padded sampling matrix (main.py:183-193: D/U .todense(), +1 row/col, corner 1) -> CSR, dropping exact
  * zeros.  Call with colidx==NULL to count: *nnz_out receives the number of non-zeros.
  *   HOST dense (rows*cols) fp32, HOST rowptr (rows+1), HOST colidx/vals (cap). */
@@ -74,71 +63,6 @@ int shb_dense_to_csr(const float* dense, int rows, int cols, int32_t* rowptr, in
  * order: the operand of the Pool backward  dx = P^T dy  (autograd of models.py:127,148). HOST pointers. */
 int shb_csr_transpose(const int32_t* rowptr, const int32_t* colidx, const float* vals, int rows, int cols,
                       int32_t* t_rowptr, int32_t* t_colidx, float* t_vals);
-
-/* ------------------------------------------------------------------ SpiralConv (models.py:34-53) */
-
-/* y[b,j,:] = act( W . concat_s x[b, table[j,s], :] + bias ),  and y[b,rows_out-1,:] = 0 when zero_last_row
- * (the mask multiply of models.py:48-51).  Replaces index (models.py:42) + addmm (:45) + activation (:46)
- * + mask (:49-51) with one fused gather-GEMM.
- *   x (B, rows_in, Cin); w (Cout, S*Cin) -- nn.Linear's own layout, k = s*Cin + c, stored as `dtype`;
- *   bias (Cout) ALWAYS fp32, or NULL;  y (B, rows_out, Cout).
- *   rows_out may be smaller than rows_in (conv fused with a selection down-pool).
- *   src_dummy_zero != 0 is a promise that x[b, rows_in-1, :] == 0 (the producer masked it, models.py:51): gathers of the
- *   dummy row (13-22 % of all slots) are then zero-filled without touching memory.  0 is always correct. */
-int shb_spiralconv_fwd(const void* x, const int32_t* table, const void* w, const void* bias, void* y, int B,
-                       int rows_in, int rows_out, int S, int Cin, int Cout, int act, int zero_last_row,
-                       int src_dummy_zero, int dtype, void* stream);
-
-/* gz = gy * act'(.) expressed through the saved OUTPUT y, zero on the dummy row when zero_last_row
- * (ELU' = y+1 for y<=0 etc.).  Replaces EluBackward/MulBackward of models.py:46,51.
- *   gy, y (B, rows_out, Cout);  gz (B, rows_out, gz_channels), gz_channels >= Cout, extra channels zero-filled
- *   (the host pads 3-channel gradients to 16 so that they can take the tensor-core path).
- *   In place (gz==gy) is allowed when gz_channels == Cout.
- *   gb (Cout) fp32 or NULL: the bias gradient sum_{b,j} gz[b,j,:] (the column sums AddmmBackward produces for
- *   models.py:45), accumulated in the same pass (fixed-order two-stage reduction); needs `workspace` of
- *   shb_spiralconv_bwd_act_workspace(gz_channels) bytes. */
-size_t shb_spiralconv_bwd_act_workspace(int gz_channels);
-int shb_spiralconv_bwd_act(const void* gy, const void* y, void* gz, int B, int rows_out, int Cout, int gz_channels,
-                           int act, int zero_last_row, void* gb, void* workspace, size_t workspace_bytes, int dtype,
-                           void* stream);
-
-/* dst[r, c] = c < C ? src[r, c] : 0, converting between fp32 and bf16 on the way: channel zero-padding of
- * narrow activations (the 3-channel mesh coordinates of models.py:157) to a 16-byte-chunk multiple.
- *   src (rows, C) as dtype_src;  dst (rows, Cp) as dtype_dst. */
-int shb_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cp, int dtype_src, int dtype_dst,
-                     void* stream);
-
-/* Weight/bias gradient: gw[n, s*Cin+c] = sum_{b,j} gz[b,j,n] * x[b, table[j,s], c];  gb[n] = sum gz[b,j,n].
- * Replaces the  dZ^T . A  mm of AddmmBackward (models.py:45) without materialising A.  Split over rows with a
- * fixed-order second-stage reduction: bit-reproducible.  gw (Cout, S*Cin) and gb (Cout) are ALWAYS fp32
- * (master-weight gradients), whatever `dtype` x and gz are stored in.  gb may be NULL.
- *   workspace: shb_spiralconv_wgrad_workspace() bytes. */
-size_t shb_spiralconv_wgrad_workspace(int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dtype);
-int shb_spiralconv_bwd_wgrad(const void* x, const int32_t* table, const void* gz, void* gw, void* gb,
-                             void* workspace, size_t workspace_bytes, int B, int rows_in, int rows_out, int S,
-                             int Cin, int Cout, int src_dummy_zero, int dtype, void* stream);
-
-/* Input gradient: gx[b,u,:] = sum_{(j,s): table[j,s]==u} gz[b,j,:] . W[:, s*Cin:(s+1)*Cin], evaluated as a
- * gather-sum GEMM over the (u,s)-keyed inverse table -- no float atomics, fixed summation order.  Replaces
- * mm (dA = dZ.W) + index_put_(accumulate=True) of the autograd of models.py:42,45.
- *   quads (rows_in, S, 4) uint16 or NULL: the first four entries of every key inline (see
- *   shb_build_inverse_spiral_quads) -- lets the tensor-core path issue all loads of a tile without dependent index
- *   loads (with two inline entries ~93 % of warp-stages still took the three-round-trip CSR path; with four, ~7 %).
- *   NULL selects the CUDA-core path.
- *   dummy_row_grad: 0 -> gx[b, rows_in-1, :] = 0 (its producer masks it: every layer but the first decoder
- *   conv of the plain AE); 1 -> computed by a segmented fixed-order reduction. */
-int shb_spiralconv_bwd_dgrad(const void* gz, const int32_t* keyptr, const int32_t* rows, const uint16_t* quads,
-                             const void* w, void* gx,
-                             int B, int rows_in, int rows_out, int S, int Cin, int Cout, int dummy_row_grad,
-                             int dtype, void* stream);
-
-/* ------------------------------------------------------------------ Pool (models.py:127,148,250,276) */
-
-/* y[b,r,:] = sum_e vals[e] * x[b, colidx[e], :]  for e in [rowptr[r], rowptr[r+1]).  CSR SpMM over batch-major
- * features; replaces torch.matmul with the dense (1, rows_out, rows_in) D/U.  Use the transposed CSR for
- * the backward.  x (B, rows_in, C); y (B, rows_out, C). */
-int shb_pool_spmm(const void* x, const int32_t* rowptr, const int32_t* colidx, const float* vals, void* y, int B,
-                  int rows_in, int rows_out, int C, int dtype, void* stream);
 
 /* ------------------------------------------------------------------ losses (train_funcs.py:135,145-152,501) */
 

@@ -16,13 +16,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 DST = os.path.join(HERE, "_ref")
 FILES = ["models.py", os.path.join("configure", "__init__.py"), os.path.join("configure", "cfgs.py")]
+# the reference's training loop and what it imports: staged for the drop-in test that drives the CUDA model through
+# train_funcs.train_autoencoder_dataloader itself (tests/test_gpu_dropin_loop.py)
+LOOP_FILES = ["train_funcs.py", "utils_SH.py", "utils_distance.py", "mesh_sampling.py", "shape_data.py", "utils_spiral.py"]
 
 
 def build(verbose=False):
     """Returns True if oracle/_ref/ holds the reference files (freshly staged or already there)."""
     if not os.path.isdir(REF):
         return available()
-    for rel in FILES:
+    for rel in FILES + LOOP_FILES:
         src, dst = os.path.join(REF, rel), os.path.join(DST, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
@@ -32,8 +35,26 @@ def build(verbose=False):
     return available()
 
 
-def available():
-    return all(os.path.exists(os.path.join(DST, rel)) for rel in FILES)
+def available(loop=False):
+    return all(os.path.exists(os.path.join(DST, rel)) for rel in FILES + (LOOP_FILES if loop else []))
+
+
+def import_reference_module(name):
+    """Import a staged reference module by name (e.g. "train_funcs") with the inert third-party stand-ins of
+    tests/golden/_ref_stubs.py (yacs, psbody, opendr, trimesh, torch_scatter, tensorboardX)."""
+    if not available(loop=True):
+        raise ImportError("oracle/_ref does not hold the reference's training loop (run oracle/build_ref.py)")
+    import importlib
+
+    sys.path.insert(0, os.path.join(HERE, "..", "tests", "golden"))
+    import _ref_stubs
+
+    _ref_stubs.install()
+    while "/root/reference" in sys.path:  # the staged copy is the one under test, here and on the GPU box
+        sys.path.remove("/root/reference")
+    if DST not in sys.path:
+        sys.path.insert(0, DST)
+    return importlib.import_module(name)
 
 
 def import_reference_models():

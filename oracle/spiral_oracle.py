@@ -4,7 +4,7 @@ This file restates, as plain functions over CPU torch tensors (any float dtype; 
 the algorithm of the reference's ``models.py`` and of the loss lines of ``train_funcs.py``.  It exists so that
 the CUDA path can be checked on a box that does not have ``/root/reference``.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it;
-the product package ``semantichuman_b200`` never does (tests/test_no_oracle_in_product.py enforces that).
+the product package ``semantichuman_b200`` never does (tests/test_capi_cpu.py::test_product_never_imports_oracle enforces that).
 
 Pinning: the reference has no tests or golden vectors of its own, so the oracle is pinned
 against outputs of the reference itself, generated in the build container by ``tests/golden/make_golden.py``
@@ -261,17 +261,6 @@ def inverse_spiral_csr(table, rows_in):
     rowptr = np.zeros(rows_in + 1, np.int32)
     np.add.at(rowptr, flat + 1, 1)
     return np.cumsum(rowptr).astype(np.int32), slots
-
-
-def inverse_spiral_by_slot(table, rows_in):
-    """Key u*S+s -> ascending output rows j with table[j,s]==u."""
-    t = np.asarray(table).astype(np.int64)
-    rows_out, S = t.shape
-    key = (t * S + np.arange(S)[None, :]).reshape(-1)
-    order = np.argsort(key, kind="stable")
-    keyptr = np.zeros(rows_in * S + 1, np.int64)
-    np.add.at(keyptr, key + 1, 1)
-    return np.cumsum(keyptr).astype(np.int32), (order // S).astype(np.int32)
 
 
 def dense_to_csr(dense):

@@ -16,18 +16,8 @@ SIGNATURES = {
     "shb_abi_version": (c_int, []),
     "shb_error_string": (ctypes.c_char_p, [c_int]),
     "shb_build_inverse_spiral_csr": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
-    "shb_build_inverse_spiral_by_slot": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
-    "shb_build_inverse_spiral_quads": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "shb_csr_transpose": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
-    "shb_spiralconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
-    "shb_spiralconv_bwd_act_workspace": (c_size, [c_int]),
-    "shb_spiralconv_bwd_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_size, c_int, c_vp]),
-    "shb_pad_channels": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
-    "shb_spiralconv_wgrad_workspace": (c_size, [c_int] * 7),
-    "shb_spiralconv_bwd_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size] + [c_int] * 8 + [c_vp]),
-    "shb_spiralconv_bwd_dgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),
-    "shb_pool_spmm": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 5 + [c_vp]),
     "shb_l1_loss_workspace": (c_size, [c_i64]),
     "shb_l1_loss_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_size, c_vp, c_int, c_vp]),
     "shb_l1_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
@@ -69,7 +59,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.shb_abi_version() != 1:
+    if lib.shb_abi_version() != 2:
         raise ImportError("libshb200.so ABI version mismatch")
     return lib
 

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const floa
   }
   __syncthreads();
   const float step_size = bc_s[0], bc2_sqrt = bc_s[1];
-  const float b1 = (float)b1_d, b2 = (float)b2_d;
+  // 1 - beta in double, then rounded (as torch's Python scalars): 1.f - 0.999f is 1.3e-5 away from 0.001f
+  const float b2 = (float)b2_d, omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);
   const int total_chunks = t.chunk_start[t.count];
   for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
     int ti = 0;
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const floa
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float gk = ga[k] + wd * pa[k];
-        ma[k] = ma[k] + (1.f - b1) * (gk - ma[k]);          // lerp form, as torch: exp_avg.lerp_(grad, 1 - beta1)
-        va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+        ma[k] = ma[k] + omb1 * (gk - ma[k]);          // lerp form, as torch: exp_avg.lerp_(grad, 1 - beta1)
+        va[k] = b2 * va[k] + omb2 * gk * gk;
         const float denom = sqrtf(va[k]) / bc2_sqrt + eps;
         pa[k] = pa[k] - step_size * (ma[k] / denom);
       }
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const floa
     }
     for (long long i = n4 + threadIdx.x; i < n; i += 256) {
       const float gk = g[i] + wd * p[i];
-      const float mk = m[i] + (1.f - b1) * (gk - m[i]);
-      const float vk = b2 * v[i] + (1.f - b2) * gk * gk;
+      const float mk = m[i] + omb1 * (gk - m[i]);
+      const float vk = b2 * v[i] + omb2 * gk * gk;
       const float pk = p[i] - step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
       p[i] = pk; m[i] = mk; v[i] = vk;
       if (sh != nullptr) sh[i] = __float2bfloat16_rn(pk);

@@ -40,42 +40,6 @@ int shb_build_inverse_spiral_csr(const int32_t* table, int rows_out, int S, int 
 }
 
 // Key (u, s) -> ascending output rows j with table[j, s] == u.
-int shb_build_inverse_spiral_by_slot(const int32_t* table, int rows_out, int S, int rows_in, int32_t* keyptr,
-                                     int32_t* rows) {
-  if (!table || !keyptr || !rows || rows_out <= 0 || S <= 0 || rows_in <= 0) return SHB_E_ARG;
-  const long long nkeys = (long long)rows_in * S;
-  for (long long k = 0; k <= nkeys; ++k) keyptr[k] = 0;
-  for (int j = 0; j < rows_out; ++j)
-    for (int s = 0; s < S; ++s) {
-      const int u = table[(long long)j * S + s];
-      if (u < 0 || u >= rows_in) return SHB_E_SHAPE;
-      keyptr[(long long)u * S + s + 1]++;
-    }
-  for (long long k = 0; k < nkeys; ++k) keyptr[k + 1] += keyptr[k];
-  std::vector<int32_t> cur(keyptr, keyptr + nkeys);
-  for (int j = 0; j < rows_out; ++j)
-    for (int s = 0; s < S; ++s) rows[cur[(long long)table[(long long)j * S + s] * S + s]++] = j;
-  return 0;
-}
-
-int shb_build_inverse_spiral_quads(const int32_t* keyptr, const int32_t* rows, int rows_in, int S, uint16_t* quads) {
-  if (!keyptr || !rows || !quads || rows_in <= 0 || S <= 0) return SHB_E_ARG;
-  const long long nkeys = (long long)rows_in * S;
-  for (long long k = 0; k < nkeys; ++k) {
-    const int e0 = keyptr[k], cnt = keyptr[k + 1] - e0;
-    for (int t = 0; t < 4; ++t) {
-      uint16_t v = 0xFFFF;  // none
-      if (t < cnt) {
-        if (rows[e0 + t] < 0 || rows[e0 + t] > 0xFFFD) return SHB_E_SHAPE;  // row ids must fit 16 bits
-        v = (uint16_t)rows[e0 + t];
-      }
-      quads[4 * k + t] = v;
-    }
-    if (cnt > 4) quads[4 * k + 3] = 0xFFFE;  // overflow: entries 3.. continue in the CSR
-  }
-  return 0;
-}
-
 int shb_dense_to_csr(const float* dense, int rows, int cols, int32_t* rowptr, int32_t* colidx, float* vals,
                      int64_t cap, int64_t* nnz_out) {
   if (!dense || rows <= 0 || cols <= 0 || !nnz_out) return SHB_E_ARG;

@@ -474,14 +474,18 @@ struct SlabConvPlan { int NP, nstage, SPS; size_t smem; };
 static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
   const int Q = S * CS / 8;
   const size_t slab_b = (size_t)P * CS * 256;
-  int SPS = 1;
-  while (SPS < SC_MAX_SPS && slab_b * SPS * 2 <= 32768) SPS *= 2;
-  const size_t stage_b = slab_b * SPS, zero_b = CS == 8 ? PLANE_STRIDE : 0;
+  const size_t zero_b = CS == 8 ? PLANE_STRIDE : 0;
+  static const size_t stage_cap = [] { const char* e = getenv("SHB_SLAB_STAGE_KB"); return (size_t)(e ? atoi(e) : 64) * 1024; }();
   for (int NP = NPt > 256 ? 256 : NPt; NP >= 16; NP -= 16) {
     if (NPt % NP != 0 && NP != NPt) continue;  // equal passes
     const size_t img_region = (((size_t)P * NP * Q * 16 + (CS == 8 ? 128 : 0) + 1023) / 1024) * 1024;
-    if (img_region + zero_b + 2 * stage_b > SC_SMEM_MAX) continue;
-    size_t n = (SC_SMEM_MAX - img_region - zero_b) / stage_b;
+    if (img_region + zero_b + 2 * slab_b > SC_SMEM_MAX) continue;
+    const size_t room = SC_SMEM_MAX - img_region - zero_b;
+    // slabs per stage: as many as keep a stage <= stage_cap (one barrier round trip per stage) with >= 3 stages in the ring
+    int SPS = 1;
+    while (SPS < SC_MAX_SPS && slab_b * SPS * 2 <= stage_cap && room / (slab_b * SPS * 2) >= 3) SPS *= 2;
+    const size_t stage_b = slab_b * SPS;
+    size_t n = room / stage_b;
     if (n < 3 && NP > 16) continue;  // prefer a narrower pass with a deeper ring
     if (n > SC_MAX_STAGES) n = SC_MAX_STAGES;
     out->NP = NP; out->nstage = (int)n; out->SPS = SPS; out->smem = img_region + zero_b + n * stage_b;

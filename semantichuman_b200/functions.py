@@ -1,4 +1,5 @@
-"""torch.autograd.Functions over the C ABI of libshb200 (include/shb200.h).
+"""torch.autograd.Functions over the C ABI of libshb200 (include/shb200.h): losses, grouped heads, FC shadow GEMMs.
+The SpiralConv / Pool operators live in slab.py.
 
 torch is plumbing here: it owns device memory, streams and the autograd graph; every arithmetic step of the
 path is a kernel of libshb200.  Tensors must be CUDA tensors -- there is no CPU path (north_star).
@@ -87,156 +88,6 @@ def _pool_meta(B, pm, C, esize, transposed):
     rows_read = pm.rows_out if pm.is_selection else (pm.rows_out if transposed else pm.rows_in)
     rows_written = pm.rows_in if transposed else pm.rows_out
     return {"flops": 2.0 * B * pm.nnz * C, "bytes": float(B) * (rows_read + rows_written) * C * esize + pm.nnz * 8.0}
-
-
-def _pad16(c):
-    return (c + 15) // 16 * 16
-
-
-def _pad_bf16(c, S):
-    """Channel count the tcgen05 kernels take for a c-channel operand: a multiple of 16, or 8 (one 16-byte chunk per
-    gathered row -- the 3-channel mesh coordinates) when the spiral length is even (an MMA consumes two chunks of K)."""
-    if c % 16 == 0:
-        return c
-    return 8 if (c <= 8 and S % 2 == 0) else _pad16(c)
-
-
-def pad_channels(x, cp, out_dtype=None):
-    """(…, C) -> (…, cp) zero-padded along the channel axis (+ optional fp32<->bf16 cast) in one kernel."""
-    out_dtype = x.dtype if out_dtype is None else out_dtype
-    x = x.contiguous()
-    C = x.shape[-1]
-    out = torch.empty(x.shape[:-1] + (cp,), dtype=out_dtype, device=x.device)
-    rows = x.numel() // C
-    _call("pad_channels", {"bytes": float(rows) * (C * x.element_size() + cp * out.element_size())}, lib.shb_pad_channels,
-          _p(x), _p(out), rows, C, cp, _DT[x.dtype], _DT[out_dtype], _stream())
-    _count()
-    return out
-
-
-class SpiralConvFn(torch.autograd.Function):
-    """y = mask * act(W . gather(x) + b)   (models.py:34-53) -- one fused kernel forward; backward =
-    act' kernel + weight-gradient kernel (+ fixed-order reduce) + inverse-table input-gradient kernel.
-
-    bf16 mode: operands whose channel count is not a multiple of 16 (the 3-channel mesh coordinates at both ends of
-    the autoencoder) are zero-padded to 8 (even spiral length) or 16 so that every layer takes the tcgen05 path
-    (16-byte gather chunks, UMMA K = 16); the padding never leaves this function (gradients are sliced back)."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, geom, act, compute_dtype):
-        _cuda(x, weight, bias)
-        if x.dim() != 3:
-            raise ValueError("x must be (B, V+1, C)")
-        cdt = x.dtype if compute_dtype is None else compute_dtype
-        B, rows_in, cin = x.shape
-        cout, k = weight.shape
-        if rows_in != geom.rows_in or k != geom.S * cin:
-            raise ValueError(f"shape mismatch: x {tuple(x.shape)}, weight {tuple(weight.shape)}, "
-                             f"geometry rows_in={geom.rows_in} S={geom.S}")
-        if geom.table.device != x.device:
-            raise RuntimeError("spiral tables live on a different device than x")
-        S = geom.S
-        cin_p = _pad_bf16(cin, S) if cdt == torch.bfloat16 else cin
-        if cin_p != cin or x.dtype != cdt:
-            xk = pad_channels(x, cin_p, cdt)  # pad and/or cast in one pass
-        else:
-            xk = x.contiguous()
-        w = weight.detach()
-        if cin_p != cin:
-            w = torch.nn.functional.pad(w.view(cout, S, cin), (0, cin_p - cin)).reshape(cout, S * cin_p)
-        w = w.to(cdt).contiguous()
-        b32 = None if bias is None else bias.detach().float().contiguous()
-        y = torch.empty((B, geom.rows_out, cout), dtype=cdt, device=x.device)
-        meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, xk.element_size())
-        _call(f"spiralconv_fwd[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]", meta, lib.shb_spiralconv_fwd, _p(xk),
-              _p(geom.table), _p(w), _p(b32), _p(y), B, rows_in, geom.rows_out, S, cin_p, cout, act,
-              int(geom.zero_last_row), int(geom.src_dummy_zero), _dt(xk), _stream())
-        _count()
-        ctx.save_for_backward(xk, w, y)
-        ctx.geom, ctx.act, ctx.has_bias = geom, act, bias is not None
-        ctx.wdtype, ctx.xdtype, ctx.cin = weight.dtype, x.dtype, cin
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, w, y = ctx.saved_tensors
-        geom, act, cin = ctx.geom, ctx.act, ctx.cin
-        B, rows_in, cin_p = x.shape
-        cout, S = w.shape[0], geom.S
-        gy = gy.contiguous()
-        if gy.dtype != x.dtype:
-            gy = gy.to(x.dtype)
-        dt, st = _dt(x), _stream()
-        bf16 = x.dtype == torch.bfloat16
-        cout_p = _pad_bf16(cout, S) if (bf16 and cout % 8) else cout
-        gz = torch.empty((B, geom.rows_out, cout_p), dtype=x.dtype, device=x.device)
-        tag = f"[{rows_in}>{geom.rows_out}x{S}x{cin}>{cout}]"
-        meta = _conv_meta(B, rows_in, geom.rows_out, S, cin, cout, x.element_size())
-        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
-        gb = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_gb else None
-        abytes = lib.shb_spiralconv_bwd_act_workspace(cout_p) if want_gb else 0
-        aws = torch.empty(abytes, dtype=torch.uint8, device=x.device) if want_gb else None
-        _call("spiralconv_bwd_act" + tag, {"bytes": (2.0 * gy.numel() + gz.numel()) * gy.element_size()},
-              lib.shb_spiralconv_bwd_act, _p(gy), _p(y), _p(gz), B, geom.rows_out, cout, cout_p, act,
-              int(geom.zero_last_row), _p(gb), _p(aws), abytes, dt, st)
-        _count(3 if want_gb else 1)
-        if cout_p != cout:  # zero rows for the padded output channels
-            w = torch.nn.functional.pad(w, (0, 0, 0, cout_p - cout)).contiguous()
-        gx = gw = None
-        if ctx.needs_input_grad[1]:
-            nbytes = lib.shb_spiralconv_wgrad_workspace(B, rows_in, geom.rows_out, S, cin_p, cout_p, dt)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-            gw = torch.empty((cout_p, S * cin_p), dtype=torch.float32, device=x.device)
-            _call("spiralconv_bwd_wgrad" + tag, meta, lib.shb_spiralconv_bwd_wgrad, _p(x), _p(geom.table), _p(gz), _p(gw),
-                  None, _p(ws), nbytes, B, rows_in, geom.rows_out, S, cin_p, cout_p, int(geom.src_dummy_zero), dt, st)
-            _count(2)
-            if cout_p != cout or cin_p != cin:
-                gw = gw.view(cout_p, S, cin_p)[:cout, :, :cin].reshape(cout, S * cin)
-            if ctx.wdtype != torch.float32:
-                gw = gw.to(ctx.wdtype)
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            _call("spiralconv_bwd_dgrad" + tag, meta, lib.shb_spiralconv_bwd_dgrad, _p(gz), _p(geom.keyptr),
-                  _p(geom.inv_rows), _p(geom.inv_quads), _p(w), _p(gx), B, rows_in, geom.rows_out, S, cin_p, cout_p,
-                  int(geom.dummy_row_grad), dt, st)
-            _count(2 if geom.dummy_row_grad else 1)
-            if cin_p != cin:
-                gx = gx[..., :cin]
-            if gx.dtype != ctx.xdtype:
-                gx = gx.to(ctx.xdtype)
-        return gx, gw, gb, None, None, None
-
-
-class PoolFn(torch.autograd.Function):
-    """y[b] = P . x[b] with P in CSR (models.py:127,148); backward uses the CSR of P^T.  ``transposed=True`` applies
-    P^T in the forward (and P in the backward): the inverse gather when P is a permutation."""
-
-    @staticmethod
-    def forward(ctx, x, pm, transposed=False):
-        _cuda(x)
-        x = x.contiguous()
-        B, rows, C = x.shape
-        ctx.pm, ctx.transposed = pm, bool(transposed)
-        return PoolFn._apply(x, pm, ctx.transposed, B, rows, C)
-
-    @staticmethod
-    def _apply(x, pm, transposed, B, rows, C):
-        rows_in, rows_out = (pm.rows_out, pm.rows_in) if transposed else (pm.rows_in, pm.rows_out)
-        if rows != rows_in:
-            raise ValueError(f"pool expects {rows_in} rows, got {rows}")
-        rowptr, colidx, vals = (pm.t_rowptr, pm.t_colidx, pm.t_vals) if transposed else (pm.rowptr, pm.colidx, pm.vals)
-        y = torch.empty((B, rows_out, C), dtype=x.dtype, device=x.device)
-        name = f"pool_spmm{'_bwd' if transposed else ''}[{rows_in}>{rows_out}x{C}]"
-        _call(name, _pool_meta(B, pm, C, x.element_size(), transposed), lib.shb_pool_spmm, _p(x), _p(rowptr), _p(colidx),
-              _p(vals), _p(y), B, rows_in, rows_out, C, _dt(x), _stream())
-        _count()
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        gy = gy.contiguous()
-        B, rows, C = gy.shape
-        return PoolFn._apply(gy, ctx.pm, not ctx.transposed, B, rows, C), None, None
 
 
 class L1LossFn(torch.autograd.Function):
@@ -542,15 +393,19 @@ class LinearShadowFn(torch.autograd.Function):
 
 
 def spiral_conv(x, weight, bias, geom, activation="elu", compute_dtype=None):
-    """compute_dtype: storage/operand dtype of this layer (default: x.dtype); a differing input is cast (and, in
-    bf16 mode, channel-padded) by one fused kernel."""
+    """Stand-alone SpiralConv on a (B, V+1, C) tensor (see slab.conv_rows)."""
+    from . import slab
+
     if activation not in ACT_ENUM:
         raise NotImplementedError(activation)
-    return SpiralConvFn.apply(x, weight, bias, geom, ACT_ENUM[activation], compute_dtype)
+    return slab.conv_rows(x, weight, bias, geom, activation, compute_dtype)
 
 
 def pool(x, pm):
-    return PoolFn.apply(x, pm)
+    """Stand-alone Pool on a (B, rows, C) tensor (see slab.pool_rows)."""
+    from . import slab
+
+    return slab.pool_rows(x, pm)
 
 
 def l1_loss(a, b):

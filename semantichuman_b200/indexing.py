@@ -1,8 +1,7 @@
 """Host-side index layer: spiral tables, inverse-spiral tables, CSR forms of the D/U sampling matrices.
 
 Everything here runs once at model construction (setup time), through the host entry points of libshb200
-(shb_build_inverse_spiral_csr / _by_slot, shb_dense_to_csr, shb_csr_transpose), and leaves int32 tables resident on
-the device.  Reference contracts: spirals as built by utils_spiral.py:45-95 and cast at main.py:203
+(shb_build_inverse_spiral_csr, shb_dense_to_csr, shb_csr_transpose), and leaves int32 tables resident on the device.  Reference contracts: spirals as built by utils_spiral.py:45-95 and cast at main.py:203
 ((1, V+1, S) int64, -1 == dummy vertex); D/U as padded at main.py:183-205 (dense (1, Vout+1, Vin+1) fp32).
 """
 import numpy as np
@@ -42,27 +41,6 @@ def build_inverse_spiral_csr(table, rows_in):
     check(lib.shb_build_inverse_spiral_csr(table.ctypes.data, rows_out, S, rows_in, rowptr.ctypes.data,
                                            slots.ctypes.data), "shb_build_inverse_spiral_csr")
     return rowptr, slots
-
-
-def build_inverse_spiral_by_slot(table, rows_in):
-    """(keyptr (rows_in*S+1), rows (rows_out*S)) host int32; key = u*S+s."""
-    table = _i32(table)
-    rows_out, S = table.shape
-    keyptr = np.empty(rows_in * S + 1, np.int32)
-    rows = np.empty(rows_out * S, np.int32)
-    check(lib.shb_build_inverse_spiral_by_slot(table.ctypes.data, rows_out, S, rows_in, keyptr.ctypes.data,
-                                               rows.ctypes.data), "shb_build_inverse_spiral_by_slot")
-    return keyptr, rows
-
-
-def build_inverse_spiral_quads(keyptr, rows, rows_in, S):
-    """(rows_in, S, 4) host uint16: first four entries of every (u,s) key inline; 0xFFFF none; [3] == 0xFFFE -> 5+ entries
-    (entries 3.. continue in the CSR)."""
-    keyptr, rows = _i32(keyptr), _i32(rows)
-    quads = np.empty((rows_in, S, 4), np.uint16)
-    check(lib.shb_build_inverse_spiral_quads(keyptr.ctypes.data, rows.ctypes.data, rows_in, S, quads.ctypes.data),
-          "shb_build_inverse_spiral_quads")
-    return quads
 
 
 def dense_to_csr(dense):
@@ -113,49 +91,97 @@ def locality_order(table):
 
 
 class SpiralGeometry:
-    """Device-resident index tables for one SpiralConv call shape.
+    """Entry lists of one SpiralConv call shape, resident on the device (the kernels' view of a spiral table).
 
-    table    (rows_out, S) int32: source row of x for output row j, slot s (already -1 -> rows_in-1).
-    keyptr / inv_rows: the (u, s)-keyed inverse relation used by the input-gradient kernel.
-    rows_out < rows_in when the conv is fused with a selection down-pool (output rows = kept vertices + dummy).
+    table    (rows_out, S) int32: source row of x for output row j, slot s (already -1 -> rows_in-1); rows_out < rows_in
+             when the conv is fused with a selection down-pool (output rows = kept vertices + dummy).
+    forward : for every output row j the entries (table[j,s] << 5 | s); entries reading the source's dummy row are dropped
+              when that row is known to be zero (`src_dummy_zero`: its producer masked it).
+    backward: for every source row u the entries (j << 5 | s) with table[j,s] == u, ascending in (j, s) -- the inverse-
+              spiral CSR of SURVEY 8 a-8 (shb_build_inverse_spiral_csr), i.e. the fixed summation order of the input
+              gradient; rows whose gz is zero by the mask (`zero_last_row`) are dropped, and the dummy source row gets no
+              entries unless its gradient is wanted (`dummy_row_grad`).
     """
 
     def __init__(self, table, rows_in, device, zero_last_row=True, dummy_row_grad=True, src_dummy_zero=False):
         table = _i32(table)
         self.rows_out, self.S = int(table.shape[0]), int(table.shape[1])
         self.rows_in = int(rows_in)
-        self.zero_last_row = bool(zero_last_row)
-        self.dummy_row_grad = bool(dummy_row_grad)
-        # promise that the input's dummy row is all zeros (its producer masked it): its gathers are zero-filled
-        self.src_dummy_zero = bool(src_dummy_zero)
+        if self.S > 32:
+            raise ValueError("the kernels support spiral lengths up to 32")
+        if table.min() < 0 or table.max() >= rows_in:
+            raise ValueError("spiral index out of range")
+        self.zero_last_row, self.dummy_row_grad, self.src_dummy_zero = bool(zero_last_row), bool(dummy_row_grad), bool(src_dummy_zero)
         self.table_host = table
-        keyptr, rows = build_inverse_spiral_by_slot(table, self.rows_in)
         self.device = torch.device(device)
+        S, dummy = self.S, self.rows_in - 1
+        slots = np.tile(np.arange(S, dtype=np.int64), self.rows_out)
+        flat = table.reshape(-1).astype(np.int64)
+        # forward lists
+        keep = np.ones(flat.shape, bool) if not self.src_dummy_zero else flat != dummy
+        counts = keep.reshape(self.rows_out, S).sum(1)
+        self.ptr_f = self._dev(np.concatenate([[0], np.cumsum(counts)]))
+        self.ent_f = self._dev(((flat << 5) | slots)[keep])
+        # backward lists: the canonical inverse CSR (flat positions j*S+s, ascending per source row), then the dead
+        # entries taken out
+        rowptr, pos = build_inverse_spiral_csr(table, self.rows_in)
+        pos = pos.astype(np.int64)
+        src_of = np.repeat(np.arange(self.rows_in, dtype=np.int64), np.diff(rowptr))
+        jj, ss = pos // S, pos % S
+        live = np.ones(pos.shape, bool)
+        if self.zero_last_row:
+            live &= jj != self.rows_out - 1
+        if not self.dummy_row_grad:
+            live &= src_of != dummy
+        # A live dummy source row (the FC row under the first decoder conv) is referenced by every padded spiral entry:
+        # hundreds of entries in ONE list, i.e. one tile that a single CTA would grind through.  Its list is cut into
+        # sub-lists that run as ordinary tiles into a scratch tensor (one partial row each); a Pool row then adds the
+        # partials in order and applies the producer's activation derivative.
+        self.dummy_split = None
+        to_dummy = live & (src_of == dummy)
+        n_dummy = int(to_dummy.sum())
+        if self.dummy_row_grad and n_dummy > 4 * S:
+            live &= src_of != dummy
+            ents = (jj[to_dummy] << 5) | ss[to_dummy]
+            T = (n_dummy + 47) // 48
+            bounds = (np.arange(T + 1, dtype=np.int64) * n_dummy) // T
+            self.dummy_split = (T, self._dev(bounds), self._dev(ents), self._dev(np.array([0, T])), self._dev(np.arange(T)),
+                                torch.ones(T, dtype=torch.float32, device=self.device))
+        counts_b = np.bincount(src_of[live], minlength=self.rows_in)
+        self.ptr_b = self._dev(np.concatenate([[0], np.cumsum(counts_b)]))
+        self.ent_b = self._dev(((jj << 5) | ss)[live])
         self.table = torch.from_numpy(table).to(self.device)
-        self.keyptr = torch.from_numpy(keyptr).to(self.device)
-        self.inv_rows = torch.from_numpy(rows).to(self.device)
-        # uint16 rows: viewed as int16 for torch; None (-> CUDA-core dgrad) when row ids do not fit
-        self.inv_quads = None
-        if self.rows_out <= 0xFFFD:
-            q = build_inverse_spiral_quads(keyptr, rows, self.rows_in, self.S)
-            self.inv_quads = torch.from_numpy(q.view(np.int16)).to(self.device)
+        self.n_fwd_entries, self.n_bwd_entries = int(counts.sum()), int(counts_b.sum())
+
+    def _dev(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        if a.size and a.max() >= 2 ** 31:
+            raise ValueError("table too large for 32-bit entry lists")
+        if a.size == 0:
+            a = np.zeros(1, np.int64)
+        return torch.from_numpy(a.astype(np.int32)).to(self.device)
 
     @classmethod
     def from_spiral(cls, spiral_adj, device, **kw):
         table = normalise_spiral(spiral_adj)
         return cls(table, table.shape[0], device, **kw)
 
+    def _flags(self, kw):
+        f = dict(zero_last_row=self.zero_last_row, dummy_row_grad=self.dummy_row_grad, src_dummy_zero=self.src_dummy_zero)
+        f.update({k: bool(v) for k, v in kw.items()})
+        return f
+
     def restricted(self, out_rows, **kw):
-        """Geometry that evaluates only `out_rows` (ascending source-vertex ids, dummy last)."""
+        """Geometry that evaluates only `out_rows` (source-vertex ids, dummy last)."""
         out_rows = np.asarray(out_rows, dtype=np.int64)
-        return SpiralGeometry(self.table_host[out_rows], self.rows_in, self.device, **kw)
+        return SpiralGeometry(self.table_host[out_rows], self.rows_in, self.device, **self._flags(kw))
 
     def with_flags(self, **kw):
-        g = object.__new__(SpiralGeometry)
-        g.__dict__.update(self.__dict__)
-        for k, v in kw.items():
-            setattr(g, k, bool(v))
-        return g
+        """Same table, different promises about the dummy rows (the entry lists depend on them)."""
+        f = self._flags(kw)
+        if all(getattr(self, k) == v for k, v in f.items()):
+            return self
+        return SpiralGeometry(self.table_host, self.rows_in, self.device, **f)
 
 
 class PoolMatrix:

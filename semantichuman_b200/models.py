@@ -7,11 +7,12 @@ script (main.py:241-259) and editing script (demo.py / utils_SH.py:358-376) can 
 and load the reference's checkpoints.
 
 What is different underneath
-  * SpiralConv is ONE fused gather-GEMM kernel (+bias +activation +dummy-row mask); the gathered
-    (B*(V+1), S*Cin) matrix of models.py:42 is never materialised.
-  * The dense D/U ``torch.matmul`` of models.py:127,148 becomes a CSR SpMM; D matrices that are pure row
+  * Inside the trunks activations live batch-innermost in 128-sample slabs (slab.py): SpiralConv is ONE fused kernel that
+    moves the S neighbour slabs of an output vertex by TMA straight into tensor-core operands (+bias +activation
+    +dummy-row mask); the gathered (B*(V+1), S*Cin) matrix of models.py:42 is never materialised.
+  * The dense D/U ``torch.matmul`` of models.py:127,148 becomes a CSR sum of whole slabs; D matrices that are pure row
     selections (mesh_sampling.py:214-227) are folded into the preceding conv, which then only evaluates the kept
-    vertices (bit-identical, half the work).
+    vertices (half the work).
   * Index tables are built once per level at construction; ``S[i].repeat(B,1,1)`` (models.py:122) is never formed.
   * No CPU path: CPU tensors raise.
 """
@@ -149,7 +150,6 @@ class _SpiralTrunk(nn.Module):
         # row-permuted on the way in and back on the way out, and the last level keeps the caller's order (FC layout).
         self._perm = self._level_orders(tables, n_levels) if reorder else None
         sel_rows = [pm.selection_cols if pm.is_selection else None for pm in self._pD]
-        self._io_perm = None
         if self._perm is not None:
             full = [np.concatenate([q, [len(q)]]) for q in self._perm]           # + dummy
             pos = []
@@ -161,12 +161,11 @@ class _SpiralTrunk(nn.Module):
             sel_rows = [None if sel_rows[i] is None else pos[i][sel_rows[i][full[i + 1]]] for i in range(n_levels)]
             self._pD = [self._pD[i].permuted(full[i + 1], full[i]) for i in range(n_levels)]
             self._pU = [self._pU[i].permuted(full[i], full[i + 1]) for i in range(n_levels)]
-            self._io_perm = PoolMatrix.from_permutation(full[0], dev)
         self._perm_dev = None if self._perm is None else torch.as_tensor(full[0], dtype=torch.int32, device=dev)
         # a pool keeps the dummy row zero only if its last row is exactly e_dummy (main.py:190-191 builds it that way)
         d_ok = [pm.dummy_preserving for pm in self._pD]
         u_ok = [pm.dummy_preserving for pm in self._pU]
-        geoms = [slab.SlabGeometry(tables[i], tables[i].shape[0], dev, dummy_row_grad=False) for i in range(n_levels)]
+        geoms = [SpiralGeometry(tables[i], tables[i].shape[0], dev, dummy_row_grad=False) for i in range(n_levels)]
         # encoder plan: (conv index, geometry, pool-after or None)
         self._enc_plan = []
         for j, lvl in enumerate(self._enc_lvl):

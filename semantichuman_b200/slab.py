@@ -21,6 +21,9 @@ import torch
 from . import functions as fn
 from ._capi import ACT_ENUM, BF16, F32, lib
 from .functions import _call, _count, _cuda, _p, _stream
+from .indexing import SpiralGeometry
+
+SlabGeometry = SpiralGeometry  # the kernels' geometry class (kept under its first name for the tests and scripts)
 
 CHUNK = 128
 
@@ -61,89 +64,6 @@ class Slab:
     @property
     def esize_bytes(self):
         return 2 * self.planes
-
-
-class SlabGeometry:
-    """Entry lists of one SpiralConv call shape, resident on the device.
-
-    forward : for every output row j the entries (table[j,s] << 5 | s); entries reading the source's dummy row are dropped
-              when that row is known to be zero.
-    backward: for every source row u the entries (j << 5 | s) with table[j,s] == u, ascending in (j, s) -- the fixed
-              summation order of the input gradient; rows whose gz is zero by the mask are dropped, and the
-              dummy source row gets no entries unless its gradient is wanted.
-    """
-
-    def __init__(self, table, rows_in, device, zero_last_row=True, dummy_row_grad=True, src_dummy_zero=False):
-        table = np.ascontiguousarray(table, dtype=np.int32)
-        self.rows_out, self.S = int(table.shape[0]), int(table.shape[1])
-        self.rows_in = int(rows_in)
-        if self.S > 32:
-            raise ValueError("slab kernels support spiral lengths up to 32")
-        if table.min() < 0 or table.max() >= rows_in:
-            raise ValueError("spiral index out of range")
-        self.zero_last_row, self.dummy_row_grad, self.src_dummy_zero = bool(zero_last_row), bool(dummy_row_grad), bool(src_dummy_zero)
-        self.table_host = table
-        self.device = torch.device(device)
-        S = self.S
-        slots = np.tile(np.arange(S, dtype=np.int64), self.rows_out)
-        flat = table.reshape(-1).astype(np.int64)
-        # forward lists
-        keep = np.ones(flat.shape, bool) if not self.src_dummy_zero else flat != self.rows_in - 1
-        counts = keep.reshape(self.rows_out, S).sum(1)
-        self.ptr_f = self._dev(np.concatenate([[0], np.cumsum(counts)]))
-        self.ent_f = self._dev(((flat << 5) | slots)[keep])
-        # backward lists: stable sort of the flattened table by source row == ascending (j, s) within a row
-        j_of = np.repeat(np.arange(self.rows_out, dtype=np.int64), S)
-        live = np.ones(flat.shape, bool)
-        if self.zero_last_row:
-            live &= j_of != self.rows_out - 1
-        if not self.dummy_row_grad:
-            live &= flat != self.rows_in - 1
-        # A live dummy source row (the FC row under the first decoder conv) is referenced by every padded spiral entry:
-        # hundreds of entries in ONE list, i.e. one tile that a single CTA would grind through.  Its list is cut into
-        # sub-lists that run as ordinary tiles into a scratch tensor (one partial row each); a Pool row then adds the
-        # partials in order and applies the producer's activation derivative.
-        self.dummy_split = None
-        to_dummy = live & (flat == self.rows_in - 1)
-        n_dummy = int(to_dummy.sum())
-        if self.dummy_row_grad and n_dummy > 4 * S:
-            live &= flat != self.rows_in - 1
-            ents = ((j_of[to_dummy] << 5) | slots[to_dummy])  # ascending (j, s): the fixed summation order
-            T = (n_dummy + 47) // 48
-            bounds = (np.arange(T + 1, dtype=np.int64) * n_dummy) // T
-            self.dummy_split = (T, self._dev(bounds), self._dev(ents), self._dev(np.array([0, T])), self._dev(np.arange(T)),
-                                torch.ones(T, dtype=torch.float32, device=self.device))
-        order = np.argsort(flat[live], kind="stable")
-        counts_b = np.bincount(flat[live], minlength=self.rows_in)
-        self.ptr_b = self._dev(np.concatenate([[0], np.cumsum(counts_b)]))
-        self.ent_b = self._dev(((j_of[live] << 5) | slots[live])[order])
-        self.table = torch.from_numpy(table).to(self.device)
-        self.n_fwd_entries, self.n_bwd_entries = int(counts.sum()), int(counts_b.sum())
-
-    def _dev(self, a):
-        a = np.ascontiguousarray(a, dtype=np.int64)
-        if a.size and a.max() >= 2 ** 31:
-            raise ValueError("table too large for 32-bit entry lists")
-        if a.size == 0:
-            a = np.zeros(1, np.int64)
-        return torch.from_numpy(a.astype(np.int32)).to(self.device)
-
-    def _flags(self, kw):
-        f = dict(zero_last_row=self.zero_last_row, dummy_row_grad=self.dummy_row_grad, src_dummy_zero=self.src_dummy_zero)
-        f.update({k: bool(v) for k, v in kw.items()})
-        return f
-
-    def restricted(self, out_rows, **kw):
-        """Geometry that evaluates only `out_rows` (source-vertex ids, dummy last)."""
-        out_rows = np.asarray(out_rows, dtype=np.int64)
-        return SlabGeometry(self.table_host[out_rows], self.rows_in, self.device, **self._flags(kw))
-
-    def with_flags(self, **kw):
-        """Same table, different promises about the dummy rows (the entry lists depend on them)."""
-        f = self._flags(kw)
-        if all(getattr(self, k) == v for k, v in f.items()):
-            return self
-        return SlabGeometry(self.table_host, self.rows_in, self.device, **f)
 
 
 def _dt(t):
@@ -342,3 +262,28 @@ def spiral_conv(s, weight, bias, geom, activation="elu", want_gx=True):
     t = SlabConvFn.apply(s.t, weight, bias, geom, act, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked), want_gx)
     cout = weight.shape[0]
     return Slab(t, geom.rows_out, s.B, cout, pad_channels(cout), s.planes, act, geom.zero_last_row)
+
+
+def conv_rows(x, weight, bias, geom, activation="elu", compute_dtype=None):
+    """The stand-alone SpiralConv call (models.py:34-53) on a caller-layout tensor: rows -> slabs, the fused kernel, slabs ->
+    rows.  compute_dtype float32 (default for float32 input): hi/lo split operands, 1e-4 parity; bfloat16: 2e-2."""
+    cdt = x.dtype if compute_dtype is None else compute_dtype
+    if cdt not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"semantichuman_b200 supports float32 and bfloat16 activations, got {cdt}")
+    _cuda(x, weight, bias)
+    if x.dim() != 3:
+        raise ValueError("x must be (B, V+1, C)")
+    if x.shape[1] != geom.rows_in or weight.shape[1] != geom.S * x.shape[2]:
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)}, weight {tuple(weight.shape)}, geometry rows_in={geom.rows_in} "
+                         f"S={geom.S}")
+    s = from_rows(x, None, 1 if cdt == torch.bfloat16 else 2)
+    return to_rows(spiral_conv(s, weight, bias, geom, activation), None, cdt)
+
+
+def pool_rows(x, pm):
+    """The stand-alone Pool call (torch.matmul(D|U, x), models.py:127,148) on a caller-layout tensor."""
+    _cuda(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"semantichuman_b200 supports float32 and bfloat16 activations, got {x.dtype}")
+    s = from_rows(x, None, 1 if x.dtype == torch.bfloat16 else 2)
+    return to_rows(pool(s, pm), None, x.dtype)

@@ -1,4 +1,4 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU port of the reference's training step) prints one
+"""bench.py contract checks that need no GPU: the reference arm (the reference's own model on the host cores) prints one
 JSON line with the keys the driver reads, and under a multi-rank launch only rank 0 works."""
 import json
 import os
@@ -15,7 +15,7 @@ def _run(env_extra, *args):
 
 
 def test_reference_arm_json_line():
-    r = _run({}, "--impl", "reference", "--steps", "1", "--warmup", "1")
+    r = _run({}, "--impl", "reference", "--steps", "1", "--warmup", "1", "--batch", "8")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -25,7 +25,10 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and abs(d["value"] - d["e2e"]["value"]) < 1e-9
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "batch" in cb["sample"]
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "models.py"))  # the reference's own file, when staged
+    assert cb["kind"] == ("reference" if staged else "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert "batch 8" in cb["sample"] and d["config"]["batch_per_gpu"] == 8  # the config states the batch that ran
+    assert "semantichuman_b200" not in r.stderr  # the arm never loads the product package
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
 
 

@@ -28,14 +28,21 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in include/shb200.h but not exported by libshb200.so"
         assert n in _capi.SIGNATURES, f"{n} has no ctypes signature in _capi.py"
     assert sorted(_capi.SIGNATURES) == names
-    assert _capi.lib.shb_abi_version() == 1
+    assert _capi.lib.shb_abi_version() == 2
     assert b"invalid argument" in _capi.lib.shb_error_string(-1)
 
 
 def test_argument_errors_are_reported_not_crashed():
     # null pointers are rejected before any launch (no GPU needed)
-    assert _capi.lib.shb_spiralconv_fwd(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, None) == -1
-    assert _capi.lib.shb_pool_spmm(None, None, None, None, None, 1, 1, 1, 1, 0, None) == -1
+    assert _capi.lib.shb_slab_conv(None, None, None, None, None, None, None, 1, 1, 9, 16, 16, 16, 0, 0, 0, 1, None) == -1
+    assert _capi.lib.shb_slab_pool(None, None, None, None, None, None, 1, 1, 16, 0, 0, 1, None) == -1
+    assert _capi.lib.shb_slab_wgrad(None, None, None, None, None, None, 0, 1, 1, 9, 16, 16, 16, 16, 0, 1, None) == -1
+    assert _capi.lib.shb_adam_step(0, None, None, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
+    # shapes the kernels cannot take are refused loudly (no silent fallback): spiral length, channel counts, planes
+    assert _capi.lib.shb_slab_conv_supported(33, 16, 16, 1) == 0 and _capi.lib.shb_slab_conv_supported(9, 24, 16, 1) == 0
+    assert _capi.lib.shb_slab_conv_supported(14, 32, 16, 1) == 1 and _capi.lib.shb_slab_conv_supported(8, 128, 64, 2) == 1
+    assert _capi.lib.shb_slab_wgrad_supported(8, 128, 64, 2) == 1 and _capi.lib.shb_slab_wgrad_supported(8, 48, 64, 1) == 0
+    assert _capi.lib.shb_slab_tensor_bytes(6891, 256, 32, 1) == 6891 * 2 * 32 * 256
     with pytest.raises(RuntimeError):
         _capi.check(-3, "x")
 
@@ -51,23 +58,44 @@ def test_inverse_spiral_tables_bit_exact(tag, cfg):
         rp, sl = indexing.build_inverse_spiral_csr(t, n)
         rp2, sl2 = so.inverse_spiral_csr(t, n)
         assert rp.dtype == np.int32 and (rp == rp2).all() and (sl == sl2).all()
-        kp, rows = indexing.build_inverse_spiral_by_slot(t, n)
-        kp2, rows2 = so.inverse_spiral_by_slot(t, n)
-        assert (kp == kp2).all() and (rows == rows2).all()
         # every slot appears exactly once, and the relation inverts the table
         assert sorted(sl.tolist()) == list(range(t.size))
         u = np.repeat(np.arange(n), np.diff(rp))
         assert (t.reshape(-1)[sl] == u).all()
 
 
-def test_inverse_tables_for_restricted_rows():
+def test_entry_lists_of_the_kernels():
+    """SpiralGeometry (what the slab kernels consume): forward lists = the table itself, backward lists = the inverse-spiral
+    CSR in ascending (j, s) order with masked rows dropped; restricted output rows; dummy-row handling."""
     h = Hierarchy("small")
     t = indexing.normalise_spiral(h.spirals()[0])
-    keep = np.concatenate([h.raw["D0_col"], [t.shape[0] - 1]])
-    sub = t[keep]
-    kp, rows = indexing.build_inverse_spiral_by_slot(sub, t.shape[0])
-    kp2, rows2 = so.inverse_spiral_by_slot(sub, t.shape[0])
-    assert (kp == kp2).all() and (rows == rows2).all()
+    n, S = t.shape
+    g = indexing.SpiralGeometry(t, n, "cpu", zero_last_row=False, dummy_row_grad=True)
+    assert g.dummy_split is None or g.dummy_split[0] >= 1
+    pf, ef = g.ptr_f.numpy(), g.ent_f.numpy()
+    assert (pf == np.arange(n + 1) * S).all() and ((ef >> 5) == t.reshape(-1)).all() and ((ef & 31) == np.tile(np.arange(S), n)).all()
+    # backward: together with the split-off dummy list, exactly the canonical inverse CSR (stable counting sort)
+    rp, sl = so.inverse_spiral_csr(t, n)
+    pb, eb = g.ptr_b.numpy(), g.ent_b.numpy()[: g.n_bwd_entries]
+    pos = (eb >> 5).astype(np.int64) * S + (eb & 31)
+    if g.dummy_split is None:
+        assert (pb == rp).all() and (pos == sl).all()
+    else:
+        T, bounds, ents = g.dummy_split[0], g.dummy_split[1].numpy(), g.dummy_split[2].numpy()
+        assert (pb[:-1] == rp[:-1]).all() and (pos == sl[: rp[n - 1]]).all()
+        dpos = (ents >> 5).astype(np.int64) * S + (ents & 31)
+        assert (dpos == sl[rp[n - 1]:]).all() and bounds[0] == 0 and bounds[-1] == len(ents) and len(bounds) == T + 1
+    # masked output row and dead dummy source row are dropped; forward entries on a known-zero dummy row too
+    g2 = indexing.SpiralGeometry(t, n, "cpu", zero_last_row=True, dummy_row_grad=False, src_dummy_zero=True)
+    assert g2.n_fwd_entries == int((t != n - 1).sum())
+    e2 = g2.ent_b.numpy()[: g2.n_bwd_entries]
+    assert ((e2 >> 5) != n - 1).all() and g2.ptr_b.numpy()[-1] == g2.ptr_b.numpy()[-2]
+    # a conv fused with a selection pool evaluates only the kept rows
+    keep = np.concatenate([h.raw["D0_col"], [n - 1]])
+    g3 = g2.restricted(keep)
+    assert g3.rows_out == len(keep) and g3.rows_in == n and (g3.table_host == t[keep]).all()
+    with pytest.raises(ValueError):
+        indexing.SpiralGeometry(np.zeros((4, 33), np.int32), 4, "cpu")
 
 
 def test_batch_varying_spiral_rejected():
@@ -136,28 +164,6 @@ def test_parameter_order_matches_reference_state_dict():
         assert groups[0] == "conv" and groups[-1] == "dconv", groups
         inner = [p for p in pos if p is not None]
         assert inner == sorted(inner), groups
-
-
-def test_inverse_quads_table():
-    """quads[u,s,0..3]: first four entries of key (u,s) inline as uint16, 0xFFFF none, [3]==0xFFFE -> 5+ entries."""
-    h = Hierarchy("2222")
-    t = indexing.normalise_spiral(h.spirals()[0])
-    n, S = t.shape
-    kp, rows = indexing.build_inverse_spiral_by_slot(t, n)
-    q = indexing.build_inverse_spiral_quads(kp, rows, n, S)
-    assert q.shape == (n, S, 4) and q.dtype == np.uint16
-    cnt = np.diff(kp).reshape(n, S)
-    for (u, s) in [(0, 0), (17, 1), (n - 2, 3), (414, 0), (n - 1, 2)]:
-        e0, c = kp[u * S + s], cnt[u, s]
-        want = [rows[e0 + i] if i < c else 0xFFFF for i in range(4)]
-        if c > 4:
-            want[3] = 0xFFFE
-        assert q[u, s].tolist() == want
-    # vectorised check of the whole table
-    first = np.where(cnt > 0, rows[np.minimum(kp[:-1], len(rows) - 1)].reshape(n, S), 0xFFFF)
-    assert (q[..., 0] == first).all()
-    assert ((q[..., 3] == 0xFFFE) == (cnt > 4)).all()
-    assert ((q[..., 1] == 0xFFFF) == (cnt < 2)).all()
 
 
 def test_locality_order_and_permuted_pool_matrices():
