@@ -55,12 +55,13 @@ class GradSync:
             members = [(n, p) for n, p in named if _bucket_of(n) == b]
             if not members:
                 continue
-            total = sum(p.numel() for _, p in members)
+            # every member starts on a 16-byte boundary (the optimizer kernel moves float4s); the padding stays zero
+            total = sum((p.numel() + 3) // 4 * 4 for _, p in members)
             flat = torch.zeros(total, dtype=members[0][1].dtype, device=members[0][1].device)
             off = 0
             for _, p in members:
                 p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
-                off += p.numel()
+                off += (p.numel() + 3) // 4 * 4
             bucket = {"flat": flat, "params": [p for _, p in members], "pending": 0, "work": None}
             self.buckets.append(bucket)
             for _, p in members:
