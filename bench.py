@@ -103,6 +103,7 @@ def base_config(args, world):
                         "N=8 is configs[3]'s global batch 2048)",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "params": 28559811, "optimizer": "Adam(lr=1e-3, wd=5e-5)", "parallelism": f"dp{world}",
+            "comm_sms": (getattr(args, "comm_sms", 0) if world > 1 else 0),
             "cuda_graph": bool(not getattr(args, "no_graph", False)),
             "cache": f"{N_INPUT_BATCHES} distinct input batches rotated; per-step working set (activations + 114 MB "
                      "weights + Adam state) exceeds the 126 MB L2"}
@@ -227,7 +228,9 @@ def run_own(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from semantichuman_b200.dp import init_data_parallel
+
+        init_data_parallel(dev, comm_sms=args.comm_sms)
     dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
 
     h = Hierarchy("2222")
@@ -237,7 +240,7 @@ def run_own(args):
     fill_deterministic_(model, seed=2)
     model = model.to(dev).set_compute_dtype(dtype)
     use_graph = not args.no_graph  # whole step (incl. the gradient all-reduces at N>1) replayed as one CUDA graph per rank
-    step = TrainStep(model, graph=use_graph)
+    step = TrainStep(model, graph=use_graph, comm_sms=args.comm_sms if world > 1 else 0)
     B = args.batch
     host = [synthetic_meshes(h.verts0, B, seed=1000 * rank + i).pin_memory() for i in range(N_INPUT_BATCHES)]
     resident = [x.to(dev) for x in host]
@@ -410,6 +413,9 @@ def main():
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--comm-sms", type=int, default=24,
+                    help="N>1: CTAs NCCL may use = SMs the persistent kernels leave free while a gradient bucket is in flight; "
+                         "0 = NCCL defaults, no reservation")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the in-run cpu_baseline sample (10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

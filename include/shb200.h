@@ -42,6 +42,10 @@ enum { SHB_F32 = 0, SHB_BF16 = 1 };
 enum { SHB_E_ARG = -1, SHB_E_DTYPE = -2, SHB_E_SHAPE = -3, SHB_E_WORKSPACE = -4, SHB_E_UNSUPPORTED = -5 };
 
 int shb_abi_version(void);
+/* SMs the persistent kernels (SpiralConv forward / input gradient / weight gradient: one CTA per SM) launch on, 1..148
+ * (default 148).  A data-parallel step sets 148 - k so that the NCCL all-reduce of the gradient buckets, limited to k CTAs,
+ * overlaps the rest of the backward instead of queueing behind it.  Process-wide setting; not a per-call argument. */
+int shb_set_persistent_sms(int n);
 const char* shb_error_string(int code);
 
 /* ------------------------------------------------------------------ host-side index construction (CPU) */

@@ -14,6 +14,7 @@ c_int, c_i64, c_size, c_vp, c_float = ctypes.c_int, ctypes.c_int64, ctypes.c_siz
 # name -> (restype, argtypes); one entry per declaration in include/shb200.h
 SIGNATURES = {
     "shb_abi_version": (c_int, []),
+    "shb_set_persistent_sms": (c_int, [c_int]),
     "shb_error_string": (ctypes.c_char_p, [c_int]),
     "shb_build_inverse_spiral_csr": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "shb_dense_to_csr": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),

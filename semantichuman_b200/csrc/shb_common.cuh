@@ -10,6 +10,11 @@ namespace shb {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+// SMs the persistent (one CTA per SM, all shared memory) kernels may occupy.  Data-parallel runs lower it by a few SMs so
+// that NCCL's all-reduce CTAs can run BESIDE the backward kernels instead of waiting for one of them to retire
+// (shb_set_persistent_sms; default: all 148).
+int persistent_sms();
+
 #define SHB_LAUNCH_CHECK()                           \
   do {                                               \
     cudaError_t e__ = cudaPeekAtLastError();         \

@@ -4,7 +4,18 @@
 
 #include "shb_common.cuh"
 
+namespace shb {
+static int g_persistent_sms = kNumSMs;
+int persistent_sms() { return g_persistent_sms; }
+}  // namespace shb
+
 extern "C" {
+
+int shb_set_persistent_sms(int n) {
+  if (n < 1 || n > shb::kNumSMs) return SHB_E_ARG;
+  shb::g_persistent_sms = n;
+  return 0;
+}
 
 int shb_abi_version(void) { return SHB_ABI_VERSION; }
 

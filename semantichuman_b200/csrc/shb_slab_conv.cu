@@ -506,7 +506,7 @@ static int slab_conv_launch(const SlabConvParams& p, size_t smem, cudaStream_t s
     if (e != cudaSuccess) return (int)e;
     attr_set[p.P] = true;
   }
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const int grid = p.num_tiles < persistent_sms() ? p.num_tiles : persistent_sms();
   const int threads = SC_LEAD_WARPS * 32 + 128 * p.EG;
   const int nk = p.CS >= 16 ? p.CS / 16 : 1;  // MMAs (K = 16) per slab and plane
 #define SHB_SC_GO(PL, K) slab_conv_kernel<PL, K><<<grid, threads, smem, st>>>(p)

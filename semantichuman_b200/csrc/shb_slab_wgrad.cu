@@ -367,7 +367,7 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
   p.num_tiles = rows_eff * p.NB;
   float* partial = (float*)workspace;
   float* bias_partial = partial + (size_t)kNumSMs * plan.G * 128 * NPt;
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const int grid = p.num_tiles < persistent_sms() ? p.num_tiles : persistent_sms();
   if (grid > 0) {
     for (int n0 = 0; n0 < NPt; n0 += plan.N) {
       if (n0 >= Cout_p) break;

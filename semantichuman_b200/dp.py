@@ -26,6 +26,22 @@ def shard_batch(global_batch, rank, world):
 N_BUCKETS = 4
 
 
+def init_data_parallel(device, comm_sms=24):
+    """Create the NCCL process group of a data-parallel run with NCCL limited to `comm_sms` CTAs (0: NCCL's defaults).
+    GradSync(model, comm_sms=...) then keeps that many SMs free of the persistent SpiralConv kernels WHILE a large gradient
+    bucket is in flight (measured on 2 B200: with all 148 SMs -- and all of their shared memory -- held by one-CTA-per-SM
+    kernels the all-reduce cannot start beside them and its 0.3 ms stay exposed; reserving SMs for the whole step costs more
+    than it hides)."""
+    if comm_sms and comm_sms > 0:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(comm_sms)
+        opts.config.min_ctas = min(int(comm_sms), 4)
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=device)
+    return dist.get_world_size()
+
+
 def _bucket_of(name):
     """Backward order: decoder convs -> decoder-side latent layers -> encoder-side latent layers -> encoder convs."""
     if name.startswith("dconv."):
@@ -40,8 +56,10 @@ def _bucket_of(name):
 class GradSync:
     """Flat-bucket gradient all-reduce overlapped with backward."""
 
-    def __init__(self, model, process_group=None):
+    def __init__(self, model, process_group=None, comm_sms=0):
         self.pg = process_group
+        self.comm_sms = int(comm_sms)   # SMs kept free of persistent kernels while a large bucket is being reduced
+        self._capped = False
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         # NCCL averages inside the collective; gloo (CPU tests of this logic) has no AVG: sum, then scale in finish()
         self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
@@ -74,7 +92,15 @@ class GradSync:
             if bucket["pending"] == 0 and self.world > 1:
                 op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
                 bucket["work"] = dist.all_reduce(bucket["flat"], op=op, group=self.pg, async_op=True)
+                if self.comm_sms > 0 and bucket["flat"].numel() >= (1 << 20) and not self._capped:
+                    self._cap(True)  # kernels enqueued from here to finish() leave room for NCCL's CTAs
         return hook
+
+    def _cap(self, on):
+        from ._capi import check, lib
+
+        check(lib.shb_set_persistent_sms(148 - self.comm_sms if on else 148), "shb_set_persistent_sms")
+        self._capped = on
 
     def reset(self):
         """Call before each backward (instead of optimizer.zero_grad(set_to_none=True), which would drop the views)."""
@@ -89,6 +115,8 @@ class GradSync:
 
     def finish(self):
         """Join the outstanding all-reduces (the current stream waits; the host does not block)."""
+        if self._capped:
+            self._cap(False)
         for b in self.buckets:
             if b["work"] is not None:
                 b["work"].wait()

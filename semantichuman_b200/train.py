@@ -17,9 +17,9 @@ from .optim import Adam
 
 
 class TrainStep:
-    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False):
+    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False, comm_sms=0):
         self.model = model
-        self.sync = GradSync(model)
+        self.sync = GradSync(model, comm_sms=comm_sms)
         self.graph_enabled = bool(graph)
         # own multi-tensor Adam (device-side step count: replayable; writes the bf16 weight shadows in the same pass)
         shadows = model.shadow_map() if hasattr(model, "shadow_map") else None
