@@ -86,7 +86,8 @@ def test_two_rank_average_equals_full_batch():
         for a, b in zip(grads, full):
             assert torch.allclose(torch.from_numpy(a), b, atol=1e-6, rtol=1e-5)
         assert order[:4] == [0, 1, 2, 3]  # decoder convs -> fc_latent_dec -> fc_latent_enc -> encoder convs
-        assert nbytes == 4 * sum(p.numel() for p in model.parameters())
+        # every member starts on a 16-byte boundary inside its flat bucket (the optimizer kernel moves float4s)
+        assert nbytes == 4 * sum((p.numel() + 3) // 4 * 4 for p in model.parameters())
     for a, b in zip(got[0][1], got[1][1]):
         assert (a == b).all()
 
