@@ -129,10 +129,23 @@ class PartNormLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, measure, P, Q, relative):
-        _cuda(z, measure, P, Q)
+        _cuda(z, measure)
         z = z.float().contiguous()
         measure = measure.float().contiguous()
+        if z.dim() != 3 or measure.dim() != 2 or measure.shape[0] != z.shape[0]:
+            raise ValueError("partnorm_loss expects z (B, n_parts, L) and measure (B, n_measure)")
         B, n_parts, L = z.shape
+        # the kernel reads P / Q as int32 device arrays and writes gz rows P[i]: validate on the host (small index lists)
+        P = torch.as_tensor(P).detach().to("cpu", torch.int64).reshape(-1)
+        Q = torch.as_tensor(Q).detach().to("cpu", torch.int64).reshape(-1)
+        if P.numel() == 0 or P.numel() != Q.numel():
+            raise ValueError("partnorm_loss: P and Q must be non-empty index lists of equal length")
+        if int(P.min()) < 0 or int(P.max()) >= n_parts or int(Q.min()) < 0 or int(Q.max()) >= measure.shape[1]:
+            raise ValueError("partnorm_loss: part / measure index out of range")
+        if P.unique().numel() != P.numel():
+            raise ValueError("partnorm_loss: a part may appear once in P (its gradient row is written once)")
+        P = P.to(torch.int32).to(z.device)
+        Q = Q.to(torch.int32).to(z.device)
         out = torch.empty((), dtype=torch.float32, device=z.device)
         gz = torch.empty_like(z)
         _call("partnorm_loss_fwd_bwd", {"bytes": 2.0 * z.numel() * 4}, lib.shb_partnorm_loss_fwd_bwd, _p(z), _p(measure),

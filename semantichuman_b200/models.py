@@ -321,10 +321,11 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
 
     def __init__(self, kps_index_list, vert_part_index_dict, filters_enc, filters_dec, latent_size, part_kps_latent_size,
                  sizes, spiral_sizes, spirals, D, U, device, VAE_flag=False, activation='elu', fuse_pool=True,
-                 reorder=True, grouped_heads=True):
+                 reorder=True, grouped_heads=True, skl_list=None):
         super().__init__()
-        self.newskl_list = DEFAULT_NEWSKL_LIST
-        self.kps_keep = [i for i in range(len(self.newskl_list) + 4) if i not in (3, 13, 14)]
+        # models.py:169,285 read cfg.CONSTANTS.newskl_list at call time (27 bones by default, 31 under the shipped yaml
+        # configs): pass `skl_list`, or assign `model.newskl_list` later -- kps_keep follows it
+        self.newskl_list = DEFAULT_NEWSKL_LIST if skl_list is None else [list(b) for b in skl_list]
         self.kps_index_list = kps_index_list
         self.vert_part_index_dict = vert_part_index_dict
         self.part_kps_latent_size = part_kps_latent_size
@@ -393,6 +394,10 @@ class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):
         x = torch.zeros_like(x).index_copy(1, self._re_index, x)
         x = torch.cat([x, dummy.to(x.dtype).expand(bsize, -1, -1)], dim=1)
         return self._decode_trunk(x)
+
+    @property
+    def kps_keep(self):
+        return [i for i in range(len(self.newskl_list) + 4) if i not in (3, 13, 14)]
 
     def kps2skl(self, kps_tmp):
         """models.py:284-304: keypoints -> (unit direction, length) per bone of ``newskl_list``."""

@@ -40,7 +40,7 @@ def test_hierarchy_matches_reference_fixture(tag):
         for l in range(1, len(verts)):  # main.py:161-167: nearest coarse vertex to the level-0 reference vertex
             refpts.append(np.argmin(euclidean_distances(verts[l], verts[0][refpts[0]]), axis=0).tolist())
         assert [r[0] for r in refpts] == h.refpts
-        tables, sizes = spr.generate_spirals([2, 2, 1, 1, 1], verts, faces, refpts, dilation=[2, 2, 1, 1, 1])
+        tables, sizes, _ = spr.generate_spirals([2, 2, 1, 1, 1], verts, faces, refpts, dilation=[2, 2, 1, 1, 1])
         assert sizes == h.spiral_sizes
         for l, t in enumerate(tables):
             assert np.array_equal(t[0].astype(np.int64), h.spirals_np[l])

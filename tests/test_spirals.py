@@ -17,7 +17,7 @@ def test_spirals_bit_exact(tag, cfg):
     steps, dil = CONFIGS[cfg]
     n = h.n_levels + 1
     verts = [h.level_verts(l) for l in range(n)]
-    tables, sizes = sp.generate_spirals(steps[:n], verts, h.faces, [[r] for r in h.refpts], dilation=dil[:n])
+    tables, sizes, _ = sp.generate_spirals(steps[:n], verts, h.faces, [[r] for r in h.refpts], dilation=dil[:n])
     assert sizes == h.spiral_sizes
     for l in range(n):
         assert tables[l].shape == (1, h.sizes[l] + 1, sizes[l]) and tables[l].dtype == np.float64
