@@ -9,8 +9,9 @@
 One step = forward + L1 loss + backward (+ gradient all-reduce when N>1) + Adam (main.py:262 hyper-parameters) over
 one batch of synthetic meshes; weights are deterministic random-init; per-GPU batch 256 (weak scaling: N=8 is
 BASELINE.json's global batch 2048).  Prints ONE JSON line on rank 0.  The headline is north_star's bf16 mode (bf16
-operands, fp32 accumulation and master weights, parity 2e-2); the exact-fp32 mode (parity 1e-4) is timed in the same
-run and reported under "other_mode".
+operands, fp32 accumulation and master weights, parity 2e-2); the fp32 mode (bf16 hi + lo operands on the same tensor-core
+kernels, parity 1e-4 -- the reference's own precision) is timed in the same run and reported under "other_mode"; run with
+--dtype fp32 to make it the headline line.
 """
 import argparse
 import json
@@ -350,6 +351,14 @@ def run_own(args):
                  "peak_source": peaks["source"] + " (sustained figures: kernel timed inside a long step)",
                  "arith_intensity_flop_per_byte": ai})
     kernels = sorted(((k, v["ms"] / args.steps) for k, v in per.items()), key=lambda kv: -kv[1])
+    families = {}
+    for k, v in kernels:
+        families[k.split("[")[0]] = round(families.get(k.split("[")[0], 0.0) + v, 4)
+    if args.kernels_out:
+        json.dump({k: {"ms_per_step": v, "launches_per_step": per[k]["launches"] / args.steps,
+                       "alg_bytes_per_launch": per[k]["bytes"] / max(per[k]["launches"], 1),
+                       "flops_per_launch": per[k]["flops"] / max(per[k]["launches"], 1)} for k, v in kernels},
+                  open(args.kernels_out, "w"), indent=1)
     step_flops = sum(v["flops"] for v in per.values()) / args.steps
     step_bytes = sum(v["bytes"] for v in per.values()) / args.steps
 
@@ -371,8 +380,9 @@ def run_own(args):
         oms = o0.elapsed_time(o1) / n_other
         other = {"dtype": "f32" if odt == torch.float32 else "bf16", "ms_per_step": oms, "value": B / (oms * 1e-3),
                  "unit": "meshes/s", "steps": n_other,
-                 "note": "exact-fp32 CUDA-core kernels, 1e-4 parity mode" if odt == torch.float32 else
-                         "bf16 tcgen05 kernels, 2e-2 parity mode"}
+                 "note": "fp32 mode: activations and weights as bf16 hi + lo, four tcgen05 products per term, fp32 accumulation; "
+                         "1e-4 parity (the reference's own precision)" if odt == torch.float32 else
+                         "bf16 mode: bf16 operands, fp32 accumulation and master weights; 2e-2 parity"}
         model.set_compute_dtype(dtype)
 
     cpu = None
@@ -395,6 +405,7 @@ def run_own(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "other_mode": other, "loss": last_loss, "loss_e2e_mean": seen / args.steps,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in kernels[:12]},
+            "kernel_families_ms_per_step": families,
             "algorithmic_per_step": {"gflop_convs_pools": step_flops / 1e9, "gbytes": step_bytes / 1e9}}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -409,13 +420,14 @@ def main():
     ap.add_argument("--impl", default="shb200", choices=["shb200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"],
                     help="bf16 (default): bf16 operands / fp32 accumulate on the tcgen05 kernels, north_star's 2e-2 mode; "
-                         "fp32: exact-fp32 CUDA-core kernels, the 1e-4 mode")
+                         "fp32: bf16 hi + lo operands (four products per term) on the same kernels, the 1e-4 mode")
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--comm-sms", type=int, default=24,
                     help="N>1: CTAs NCCL may use = SMs the persistent kernels leave free while a gradient bucket is in flight; "
                          "0 = NCCL defaults, no reservation")
+    ap.add_argument("--kernels-out", default=None, help="write the full per-kernel table of the instrumented pass here")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the in-run cpu_baseline sample (10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
