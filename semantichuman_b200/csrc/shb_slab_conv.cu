@@ -54,7 +54,7 @@ struct SlabConvParams {
 //   [0] producer wait-empty  [1] producer total   [2] MMA wait-full  [3] MMA wait-tmem  [4] MMA total
 //   [5] epilogue wait-accumulator (warp 2)  [6] epilogue total (warp 2)  [7] tiles
 #ifdef SHB_SLAB_TRACE
-__device__ long long g_slab_trace[kNumSMs * 16];
+__device__ long long g_slab_trace[2 * kNumSMs * 16];
 #define SC_T0(var) const long long var = clock64()
 #define SC_ACC(idx, t0) trace_acc[idx] += clock64() - (t0)
 #else
@@ -62,8 +62,12 @@ __device__ long long g_slab_trace[kNumSMs * 16];
 #define SC_ACC(idx, t0) do { } while (0)
 #endif
 
-template <int P, int NK>
-__global__ void __launch_bounds__(SC_MAX_THREADS, 1) slab_conv_kernel(const SlabConvParams p) {
+// DUAL: two CTAs per SM (half the shared memory and at most two epilogue groups each).  Every role of a CTA is a dependent
+// instruction chain that leaves its SM sub-partition idle most of the time (ncu: 0.3 issue slots / cycle, 17 % of the warp
+// slots); a sibling CTA fills those gaps.  Used whenever the weight image leaves room for a ring in half an SM.
+constexpr int SC_DUAL_THREADS = SC_LEAD_WARPS * 32 + 2 * 128;
+template <int P, int NK, bool DUAL>
+__global__ void __launch_bounds__(DUAL ? SC_DUAL_THREADS : SC_MAX_THREADS, DUAL ? 2 : 1) slab_conv_kernel(const SlabConvParams p) {
 #ifdef SHB_SLAB_TRACE
   long long trace_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long trace_start = clock64();
@@ -465,13 +469,14 @@ __global__ void slab_weight_image_kernel(const float* __restrict__ w, uint8_t* _
 
 // ------------------------------------------------------------------------------------------------ host side
 constexpr size_t SC_SMEM_MAX = 227 * 1024 - 3072;  // dynamic budget: leave room for the static part (barriers, tables, bias)
+constexpr size_t SC_SMEM_DUAL = 108 * 1024;         // per CTA when two share an SM (static part and the per-CTA reserve on top)
 
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 
 struct SlabConvPlan { int NP, nstage, SPS; size_t smem; };
 
 // Columns per pass (all of them unless the weight image would not leave room for a 3-stage ring), ring depth, smem bytes.
-static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
+static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out, size_t budget = SC_SMEM_MAX) {
   const int Q = S * CS / 8;
   const size_t slab_b = (size_t)P * CS * 256;
   const size_t zero_b = CS == 8 ? PLANE_STRIDE : 0;
@@ -479,8 +484,8 @@ static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
   for (int NP = NPt > 256 ? 256 : NPt; NP >= 16; NP -= 16) {
     if (NPt % NP != 0 && NP != NPt) continue;  // equal passes
     const size_t img_region = (((size_t)P * NP * Q * 16 + (CS == 8 ? 128 : 0) + 1023) / 1024) * 1024;
-    if (img_region + zero_b + 2 * slab_b > SC_SMEM_MAX) continue;
-    const size_t room = SC_SMEM_MAX - img_region - zero_b;
+    if (img_region + zero_b + 2 * slab_b > budget) continue;
+    const size_t room = budget - img_region - zero_b;
     // slabs per stage: as many as keep a stage <= stage_cap (one barrier round trip per stage) with >= 3 stages in the ring
     int SPS = 1;
     while (SPS < SC_MAX_SPS && slab_b * SPS * 2 <= stage_cap && room / (slab_b * SPS * 2) >= 3) SPS *= 2;
@@ -494,43 +499,46 @@ static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out) {
   return false;
 }
 
-static int slab_conv_launch(const SlabConvParams& p, size_t smem, cudaStream_t st) {
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[p.P]) {
-    cudaError_t e = cudaSuccess;
-#define SHB_SC_ATTR(PL, K) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(slab_conv_kernel<PL, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX)
-    if (p.P == 1) { SHB_SC_ATTR(1, 1); SHB_SC_ATTR(1, 2); SHB_SC_ATTR(1, 4); SHB_SC_ATTR(1, 8); SHB_SC_ATTR(1, 16); }
-    else { SHB_SC_ATTR(2, 1); SHB_SC_ATTR(2, 2); SHB_SC_ATTR(2, 4); SHB_SC_ATTR(2, 8); }
-#undef SHB_SC_ATTR
+template <int P, int NK, bool DUAL> static int slab_conv_go(const SlabConvParams& p, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;  // per instantiation; the attribute is sticky
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(slab_conv_kernel<P, NK, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(DUAL ? SC_SMEM_DUAL : SC_SMEM_MAX));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(slab_conv_kernel<P, NK, DUAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return (int)e;
-    attr_set[p.P] = true;
+    attr_set = true;
   }
-  const int grid = p.num_tiles < persistent_sms() ? p.num_tiles : persistent_sms();
+  const int slots = persistent_sms() * (DUAL ? 2 : 1);
+  const int grid = p.num_tiles < slots ? p.num_tiles : slots;
   const int threads = SC_LEAD_WARPS * 32 + 128 * p.EG;
+  slab_conv_kernel<P, NK, DUAL><<<grid, threads, smem, st>>>(p);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int slab_conv_launch(const SlabConvParams& p, size_t smem, bool dual, cudaStream_t st) {
   const int nk = p.CS >= 16 ? p.CS / 16 : 1;  // MMAs (K = 16) per slab and plane
-#define SHB_SC_GO(PL, K) slab_conv_kernel<PL, K><<<grid, threads, smem, st>>>(p)
+#define SHB_SC_GO(PL, K) return dual ? slab_conv_go<PL, K, true>(p, smem, st) : slab_conv_go<PL, K, false>(p, smem, st)
   if (p.P == 1) {
     switch (nk) {
-      case 1: SHB_SC_GO(1, 1); break;
-      case 2: SHB_SC_GO(1, 2); break;
-      case 4: SHB_SC_GO(1, 4); break;
-      case 8: SHB_SC_GO(1, 8); break;
-      case 16: SHB_SC_GO(1, 16); break;
+      case 1: SHB_SC_GO(1, 1);
+      case 2: SHB_SC_GO(1, 2);
+      case 4: SHB_SC_GO(1, 4);
+      case 8: SHB_SC_GO(1, 8);
+      case 16: SHB_SC_GO(1, 16);
       default: return SHB_E_UNSUPPORTED;
     }
   } else {
     switch (nk) {
-      case 1: SHB_SC_GO(2, 1); break;
-      case 2: SHB_SC_GO(2, 2); break;
-      case 4: SHB_SC_GO(2, 4); break;
-      case 8: SHB_SC_GO(2, 8); break;
+      case 1: SHB_SC_GO(2, 1);
+      case 2: SHB_SC_GO(2, 2);
+      case 4: SHB_SC_GO(2, 4);
+      case 8: SHB_SC_GO(2, 8);
       default: return SHB_E_UNSUPPORTED;
     }
   }
 #undef SHB_SC_GO
-  SHB_LAUNCH_CHECK();
-  return 0;
 }
 
 }  // namespace shb
@@ -586,6 +594,13 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
   SlabConvPlan plan;
   const int NPt = pad16(Cd);
   slab_conv_plan(S, Cs, NPt, planes, &plan);
+  // two CTAs per SM when the whole weight image and a >= 3-stage ring fit in half an SM and two epilogue groups cover the
+  // accumulator (<= 64 columns)
+  static const bool allow_dual = [] { const char* e = getenv("SHB_SLAB_NO_DUAL"); return !(e && atoi(e)); }();
+  SlabConvPlan dplan;
+  const bool dual = allow_dual && Cd <= 64 && slab_conv_plan(S, Cs, NPt, planes, &dplan, SC_SMEM_DUAL) && dplan.NP == NPt &&
+                    dplan.nstage >= 3;
+  if (dual) plan = dplan;
   SlabConvParams p{};
   p.src = (const uint8_t*)src; p.ptr = ptr; p.ent = entries; p.dst = (uint8_t*)dst; p.ymul = (const uint8_t*)ymul;
   p.NB = slab::num_chunks(B); p.rows_dst = rows_dst;
@@ -601,6 +616,7 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
     p.w_img = (const uint8_t*)w_img + (size_t)(n0 / 8) * p.Q * 128;
     { static const int dbg = [] { const char* e = getenv("SHB_SLAB_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
     p.cpw = p.ncols >= 128 ? 32 : (p.ncols >= 64 ? 16 : 8);
+    if (dual) p.cpw = p.ncols >= 64 ? 32 : (p.ncols >= 32 ? 16 : 8);
     p.EG = p.ncols / p.cpw;
     {
       static const int eg_cap = [] { const char* e = getenv("SHB_SLAB_EG"); return e ? atoi(e) : 4; }();  // tuning knob
@@ -611,7 +627,7 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
     uint32_t cols = 32;
     while (cols < 2u * p.NP) cols <<= 1;
     p.tmem_cols = cols;
-    int rc = slab_conv_launch(p, plan.smem, (cudaStream_t)stream);
+    int rc = slab_conv_launch(p, plan.smem, dual, (cudaStream_t)stream);
     if (rc != 0) return rc;
   }
   return 0;

@@ -12,6 +12,8 @@
 //
 // Roles: warps 0-1 = TMA producers (alternate ring stages), warp 2 = MMA issuer (one elected thread), warps 3-6 = gz column
 // sums + final read-out.
+#include <stdlib.h>
+
 #include "shb_common.cuh"
 #include "shb_internal.h"
 #include "shb_slab.cuh"
@@ -40,8 +42,9 @@ struct SlabWgradParams {
   uint32_t tmem_cols;
 };
 
-template <int P>
-__global__ void __launch_bounds__(SW_THREADS, 1) slab_wgrad_kernel(const SlabWgradParams p) {
+// DUAL: two CTAs per SM (half the ring each) -- the sibling fills the issue slots the dependent role chains leave idle.
+template <int P, bool DUAL>
+__global__ void __launch_bounds__(SW_THREADS, DUAL ? 2 : 1) slab_wgrad_kernel(const SlabWgradParams p) {
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[SW_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[SW_MAX_STAGES];
@@ -293,7 +296,9 @@ static inline int pad16w(int c) { return (c + 15) / 16 * 16; }
 
 struct SlabWgradPlan { int PC, PPS, PPG, G, N, Gp, nstage; size_t smem; };
 
-static bool slab_wgrad_plan(int S, int Cin, int Cout_p, int P, SlabWgradPlan* o) {
+constexpr size_t SW_SMEM_DUAL = 108 * 1024;
+
+static bool slab_wgrad_plan(int S, int Cin, int Cout_p, int P, SlabWgradPlan* o, size_t budget = SW_SMEM_MAX, int tmem_cols = 512) {
   if (!(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256)) return false;
   o->PC = Cin < 128 ? Cin : 128;
   o->PPS = Cin / o->PC;
@@ -305,10 +310,10 @@ static bool slab_wgrad_plan(int S, int Cin, int Cout_p, int P, SlabWgradPlan* o)
     if (NPt % N != 0) continue;
     const size_t gz_buf = (((size_t)P * N * 256 + 1023) / 1024) * 1024;
     const size_t stage = (size_t)P * SW_GROUP_BYTES;
-    if (2 * gz_buf + 2 * stage > SW_SMEM_MAX) continue;
-    size_t n = (SW_SMEM_MAX - 2 * gz_buf) / stage;
+    if (2 * gz_buf + 2 * stage > budget) continue;
+    size_t n = (budget - 2 * gz_buf) / stage;
     if (n > SW_MAX_STAGES) n = SW_MAX_STAGES;
-    int Gp = 512 / N;
+    int Gp = tmem_cols / N;
     if (Gp > o->G) Gp = o->G;
     if (Gp < 1) continue;
     o->N = N; o->Gp = Gp; o->nstage = (int)n; o->smem = 2 * gz_buf + n * stage;
@@ -334,7 +339,7 @@ size_t shb_slab_wgrad_workspace(int S, int Cin, int Cout_p, int planes) {
   if (!shb_slab_wgrad_supported(S, Cin, Cout_p, planes)) return 0;
   slab_wgrad_plan(S, Cin, Cout_p, planes, &plan);
   const size_t NPt = pad16w(Cout_p);
-  return (size_t)kNumSMs * ((size_t)plan.G * 128 * NPt + NPt) * sizeof(float);
+  return (size_t)2 * kNumSMs * ((size_t)plan.G * 128 * NPt + NPt) * sizeof(float);  // up to two CTAs per SM, one partial each
 }
 
 /* x: slab tensor (rows_in, B, Cin_p); gz: slab tensor (rows_out, B, Cout_p); table (rows_out, S).
@@ -349,13 +354,26 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
   SlabWgradPlan plan;
   slab_wgrad_plan(S, Cin_p, Cout_p, planes, &plan);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[planes]) {
-    cudaError_t e = planes == 1
-                        ? cudaFuncSetAttribute(slab_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX)
-                        : cudaFuncSetAttribute(slab_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX);
+  // two CTAs per SM when a >= 3-stage ring fits in half an SM and the whole accumulator in half of TMEM, in one pass
+  static const bool allow_dual = [] { const char* e = getenv("SHB_SLAB_NO_DUAL"); return !(e && atoi(e)); }();
+  SlabWgradPlan dplan;
+  // (only where a CTA has many tiles: every CTA costs one partial in the fixed-order reduction)
+  const long long tiles_all = (long long)(skip_last ? rows_out - 1 : rows_out) * slab::num_chunks(B);
+  const bool dual = allow_dual && tiles_all >= 40LL * kNumSMs &&
+                    slab_wgrad_plan(S, Cin_p, Cout_p, planes, &dplan, SW_SMEM_DUAL, 256) && dplan.nstage >= 3 &&
+                    dplan.Gp == dplan.G && dplan.N == pad16w(Cout_p);
+  if (dual) plan = dplan;
+  static bool attr_set[3][2] = {{false, false}, {false, false}, {false, false}};
+  if (!attr_set[planes][dual]) {
+    cudaError_t e;
+    if (planes == 1)
+      e = dual ? cudaFuncSetAttribute(slab_wgrad_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_DUAL)
+               : cudaFuncSetAttribute(slab_wgrad_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX);
+    else
+      e = dual ? cudaFuncSetAttribute(slab_wgrad_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_DUAL)
+               : cudaFuncSetAttribute(slab_wgrad_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX);
     if (e != cudaSuccess) return (int)e;
-    attr_set[planes] = true;
+    attr_set[planes][dual] = true;
   }
   const int NPt = pad16w(Cout_p);
   SlabWgradParams p{};
@@ -366,8 +384,9 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
   const int rows_eff = skip_last ? rows_out - 1 : rows_out;
   p.num_tiles = rows_eff * p.NB;
   float* partial = (float*)workspace;
-  float* bias_partial = partial + (size_t)kNumSMs * plan.G * 128 * NPt;
-  const int grid = p.num_tiles < persistent_sms() ? p.num_tiles : persistent_sms();
+  float* bias_partial = partial + (size_t)2 * kNumSMs * plan.G * 128 * NPt;
+  const int slots = persistent_sms() * (dual ? 2 : 1);
+  const int grid = p.num_tiles < slots ? p.num_tiles : slots;
   if (grid > 0) {
     for (int n0 = 0; n0 < NPt; n0 += plan.N) {
       if (n0 >= Cout_p) break;
@@ -380,8 +399,13 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
         uint32_t cols = 32;
         while (cols < (uint32_t)(p.Gp * p.N)) cols <<= 1;
         p.tmem_cols = cols;
-        if (planes == 1) slab_wgrad_kernel<1><<<grid, SW_THREADS, plan.smem, st>>>(p);
-        else slab_wgrad_kernel<2><<<grid, SW_THREADS, plan.smem, st>>>(p);
+        if (planes == 1) {
+          if (dual) slab_wgrad_kernel<1, true><<<grid, SW_THREADS, plan.smem, st>>>(p);
+          else slab_wgrad_kernel<1, false><<<grid, SW_THREADS, plan.smem, st>>>(p);
+        } else {
+          if (dual) slab_wgrad_kernel<2, true><<<grid, SW_THREADS, plan.smem, st>>>(p);
+          else slab_wgrad_kernel<2, false><<<grid, SW_THREADS, plan.smem, st>>>(p);
+        }
         SHB_LAUNCH_CHECK();
       }
     }
