@@ -244,6 +244,49 @@ def pair_distance_loss(tx, rec, kps, part_index_lists, skl_list, w_mode="linear"
     return total
 
 
+def bone_guided_step_loss(params, tx, tx_interp, tx_exc, measure, J, kps_keep, kps_index_list, part_index_lists, skl_list, P, Q,
+                          factor, filters_enc, filters_dec, sizes, spirals, D, U, weights, w_mode="linear", w_threshold=0.8,
+                          leaf_parts=(0, 7, 10, 13, 16), relative=True, act="elu", part_index_lists_fine=None):
+    """The loss of ONE bone-guided training step, train_funcs.py:128-392, for edit_mode 'equal' (:213-223), exc_mode 'ori_m'
+    (:296-300), w_part_mode '1/K', without the per-sample edge / volume regularisers (:136-143, :322-332, separate oracle
+    functions in aux losses).  `factor` is the value the loop draws at :222 (passed in so that the oracle is deterministic).
+    `part_index_lists` are the part vertex lists at the COARSEST level (the model's heads, models.py:199-204);
+    `part_index_lists_fine` those at level 0 (vert_part_index_dict of the loop, used by the distance loss; default: the same).
+    Returns (total, dict of the six terms)."""
+    fine = part_index_lists if part_index_lists_fine is None else part_index_lists_fine
+    fw = dict(filters_enc=filters_enc, filters_dec=filters_dec, spirals=spirals, act=act)
+    keep = torch.as_tensor(kps_keep)
+    # :130-135 reconstruction pass
+    kps_gt = torch.matmul(J, tx[:, :-1, :])
+    tx_hat, z, _ = multiz_forward(params, tx, kps_gt[:, keep], kps_index_list, part_index_lists, filters_enc, filters_dec, sizes,
+                                  spirals, D, U, act)
+    terms = {"rec": l1_loss(tx, tx_hat), "zpartreg": zpart_reg(z, measure, P, Q, relative)}                  # :135, :144-152
+    # :160-228 interpolation pass: scale the non-leaf part codes by one factor
+    kps_i = torch.matmul(J, tx_interp[:, :-1, :])
+    new_kps = kps_i[:, keep]                                                                                  # :218-219
+    lat, lat_k, dummy = multiz_encode(params, tx_interp, new_kps, kps_index_list, part_index_lists, D=D, **fw)   # :225
+    a = torch.ones(tx_interp.shape[0], len(P), dtype=tx.dtype) * factor                                       # :223
+    lat = lat.clone()
+    for k, v in enumerate(P):
+        lat[:, v, :] = lat[:, v, :] * a[:, k][:, None]                                                        # :226-227
+    rec_i = multiz_decode(params, lat, lat_k, dummy, part_index_lists, filters_enc, filters_dec, sizes, spirals, U, act)
+    terms["interp_kps"] = l1_loss(torch.matmul(J, rec_i[:, :-1, :])[:, keep], new_kps)                        # :230-233
+    scale = torch.ones(tx_interp.shape[0], len(part_index_lists), dtype=tx.dtype)
+    scale[:, list(P)] = a
+    terms["interp_euc"] = pair_distance_loss(tx_interp[:, :-1, :], rec_i[:, :-1, :], kps_i, fine, skl_list, w_mode,
+                                             w_threshold, leaf_parts, relative, scale=scale)                  # :235-284
+    # :286-389 exchange pass: every sample is encoded with the keypoints of its mirror sample in the batch
+    kps_e = torch.matmul(J, tx_exc[:, :-1, :])
+    new_kps_e = torch.flip(kps_e, dims=[0])[:, keep]                                                          # :298-300
+    lat, lat_k, dummy = multiz_encode(params, tx_exc, new_kps_e, kps_index_list, part_index_lists, D=D, **fw)  # :319
+    rec_e = multiz_decode(params, lat, lat_k, dummy, part_index_lists, filters_enc, filters_dec, sizes, spirals, U, act)
+    terms["exc_kps"] = l1_loss(torch.matmul(J, rec_e[:, :-1, :])[:, keep], new_kps_e)                         # :334-341
+    terms["exc_euc"] = pair_distance_loss(tx_exc[:, :-1, :], rec_e[:, :-1, :], kps_e, fine, skl_list, w_mode,
+                                          w_threshold, leaf_parts, relative)                                  # :343-389
+    total = sum(weights[k] * v for k, v in terms.items())
+    return total, terms
+
+
 def normalise_spiral(spiral_idx, rows_in=None):
     """-1 -> rows_in-1 (models.py:42's negative index), int32, 2-D."""
     a = np.asarray(spiral_idx)

@@ -124,6 +124,24 @@ class L1LossFn(torch.autograd.Function):
         return ga, gb
 
 
+class PartNormIndex:
+    """Validated (part, measure) index lists of the part-measure latent loss, resident on the device.  Build once and pass as
+    `P` to partnorm_loss (with Q=None): no per-call host validation, usable inside a CUDA-graph capture."""
+
+    def __init__(self, P, Q, n_parts, n_measure, device):
+        P = torch.as_tensor(P).detach().to("cpu", torch.int64).reshape(-1)
+        Q = torch.as_tensor(Q).detach().to("cpu", torch.int64).reshape(-1)
+        if P.numel() == 0 or P.numel() != Q.numel():
+            raise ValueError("partnorm_loss: P and Q must be non-empty index lists of equal length")
+        if int(P.min()) < 0 or int(P.max()) >= n_parts or int(Q.min()) < 0 or int(Q.max()) >= n_measure:
+            raise ValueError("partnorm_loss: part / measure index out of range")
+        if P.unique().numel() != P.numel():
+            raise ValueError("partnorm_loss: a part may appear once in P (its gradient row is written once)")
+        self.n_parts, self.n_measure = int(n_parts), int(n_measure)
+        self.P = P.to(torch.int32).to(device)
+        self.Q = Q.to(torch.int32).to(device)
+
+
 class PartNormLossFn(torch.autograd.Function):
     """Part-measure latent loss (train_funcs.py:145-152); loss and d loss/d z in one launch."""
 
@@ -135,17 +153,12 @@ class PartNormLossFn(torch.autograd.Function):
         if z.dim() != 3 or measure.dim() != 2 or measure.shape[0] != z.shape[0]:
             raise ValueError("partnorm_loss expects z (B, n_parts, L) and measure (B, n_measure)")
         B, n_parts, L = z.shape
-        # the kernel reads P / Q as int32 device arrays and writes gz rows P[i]: validate on the host (small index lists)
-        P = torch.as_tensor(P).detach().to("cpu", torch.int64).reshape(-1)
-        Q = torch.as_tensor(Q).detach().to("cpu", torch.int64).reshape(-1)
-        if P.numel() == 0 or P.numel() != Q.numel():
-            raise ValueError("partnorm_loss: P and Q must be non-empty index lists of equal length")
-        if int(P.min()) < 0 or int(P.max()) >= n_parts or int(Q.min()) < 0 or int(Q.max()) >= measure.shape[1]:
-            raise ValueError("partnorm_loss: part / measure index out of range")
-        if P.unique().numel() != P.numel():
-            raise ValueError("partnorm_loss: a part may appear once in P (its gradient row is written once)")
-        P = P.to(torch.int32).to(z.device)
-        Q = Q.to(torch.int32).to(z.device)
+        # the kernel reads P / Q as int32 device arrays and writes gz rows P[i]: validated on the host (small index lists),
+        # once per call or once for all in a PartNormIndex
+        idx = P if isinstance(P, PartNormIndex) else PartNormIndex(P, Q, n_parts, measure.shape[1], z.device)
+        if idx.n_parts != n_parts or idx.n_measure != measure.shape[1] or idx.P.device != z.device:
+            raise ValueError("partnorm_loss: index lists were validated for a different shape or device")
+        P, Q = idx.P, idx.Q
         out = torch.empty((), dtype=torch.float32, device=z.device)
         gz = torch.empty_like(z)
         _call("partnorm_loss_fwd_bwd", {"bytes": 2.0 * z.numel() * 4}, lib.shb_partnorm_loss_fwd_bwd, _p(z), _p(measure),

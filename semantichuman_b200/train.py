@@ -103,3 +103,113 @@ class TrainStep:
         loss = self(xd)
         loss_host_pinned.copy_(loss.detach().reshape(loss_host_pinned.shape), non_blocking=True)
         return loss
+
+
+class BoneGuidedStep:
+    """One training step of the bone-guided model (train_funcs.py:128-392, edit_mode 'equal', exc_mode 'ori_m', w_part_mode
+    '1/K'): three passes through the model -- reconstruction, interpolation (non-leaf part codes scaled by a random factor),
+    exchange (keypoints swapped across the batch) -- six loss terms (reconstruction L1, part-measure latent loss, keypoint L1
+    and the orientation-adaptive pairwise-distance loss for both edited passes), ONE backward, Adam; optionally replayed as one
+    CUDA graph.  The per-sample edge / volume regularisers of :136-143, :322-332 are separate torch functions
+    (aux_losses.py) and not part of this step.
+
+        step = BoneGuidedStep(model, J_regressor, kps_keep, parts, skl_list, P, Q)
+        loss = step(tx, tx_interp, tx_exc, measure)
+    """
+
+    DEFAULT_WEIGHTS = {"rec": 1.0, "zpartreg": 1e-2, "interp_kps": 1.0, "interp_euc": 1e-2, "exc_kps": 1.0, "exc_euc": 1e-2}
+
+    def __init__(self, model, J_regressor, kps_keep, parts, skl_list, P, Q, leaf_parts=(0, 7, 10, 13, 16), weights=None,
+                 w_mode="linear", w_threshold=0.8, relative=True, factor=(0.4, 0.8), lr=1e-3, weight_decay=5e-5,
+                 optimizer=True, graph=False):
+        dev = next(model.parameters()).device
+        self.model = model
+        self.J = torch.as_tensor(J_regressor, dtype=torch.float32, device=dev).contiguous()
+        self.keep = torch.as_tensor(kps_keep, dtype=torch.long, device=dev)
+        self.P, self.Q = list(P), list(Q)
+        self._P_dev = torch.as_tensor(self.P, dtype=torch.long, device=dev)
+        self._pn_index = None  # validated (P, Q) lists on the device, built at the first call (needs the measure width)
+        self.layout = fn.PairLossLayout(parts, skl_list, dev, w_mode=w_mode, leaf_parts=leaf_parts)
+        self.n_parts = len(parts)
+        self.weights = dict(self.DEFAULT_WEIGHTS if weights is None else weights)
+        self.w_threshold, self.relative, self.factor = float(w_threshold), bool(relative), factor
+        self.optim = Adam(model.parameters(), lr=lr, weight_decay=weight_decay) if optimizer else None
+        self.graph_enabled = bool(graph)
+        self._graph = self._static = self._gloss = None
+        self.terms = {}
+
+    def _kps(self, v):
+        return torch.matmul(self.J, v[:, :-1, :])
+
+    def loss(self, tx, tx_interp, tx_exc, measure, factor=None):
+        m, w = self.model, self.weights
+        B = tx.shape[0]
+        t = {}
+        tx_hat, z, _ = m(tx, self._kps(tx)[:, self.keep])
+        t["rec"] = fn.l1_loss(tx, tx_hat)
+        if self._pn_index is None:
+            self._pn_index = fn.PartNormIndex(self.P, self.Q, z.shape[1], measure.shape[1], z.device)
+        t["zpartreg"] = fn.partnorm_loss(z, measure, self._pn_index, None, self.relative)
+        # interpolation pass (train_funcs.py:213-228): one factor for every non-leaf part code
+        if factor is None:
+            factor = torch.rand(1, device=tx.device) * self.factor[0] + self.factor[1]
+        factor = torch.as_tensor(factor, dtype=torch.float32, device=tx.device).reshape(1)
+        scale = torch.ones(B, self.n_parts, device=tx.device)
+        scale[:, self._P_dev] = factor
+        kps_i = self._kps(tx_interp)
+        new_kps = kps_i[:, self.keep]
+        lat, lat_k, dummy = m.encode(tx_interp, new_kps)
+        rec_i = m.decode(lat * scale[:, :, None], lat_k, dummy)
+        t["interp_kps"] = fn.l1_loss(self._kps(rec_i)[:, self.keep].contiguous(), new_kps.contiguous())
+        t["interp_euc"] = fn.pair_loss(tx_interp[:, :-1, :], rec_i[:, :-1, :], kps_i, self.layout, scale=scale,
+                                       w_threshold=self.w_threshold, relative=self.relative)
+        # exchange pass (:296-300, :319): keypoints of the mirror sample
+        kps_e = self._kps(tx_exc)
+        new_kps_e = torch.flip(kps_e, dims=[0])[:, self.keep]
+        lat, lat_k, dummy = m.encode(tx_exc, new_kps_e)
+        rec_e = m.decode(lat, lat_k, dummy)
+        t["exc_kps"] = fn.l1_loss(self._kps(rec_e)[:, self.keep].contiguous(), new_kps_e.contiguous())
+        t["exc_euc"] = fn.pair_loss(tx_exc[:, :-1, :], rec_e[:, :-1, :], kps_e, self.layout, scale=None,
+                                    w_threshold=self.w_threshold, relative=self.relative)
+        self.terms = t
+        total = None
+        for k, v in t.items():
+            total = w[k] * v if total is None else total + w[k] * v
+        return total
+
+    def _eager(self, tx, tx_interp, tx_exc, measure, factor=None):
+        for p in self.model.parameters():
+            p.grad = None
+        loss = self.loss(tx, tx_interp, tx_exc, measure, factor)
+        loss.backward()
+        if self.optim is not None:
+            self.optim.step()
+        return loss
+
+    def capture(self, tx, tx_interp, tx_exc, measure, warmup=3):
+        if not self.graph_enabled:
+            raise RuntimeError("construct BoneGuidedStep(graph=True) to capture")
+        self._static = [t.clone() for t in (tx, tx_interp, tx_exc, measure)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = fn.LAUNCHES["n"]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self._gloss = self._eager(*self._static)
+        self.launches_per_step = fn.LAUNCHES["n"] - n0
+        self._graph = g
+        return self
+
+    def __call__(self, tx, tx_interp, tx_exc, measure, factor=None):
+        if self._graph is not None and factor is None and fn.TIMER is None:
+            for dst, src in zip(self._static, (tx, tx_interp, tx_exc, measure)):
+                dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            fn.LAUNCHES["n"] += self.launches_per_step
+            return self._gloss
+        return self._eager(tx, tx_interp, tx_exc, measure, factor)
