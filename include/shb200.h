@@ -119,18 +119,18 @@ int shb_group_linear_scatter_bwd(const float* zz, const int32_t* idx, const int3
  * De / De_r = pairwise distances in tx / rec (De times scale[b,k] when scale != NULL); w from the angle (degrees) between
  * v_i - v_j and the part's bone kps[bone[k][0]] - kps[bone[k][1]] (or minus the mean of two keypoints when bone[k][2] >= 0):
  * wmode[k] = 0 all-one, 1 angle/90, 2 sin(angle), 3 angle/90 zeroed below w_threshold.  loss = sum_k part_weight[k] * mean_k.
- * fwd writes the loss and keeps the per-part normalisers in the workspace; bwd (same arguments, same workspace) writes
- * d loss / d rec * gscale[0] for every vertex (zero outside the parts; parts must not overlap).  Fixed-order reductions.
+ * fwd writes the loss and keeps the per-part normalisers in the workspace (parts must not overlap).  Fixed-order reductions.
  * kps (B, NK, 3); idx, gptr, bone (G,3), wmode (G) int32 and part_weight (G), scale (B,G) fp32 are device arrays. */
 size_t shb_pair_loss_workspace(int B, int G, int max_part_rows);
+/* grad_acc: (B, V, 3) fp32 or NULL.  When given, the forward pass also leaves the unscaled per-vertex gradient there, and
+ * shb_pair_loss_bwd (same idx / gptr / workspace) only scales it: grec = 2 * coef[part] * gscale[0] * grad_acc, zero for
+ * vertices outside every part.  One walk over the pairs serves loss and gradient. */
 int shb_pair_loss_fwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
                       const int32_t* bone, const int32_t* wmode, const float* part_weight, const float* scale,
-                      float w_threshold, int relative, float* loss_out, void* workspace, size_t workspace_bytes, int B, int V,
-                      int NK, int G, int max_part_rows, void* stream);
-int shb_pair_loss_bwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
-                      const int32_t* bone, const int32_t* wmode, const float* scale, float w_threshold, int relative,
-                      const float* gscale, float* grec, const void* workspace, size_t workspace_bytes, int B, int V, int NK,
-                      int G, int max_part_rows, void* stream);
+                      float w_threshold, int relative, float* loss_out, float* grad_acc, void* workspace, size_t workspace_bytes,
+                      int B, int V, int NK, int G, int max_part_rows, void* stream);
+int shb_pair_loss_bwd(const float* grad_acc, const int32_t* idx, const int32_t* gptr, const float* gscale, float* grec,
+                      const void* workspace, size_t workspace_bytes, int B, int V, int G, int max_part_rows, void* stream);
 
 /* ==================================================================================================================
  * Slab layout: the trunks' internal activation format (batch innermost, 128-sample chunks, 8-channel planes).

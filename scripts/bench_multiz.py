@@ -53,6 +53,34 @@ for grouped in (True, False):
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             res[mode] = {"ms_per_4096": ms, "meshes_per_s": 4096 / ms * 1e3}
+    if grouped:
+        # ---- the step the paper trains (train_funcs.py:128-392): three passes + six loss terms + one backward + Adam, B = 256
+        from semantichuman_b200.train import BoneGuidedStep
+        v0 = np.asarray(h.verts0)
+        fine = [np.sort(c) for c in np.array_split(np.argsort(v0[:, 1], kind="stable"), len(PART_LIST))]
+        g = torch.Generator().manual_seed(1)
+        J = torch.rand(35, v0.shape[0], generator=g) ** 16
+        J = J / J.sum(1, keepdim=True)
+        skl = [[15, 12], [15, 12], [12, 9], [6, 0], [0, 1, 2], [1, 4], [4, 7], [7, 10], [2, 5], [5, 8], [8, 11], [16, 18],
+               [18, 20], [20, 22], [17, 19], [19, 21], [21, 23]]
+        keep = [i for i in range(35) if i not in (3, 13, 14)]
+        data = [synthetic_meshes(h.verts0, 256, seed=40 + i).to(dev) for i in range(3)]
+        meas = torch.rand(256, 16, device=dev, generator=gen) * 0.8 + 0.2
+        for use_graph in (True, False):  # capture first: autograd's grad accumulators must first be created on the capture stream
+            bg = BoneGuidedStep(model, J, keep, fine, skl, list(range(1, 13)), list(range(0, 12)), graph=use_graph)
+            if use_graph:
+                bg.capture(*data, meas)
+            for _ in range(3):
+                bg(*data, meas)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(10):
+                loss = bg(*data, meas)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            res["bone_guided_step_graph" if use_graph else "bone_guided_step_eager"] = {
+                "ms": ms, "meshes_per_s": 3 * 256 / ms * 1e3, "loss": float(loss),
+                "note": "3 x 256 meshes per step (reconstruction, interpolation and exchange batches)"}
     # ---- one training step (recon + part-norm loss), B = 256, eager
     from semantichuman_b200.optim import Adam
     opt = Adam(model.parameters(), lr=1e-3)
@@ -74,34 +102,6 @@ for grouped in (True, False):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     res["train_step"] = {"ms": ms, "meshes_per_s": 256 / ms * 1e3, "loss": float(loss)}
-    if grouped:
-        # ---- the step the paper trains (train_funcs.py:128-392): three passes + six loss terms + one backward + Adam, B = 256
-        from semantichuman_b200.train import BoneGuidedStep
-        v0 = np.asarray(h.verts0)
-        fine = [np.sort(c) for c in np.array_split(np.argsort(v0[:, 1], kind="stable"), len(PART_LIST))]
-        g = torch.Generator().manual_seed(1)
-        J = torch.rand(35, v0.shape[0], generator=g) ** 16
-        J = J / J.sum(1, keepdim=True)
-        skl = [[15, 12], [15, 12], [12, 9], [6, 0], [0, 1, 2], [1, 4], [4, 7], [7, 10], [2, 5], [5, 8], [8, 11], [16, 18],
-               [18, 20], [20, 22], [17, 19], [19, 21], [21, 23]]
-        keep = [i for i in range(35) if i not in (3, 13, 14)]
-        data = [synthetic_meshes(h.verts0, 256, seed=40 + i).to(dev) for i in range(3)]
-        meas = torch.rand(256, 16, device=dev, generator=gen) * 0.8 + 0.2
-        for use_graph in (False, True):
-            bg = BoneGuidedStep(model, J, keep, fine, skl, list(range(1, 13)), list(range(0, 12)), graph=use_graph)
-            if use_graph:
-                bg.capture(*data, meas)
-            for _ in range(3):
-                bg(*data, meas)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); e0.record()
-            for _ in range(10):
-                loss = bg(*data, meas)
-            e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 10
-            res["bone_guided_step_graph" if use_graph else "bone_guided_step_eager"] = {
-                "ms": ms, "meshes_per_s": 3 * 256 / ms * 1e3, "loss": float(loss),
-                "note": "3 x 256 meshes per step (reconstruction, interpolation and exchange batches)"}
     out[tag] = res
     out[tag + "_xhat_checksum"] = float(y.double().abs().sum())
 print(json.dumps(out))

@@ -69,7 +69,11 @@ __device__ __forceinline__ void pl_bone(const PLParams& p, int b, int k, float3&
 }
 
 // grid (nblk, G, B): per-block (sum of terms, number of masked entries) -> partials[((b*G + k)*nblk + blk)*2 + {0,1}]
-__global__ void __launch_bounds__(PL_THREADS) pl_partial_kernel(const PLParams p, float* __restrict__ partials) {
+// With gacc != null the same pass also leaves the UNSCALED gradient sum_j sign(e_ij) (w_ij [/ De_ij]) (r_i - r_j) / |r_i - r_j|
+// of every part vertex in gacc (B, V, 3): the backward is then an elementwise scaling by 2 coef[k] gscale instead of a second
+// walk over all pairs (the pair arithmetic -- sqrt, division, acos -- is the whole cost of this loss).
+__global__ void __launch_bounds__(PL_THREADS) pl_partial_kernel(const PLParams p, float* __restrict__ partials,
+                                                                float* __restrict__ gacc) {
   __shared__ float3 sv[PL_THREADS], sr[PL_THREADS];
   __shared__ float red[PL_THREADS / 32];
   const int blk = blockIdx.x, k = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(PL_THREADS) pl_partial_kernel(const PLParams p
   const bool on = i < n;
   const int vi_id = on ? p.idx[g0 + i] : 0;
   const float3 vi = ld3(txb + (size_t)vi_id * 3), ri = ld3(rcb + (size_t)vi_id * 3);
-  float sum = 0.f, cnt = 0.f;
+  float sum = 0.f, cnt = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
   for (int j0 = 0; j0 < n; j0 += PL_THREADS) {
     __syncthreads();
     if (j0 + t < n) {
@@ -106,10 +110,22 @@ __global__ void __launch_bounds__(PL_THREADS) pl_partial_kernel(const PLParams p
         if (!pl_pair(vi, sv[jj], kd, km, mode, p.w_threshold, sc, w, De)) continue;
         const float rx = ri.x - sr[jj].x, ry = ri.y - sr[jj].y, rz = ri.z - sr[jj].z;
         const float Der = sqrtf(rx * rx + ry * ry + rz * rz);
-        sum += p.relative ? fabsf(w * Der / De - w) : fabsf(w * Der - w * De);
+        const float e = p.relative ? (w * Der / De - w) : (w * Der - w * De);
+        sum += fabsf(e);
         cnt += 1.f;
+        if (gacc != nullptr && Der != 0.f) {  // coincident reconstructed points: the reference's sqrt'(0) gives NaN; 0 here
+          const float sg = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
+          const float q = sg * (p.relative ? w / De : w) / Der;
+          gx = fmaf(q, rx, gx);
+          gy = fmaf(q, ry, gy);
+          gz = fmaf(q, rz, gz);
+        }
       }
     }
+  }
+  if (gacc != nullptr && on) {
+    float* gp = gacc + ((size_t)b * p.V + vi_id) * 3;
+    gp[0] = gx; gp[1] = gy; gp[2] = gz;
   }
   __syncthreads();
   sum = block_sum<PL_THREADS>(sum, red);
@@ -144,58 +160,21 @@ __global__ void __launch_bounds__(256) pl_final_kernel(const float* __restrict__
   if (threadIdx.x == 0) *loss_out = loss;
 }
 
-// grid (nblk, G, B): d loss / d rec for the vertices of every part (vertices outside every part: zeroed by the caller)
+// grid (nblk, G, B): d loss / d rec = 2 coef[k] gscale gacc for the vertices of every part (vertices outside every part:
+// zeroed by the caller).  The matrix holds both (i,j) and (j,i), and w, De and the mask are symmetric: factor two.
 __global__ void __launch_bounds__(PL_THREADS) pl_bwd_kernel(const PLParams p, const float* __restrict__ coef,
-                                                            const float* __restrict__ gscale, float* __restrict__ grec) {
-  __shared__ float3 sv[PL_THREADS], sr[PL_THREADS];
+                                                            const float* __restrict__ gscale, const float* __restrict__ gacc,
+                                                            float* __restrict__ grec) {
   const int blk = blockIdx.x, k = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
   const int g0 = p.gptr[k], n = p.gptr[k + 1] - g0;
-  if (blk * PL_THREADS >= n) return;
-  float3 kd; float km;
-  pl_bone(p, b, k, kd, km);
-  const int mode = p.wmode[k];
-  const float sc = p.scale ? p.scale[(size_t)b * p.G + k] : 1.f;
-  const float* txb = p.tx + (size_t)b * p.V * 3;
-  const float* rcb = p.rec + (size_t)b * p.V * 3;
   const int i = blk * PL_THREADS + t;
-  const bool on = i < n;
-  const int vi_id = on ? p.idx[g0 + i] : 0;
-  const float3 vi = ld3(txb + (size_t)vi_id * 3), ri = ld3(rcb + (size_t)vi_id * 3);
-  float gx = 0.f, gy = 0.f, gz = 0.f;
-  for (int j0 = 0; j0 < n; j0 += PL_THREADS) {
-    __syncthreads();
-    if (j0 + t < n) {
-      const int vj = p.idx[g0 + j0 + t];
-      sv[t] = ld3(txb + (size_t)vj * 3);
-      sr[t] = ld3(rcb + (size_t)vj * 3);
-    }
-    __syncthreads();
-    const int jn = min(PL_THREADS, n - j0);
-    if (on) {
-      for (int jj = 0; jj < jn; ++jj) {
-        if (j0 + jj == i) continue;
-        float w, De;
-        if (!pl_pair(vi, sv[jj], kd, km, mode, p.w_threshold, sc, w, De)) continue;
-        const float rx = ri.x - sr[jj].x, ry = ri.y - sr[jj].y, rz = ri.z - sr[jj].z;
-        const float Der = sqrtf(rx * rx + ry * ry + rz * rz);
-        if (Der == 0.f) continue;  // coincident reconstructed points: the reference's sqrt'(0) gives NaN; 0 here
-        const float e = p.relative ? (w * Der / De - w) : (w * Der - w * De);
-        const float s = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
-        const float q = s * (p.relative ? w / De : w) / Der;
-        gx = fmaf(q, rx, gx);
-        gy = fmaf(q, ry, gy);
-        gz = fmaf(q, rz, gz);
-      }
-    }
-  }
-  if (on) {
-    // the matrix holds both (i,j) and (j,i), and w, De and the mask are symmetric: each pair contributes twice
-    const float c = 2.f * coef[k] * __ldg(gscale);
-    float* gp = grec + ((size_t)b * p.V + vi_id) * 3;
-    gp[0] = c * gx;
-    gp[1] = c * gy;
-    gp[2] = c * gz;
-  }
+  if (i >= n) return;
+  const int vi_id = p.idx[g0 + i];
+  const float c = 2.f * coef[k] * __ldg(gscale);
+  const size_t o = ((size_t)b * p.V + vi_id) * 3;
+  grec[o] = c * gacc[o];
+  grec[o + 1] = c * gacc[o + 1];
+  grec[o + 2] = c * gacc[o + 2];
 }
 
 }  // namespace shb
@@ -226,8 +205,8 @@ static int pl_fill(PLParams& p, const float* tx, const float* rec, const float* 
 
 int shb_pair_loss_fwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
                       const int32_t* bone, const int32_t* wmode, const float* part_weight, const float* scale,
-                      float w_threshold, int relative, float* loss_out, void* workspace, size_t workspace_bytes, int B, int V,
-                      int NK, int G, int max_part_rows, void* stream) {
+                      float w_threshold, int relative, float* loss_out, float* grad_acc, void* workspace, size_t workspace_bytes,
+                      int B, int V, int NK, int G, int max_part_rows, void* stream) {
   PLParams p{};
   int rc = pl_fill(p, tx, rec, kps, idx, gptr, bone, wmode, scale, w_threshold, relative, B, V, NK, G, max_part_rows);
   if (rc) return rc;
@@ -236,27 +215,26 @@ int shb_pair_loss_fwd(const float* tx, const float* rec, const float* kps, const
   cudaStream_t st = (cudaStream_t)stream;
   float* partials = (float*)workspace;
   float* coef = partials + pl_partials_floats(B, G, p.nblk);
-  pl_partial_kernel<<<dim3(p.nblk, G, B), PL_THREADS, 0, st>>>(p, partials);
+  pl_partial_kernel<<<dim3(p.nblk, G, B), PL_THREADS, 0, st>>>(p, partials, grad_acc);
   SHB_LAUNCH_CHECK();
   pl_final_kernel<<<1, 256, 0, st>>>(partials, part_weight, p.nblk, B, G, coef, loss_out);
   SHB_LAUNCH_CHECK();
   return 0;
 }
 
-int shb_pair_loss_bwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
-                      const int32_t* bone, const int32_t* wmode, const float* scale, float w_threshold, int relative,
-                      const float* gscale, float* grec, const void* workspace, size_t workspace_bytes, int B, int V, int NK,
-                      int G, int max_part_rows, void* stream) {
+int shb_pair_loss_bwd(const float* grad_acc, const int32_t* idx, const int32_t* gptr, const float* gscale, float* grec,
+                      const void* workspace, size_t workspace_bytes, int B, int V, int G, int max_part_rows, void* stream) {
+  if (!grad_acc || !idx || !gptr || !gscale || !grec || !workspace) return SHB_E_ARG;
+  if (B <= 0 || V <= 0 || G <= 0 || max_part_rows <= 0) return SHB_E_ARG;
+  if (B > 65535 || G > 65535) return SHB_E_SHAPE;
   PLParams p{};
-  int rc = pl_fill(p, tx, rec, kps, idx, gptr, bone, wmode, scale, w_threshold, relative, B, V, NK, G, max_part_rows);
-  if (rc) return rc;
-  if (!gscale || !grec || !workspace) return SHB_E_ARG;
+  p.idx = idx; p.gptr = gptr; p.B = B; p.V = V; p.G = G; p.nblk = (max_part_rows + PL_THREADS - 1) / PL_THREADS;
   if (workspace_bytes < shb_pair_loss_workspace(B, G, max_part_rows)) return SHB_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const float* coef = (const float*)workspace + pl_partials_floats(B, G, p.nblk);
   cudaError_t e = cudaMemsetAsync(grec, 0, (size_t)B * V * 3 * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
-  pl_bwd_kernel<<<dim3(p.nblk, G, B), PL_THREADS, 0, st>>>(p, coef, gscale, grec);
+  pl_bwd_kernel<<<dim3(p.nblk, G, B), PL_THREADS, 0, st>>>(p, coef, gscale, grad_acc, grec);
   SHB_LAUNCH_CHECK();
   return 0;
 }

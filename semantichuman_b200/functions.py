@@ -344,27 +344,28 @@ class PairLossFn(torch.autograd.Function):
         nbytes = lib.shb_pair_loss_workspace(B, lay.G, lay.max_rows)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=tx.device)
         loss = torch.empty((), dtype=torch.float32, device=tx.device)
+        # the gradient w.r.t. rec is accumulated (unscaled) by the same walk over the pairs when it will be needed
+        gacc = torch.empty_like(rec) if ctx.needs_input_grad[1] else None
         pairs = float(B) * lay.pairs_per_sample
-        _call("pair_loss", {"bytes": 24.0 * tx.numel() / 3, "flops": 40.0 * pairs}, lib.shb_pair_loss_fwd, _p(tx), _p(rec),
+        _call("pair_loss", {"bytes": 24.0 * tx.numel() / 3, "flops": 55.0 * pairs}, lib.shb_pair_loss_fwd, _p(tx), _p(rec),
               _p(kps), _p(lay.idx), _p(lay.gptr), _p(lay.bone), _p(lay.wmode), _p(lay.pw), _p(scale), float(w_threshold),
-              int(bool(relative)), _p(loss), _p(ws), nbytes, B, V, kps.shape[1], lay.G, lay.max_rows, _stream())
+              int(bool(relative)), _p(loss), _p(gacc), _p(ws), nbytes, B, V, kps.shape[1], lay.G, lay.max_rows, _stream())
         _count(2)
-        ctx.save_for_backward(tx, rec, kps, scale if scale is not None else tx.new_empty(0), ws)
-        ctx.lay, ctx.thr, ctx.rel, ctx.has_scale, ctx.pairs = lay, float(w_threshold), int(bool(relative)), scale is not None, pairs
+        ctx.save_for_backward(gacc if gacc is not None else tx.new_empty(0), ws)
+        ctx.lay, ctx.shape = lay, (B, V)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        tx, rec, kps, scale, ws = ctx.saved_tensors
+        gacc, ws = ctx.saved_tensors
         lay = ctx.lay
-        B, V, _ = tx.shape
+        B, V = ctx.shape
         grec = None
         if ctx.needs_input_grad[1]:
-            grec = torch.empty_like(rec)
-            gs = g.float().contiguous()
-            _call("pair_loss_bwd", {"bytes": 36.0 * tx.numel() / 3, "flops": 50.0 * ctx.pairs}, lib.shb_pair_loss_bwd, _p(tx),
-                  _p(rec), _p(kps), _p(lay.idx), _p(lay.gptr), _p(lay.bone), _p(lay.wmode), _p(scale) if ctx.has_scale else None,
-                  ctx.thr, ctx.rel, _p(gs), _p(grec), _p(ws), ws.numel(), B, V, kps.shape[1], lay.G, lay.max_rows, _stream())
+            grec = torch.empty_like(gacc)
+            gs = g.detach().float().contiguous()
+            _call("pair_loss_bwd", {"bytes": 24.0 * B * V}, lib.shb_pair_loss_bwd, _p(gacc), _p(lay.idx), _p(lay.gptr), _p(gs),
+                  _p(grec), _p(ws), ws.numel(), B, V, lay.G, lay.max_rows, _stream())
             _count()
         return None, grec, None, None, None, None, None
 
