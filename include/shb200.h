@@ -200,6 +200,11 @@ int shb_adam_tick(float* step, void* stream);
 int shb_adam_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v, void* const* shadow,
                   const int64_t* numel, const float* step, double lr, double beta1, double beta2, float eps, float weight_decay,
                   void* stream);
+/* Same step with per-tensor gradient dtypes: g_is_bf16[k] != 0 (HOST array, or NULL = all fp32) marks g[k] as a bf16 tensor
+ * (a data-parallel gradient bucket that was reduced in bf16; 8-byte aligned). */
+int shb_adam_step_mixed(int count, float* const* p, const void* const* g, const uint8_t* g_is_bf16, float* const* m,
+                        float* const* v, void* const* shadow, const int64_t* numel, const float* step, double lr, double beta1,
+                        double beta2, float eps, float weight_decay, void* stream);
 int shb_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 #ifdef __cplusplus

@@ -14,11 +14,12 @@ constexpr int AD_CHUNK = 8192;   // elements per CTA-iteration
 
 struct AdamTable {
   float* p[AD_MAX_TENSORS];
-  const float* g[AD_MAX_TENSORS];
+  const void* g[AD_MAX_TENSORS];           // fp32, or bf16 where g_bf16[i] (a gradient bucket reduced in bf16)
   float* m[AD_MAX_TENSORS];
   float* v[AD_MAX_TENSORS];
   __nv_bfloat16* shadow[AD_MAX_TENSORS];   // or null
   long long n[AD_MAX_TENSORS];
+  unsigned char g_bf16[AD_MAX_TENSORS];
   int chunk_start[AD_MAX_TENSORS + 1];     // prefix sum of ceil(n / AD_CHUNK)
   int count;
 };
@@ -46,14 +47,23 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const floa
     const long long off = (long long)(c - t.chunk_start[ti]) * AD_CHUNK;
     const long long n = t.n[ti] - off < AD_CHUNK ? t.n[ti] - off : AD_CHUNK;
     float* p = t.p[ti] + off;
-    const float* g = t.g[ti] + off;
+    const bool gb16 = t.g_bf16[ti] != 0;
+    const float* g = reinterpret_cast<const float*>(t.g[ti]) + (gb16 ? 0 : off);
+    const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(t.g[ti]) + off;
     float* m = t.m[ti] + off;
     float* v = t.v[ti] + off;
     __nv_bfloat16* sh = t.shadow[ti] != nullptr ? t.shadow[ti] + off : nullptr;
     const long long n4 = n & ~3LL;
     for (long long i = (long long)threadIdx.x * 4; i < n4; i += 256 * 4) {
       float4 pp = *reinterpret_cast<const float4*>(p + i);
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i));
+      float4 gg;
+      if (gb16) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(gh + i));
+        gg = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                         __uint_as_float(raw.y & 0xffff0000u));
+      } else {
+        gg = __ldg(reinterpret_cast<const float4*>(g + i));
+      }
       float4 mm = *reinterpret_cast<const float4*>(m + i);
       float4 vv = *reinterpret_cast<const float4*>(v + i);
       float* pa = reinterpret_cast<float*>(&pp);
@@ -74,7 +84,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const floa
       if (sh != nullptr) Io<__nv_bfloat16>::st4(sh + i, pa);
     }
     for (long long i = n4 + threadIdx.x; i < n; i += 256) {
-      const float gk = g[i] + wd * p[i];
+      const float gk = (gb16 ? __bfloat162float(gh[i]) : g[i]) + wd * p[i];
       const float mk = m[i] + omb1 * (gk - m[i]);
       const float vk = b2 * v[i] + omb2 * gk * gk;
       const float pk = p[i] - step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
@@ -109,9 +119,9 @@ int shb_adam_tick(float* step, void* stream) {
   return 0;
 }
 
-int shb_adam_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v, void* const* shadow,
-                  const int64_t* numel, const float* step, double lr, double beta1, double beta2, float eps, float weight_decay,
-                  void* stream) {
+int shb_adam_step_mixed(int count, float* const* p, const void* const* g, const uint8_t* g_is_bf16, float* const* m,
+                        float* const* v, void* const* shadow, const int64_t* numel, const float* step, double lr, double beta1,
+                        double beta2, float eps, float weight_decay, void* stream) {
   if (count <= 0 || !p || !g || !m || !v || !numel || !step) return SHB_E_ARG;
   for (int base = 0; base < count; base += AD_MAX_TENSORS) {
     AdamTable t{};
@@ -122,6 +132,7 @@ int shb_adam_step(int count, float* const* p, const float* const* g, float* cons
       if (!p[k] || !g[k] || !m[k] || !v[k] || numel[k] <= 0) return SHB_E_ARG;
       if ((((uintptr_t)p[k] | (uintptr_t)g[k] | (uintptr_t)m[k] | (uintptr_t)v[k]) & 15) != 0) return SHB_E_ARG;
       t.p[i] = p[k]; t.g[i] = g[k]; t.m[i] = m[k]; t.v[i] = v[k];
+      t.g_bf16[i] = (g_is_bf16 != nullptr && g_is_bf16[k]) ? 1 : 0;
       t.shadow[i] = shadow ? (__nv_bfloat16*)shadow[k] : nullptr;
       t.n[i] = numel[k];
       t.chunk_start[i + 1] = t.chunk_start[i] + (int)((numel[k] + AD_CHUNK - 1) / AD_CHUNK);
@@ -132,6 +143,13 @@ int shb_adam_step(int count, float* const* p, const float* const* g, float* cons
     SHB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int shb_adam_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v, void* const* shadow,
+                  const int64_t* numel, const float* step, double lr, double beta1, double beta2, float eps, float weight_decay,
+                  void* stream) {
+  return shb_adam_step_mixed(count, p, reinterpret_cast<const void* const*>(g), nullptr, m, v, shadow, numel, step, lr, beta1,
+                             beta2, eps, weight_decay, stream);
 }
 
 int shb_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {

@@ -10,6 +10,13 @@ shards are equal).  Gradients live in four flat fp32 buckets ordered by when bac
 Each bucket's all-reduce is launched from an autograd post-accumulate hook the moment its last gradient lands, so
 the two 57 MB FC buckets travel while the rest of the backward is still computing (the decoder-side one starts a whole
 FC backward earlier than a single 114 MB bucket would).  ``finish()`` joins before the optimizer.
+
+Gradient sinks (``sink_dtype``): a parameter the model lists in ``direct_grad_params()`` (the two FC weights in bf16 mode)
+gets a bucket of its own that the weight-gradient GEMM writes DIRECTLY (functions.LinearShadowFn) -- no zero-fill of the
+bucket, no read-modify-write accumulate pass by autograd (together 4x the bucket size in HBM traffic per step) -- and that
+may be bf16, halving the bytes on NVLink.  Such a gradient never becomes ``p.grad`` (torch requires grad dtype == param dtype):
+the optimizer takes it from ``GradSync.sinks`` (``optim.Adam.step(grads=sync.grad_map())``).  One backward per ``reset()``:
+a sink is overwritten, not accumulated.
 """
 import torch
 import torch.distributed as dist
@@ -53,10 +60,22 @@ def _bucket_of(name):
     return 3
 
 
+class _Sink:
+    """Direct destination of one parameter's gradient: the producing kernel writes `buf`, then calls ready()."""
+
+    __slots__ = ("buf", "_sync", "_bucket")
+
+    def __init__(self, buf, sync, bucket):
+        self.buf, self._sync, self._bucket = buf, sync, bucket
+
+    def ready(self):
+        self._sync._launch(self._bucket)
+
+
 class GradSync:
     """Flat-bucket gradient all-reduce overlapped with backward."""
 
-    def __init__(self, model, process_group=None, comm_sms=0):
+    def __init__(self, model, process_group=None, comm_sms=0, sink_dtype=None):
         self.pg = process_group
         self.comm_sms = int(comm_sms)   # SMs kept free of persistent kernels while a large bucket is being reduced
         self._capped = False
@@ -67,10 +86,25 @@ class GradSync:
         self._params = [p for _, p in named]
         self.buckets = []
         self._handles = []
+        self.sinks = {}   # parameter -> _Sink
+        for p in self._params:  # a sink left by an earlier GradSync of this model must not outlive it
+            if hasattr(p, "_shb_grad_sink"):
+                del p._shb_grad_sink
         if self.world == 1:
             return  # nothing to exchange: no flat buckets, gradients are plain per-parameter tensors (reset() drops them)
+        direct = []
+        if sink_dtype is not None and hasattr(model, "direct_grad_params"):
+            if sink_dtype not in (torch.float32, torch.bfloat16):
+                raise TypeError("gradient sinks are float32 or bfloat16")
+            direct = [p for p in model.direct_grad_params() if p.requires_grad]
         for b in range(N_BUCKETS):
-            members = [(n, p) for n, p in named if _bucket_of(n) == b]
+            for n, p in named:  # a sink is a bucket of its own, placed where its parameter's bucket would be
+                if _bucket_of(n) == b and any(p is q for q in direct):
+                    flat = torch.zeros(p.numel(), dtype=sink_dtype, device=p.device)
+                    bucket = {"flat": flat, "params": [p], "pending": 0, "work": None, "sink": True}
+                    self.buckets.append(bucket)
+                    self.sinks[p] = p._shb_grad_sink = _Sink(flat.view_as(p), self, bucket)
+            members = [(n, p) for n, p in named if _bucket_of(n) == b and not any(p is q for q in direct)]
             if not members:
                 continue
             # every member starts on a 16-byte boundary (the optimizer kernel moves float4s); the padding stays zero
@@ -80,21 +114,29 @@ class GradSync:
             for _, p in members:
                 p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
                 off += (p.numel() + 3) // 4 * 4
-            bucket = {"flat": flat, "params": [p for _, p in members], "pending": 0, "work": None}
+            bucket = {"flat": flat, "params": [p for _, p in members], "pending": 0, "work": None, "sink": False}
             self.buckets.append(bucket)
             for _, p in members:
                 p.register_post_accumulate_grad_hook(self._make_hook(bucket))
         self.reset()
 
+    def _launch(self, bucket):
+        bucket["pending"] = 0
+        op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+        bucket["work"] = dist.all_reduce(bucket["flat"], op=op, group=self.pg, async_op=True)
+        if self.comm_sms > 0 and bucket["flat"].numel() >= (1 << 20) and not self._capped:
+            self._cap(True)  # kernels enqueued from here to finish() leave room for NCCL's CTAs
+
     def _make_hook(self, bucket):
         def hook(_param):
             bucket["pending"] -= 1
             if bucket["pending"] == 0 and self.world > 1:
-                op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
-                bucket["work"] = dist.all_reduce(bucket["flat"], op=op, group=self.pg, async_op=True)
-                if self.comm_sms > 0 and bucket["flat"].numel() >= (1 << 20) and not self._capped:
-                    self._cap(True)  # kernels enqueued from here to finish() leave room for NCCL's CTAs
+                self._launch(bucket)
         return hook
+
+    def grad_map(self):
+        """{parameter: reduced gradient} of the sink parameters (for optim.Adam.step(grads=...)); empty without sinks."""
+        return {p: s.buf for p, s in self.sinks.items()}
 
     def _cap(self, on):
         from ._capi import check, lib
@@ -109,7 +151,8 @@ class GradSync:
                 p.grad = None
             return
         for b in self.buckets:
-            b["flat"].zero_()
+            if not b["sink"]:
+                b["flat"].zero_()   # autograd accumulates into these; a sink is overwritten by its producer
             b["pending"] = len(b["params"])
             b["work"] = None
 

@@ -404,6 +404,7 @@ class LinearShadowFn(torch.autograd.Function):
     def forward(ctx, x, w, b, w_sh, b_sh):
         ctx.save_for_backward(x, w_sh)
         ctx.has_bias = b is not None
+        ctx.w_param = w
         return torch.addmm(b_sh, x, w_sh.t()) if b is not None else torch.mm(x, w_sh.t())
 
     @staticmethod
@@ -413,7 +414,17 @@ class LinearShadowFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.mm(g, w_sh)
         if ctx.needs_input_grad[1]:
-            gw = torch.mm(g.t(), x, out_dtype=torch.float32)
+            sink = getattr(ctx.w_param, "_shb_grad_sink", None)
+            if sink is not None:
+                # data-parallel run: the GEMM writes the weight gradient straight into its (fp32 or bf16) all-reduce bucket --
+                # no zero-fill, no accumulate pass, no cast -- and the bucket goes on the wire at once (dp.GradSync)
+                if sink.buf.dtype == g.dtype:
+                    torch.mm(g.t(), x, out=sink.buf)
+                else:
+                    torch.mm(g.t(), x, out_dtype=sink.buf.dtype, out=sink.buf)
+                sink.ready()
+            else:
+                gw = torch.mm(g.t(), x, out_dtype=torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = torch.sum(g, 0, dtype=torch.float32)
         return gx, gw, gb, None, None

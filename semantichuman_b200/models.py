@@ -241,6 +241,13 @@ class _SpiralTrunk(nn.Module):
                 self._shadow_of(p)
         return self._shadows
 
+    def direct_grad_params(self):
+        """Parameters whose gradient GEMM can write straight into a data-parallel bucket (dp.GradSync sinks): the two FC
+        weights, in bf16 mode (fp32 mode runs them through nn.Linear's own autograd)."""
+        if self.compute_dtype != torch.bfloat16:
+            return []
+        return [p for n, p in self.named_parameters() if n in ("fc_latent_enc.weight", "fc_latent_dec.weight")]
+
     def set_compute_dtype(self, dtype):
         """torch.float32 (default; every operand split into bf16 hi + lo, three tensor-core products per term, fp32
         accumulation: 1e-4 parity) or torch.bfloat16 (bf16 activations and operands, fp32 accumulation, fp32 master

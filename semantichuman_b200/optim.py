@@ -31,6 +31,7 @@ class Adam:
         n = len(self.params)
         self._arr = {k: (ctypes.c_void_p * n)() for k in "pgmvs"}
         self._numel = (ctypes.c_int64 * n)()
+        self._gbf16 = (ctypes.c_uint8 * n)()
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -40,15 +41,22 @@ class Adam:
                 p.grad.zero_()
 
     @torch.no_grad()
-    def step(self):
+    def step(self, grads=None):
+        """`grads`: optional {parameter: gradient tensor} that takes precedence over ``p.grad`` -- the data-parallel
+        gradient sinks of dp.GradSync (fp32 or bf16 buckets written by the producing GEMM and reduced in place)."""
         k = 0
         live = []
         for i, p in enumerate(self.params):
-            g = p.grad
+            g = grads.get(p) if grads else None
+            if g is None:
+                g = p.grad
             if g is None:
                 continue
-            if g.dtype != torch.float32 or not g.is_contiguous():
+            if g.shape != p.shape:
+                raise ValueError("gradient shape does not match its parameter")
+            if g.dtype not in (torch.float32, torch.bfloat16) or not g.is_contiguous():
                 g = g.float().contiguous()
+            self._gbf16[k] = 1 if g.dtype == torch.bfloat16 else 0
             live.append((p, g))  # keeps a converted gradient alive until the launch is enqueued
             sh = self.shadows.get(p)
             self._arr["p"][k], self._arr["g"][k] = p.data_ptr(), g.data_ptr()
@@ -60,9 +68,9 @@ class Adam:
             return
         st = _stream()
         check(lib.shb_adam_tick(self.step_count.data_ptr(), st), "shb_adam_tick")
-        check(lib.shb_adam_step(k, self._arr["p"], self._arr["g"], self._arr["m"], self._arr["v"], self._arr["s"], self._numel,
-                                self.step_count.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                st), "shb_adam_step")
+        check(lib.shb_adam_step_mixed(k, self._arr["p"], self._arr["g"], self._gbf16, self._arr["m"], self._arr["v"],
+                                      self._arr["s"], self._numel, self.step_count.data_ptr(), self.lr, self.betas[0],
+                                      self.betas[1], self.eps, self.weight_decay, st), "shb_adam_step_mixed")
         _count(1 + (k + 31) // 32)
         for p, _ in live:  # the kernel wrote through raw pointers: tell autograd / the shadow cache
             torch.autograd.graph.increment_version(p)

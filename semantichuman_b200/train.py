@@ -17,9 +17,14 @@ from .optim import Adam
 
 
 class TrainStep:
-    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False, comm_sms=0):
+    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False, comm_sms=0, grad_comm_dtype="auto"):
+        """`grad_comm_dtype` (multi-process runs only): dtype of the gradient sinks of the two FC weights (dp.GradSync) --
+        "auto": bfloat16 when the model computes in bf16 (the compute dtype must be set before this constructor), none in
+        fp32 mode (every gradient travels in fp32 through p.grad); or torch.float32 / torch.bfloat16 / None explicitly."""
         self.model = model
-        self.sync = GradSync(model, comm_sms=comm_sms)
+        if grad_comm_dtype == "auto":
+            grad_comm_dtype = torch.bfloat16 if getattr(model, "compute_dtype", None) == torch.bfloat16 else None
+        self.sync = GradSync(model, comm_sms=comm_sms, sink_dtype=grad_comm_dtype)
         self.graph_enabled = bool(graph)
         # own multi-tensor Adam (device-side step count: replayable; writes the bf16 weight shadows in the same pass)
         shadows = model.shadow_map() if hasattr(model, "shadow_map") else None
@@ -38,7 +43,7 @@ class TrainStep:
         loss.backward()
         self.sync.finish()
         if self.optim is not None:
-            self.optim.step()
+            self.optim.step(grads=self.sync.grad_map())
         return loss
 
     def capture(self, example_x, warmup=3):

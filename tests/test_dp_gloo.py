@@ -33,6 +33,68 @@ class _Toy(torch.nn.Module):
         return self.dconv[0].conv(x)
 
 
+class _ToySink(_Toy):
+    """The two FC layers run through functions.LinearShadowFn (plain torch GEMMs, so it runs on CPU) and offer their weights
+    as direct gradient sinks, as the autoencoder does in bf16 mode."""
+
+    def direct_grad_params(self):
+        return [self.fc_latent_enc.weight, self.fc_latent_dec.weight]
+
+    def forward(self, x):
+        from semantichuman_b200.functions import LinearShadowFn
+
+        for c in self.conv:
+            x = torch.nn.functional.elu(c.conv(x))
+        for layer in (self.fc_latent_enc, self.fc_latent_dec):
+            x = LinearShadowFn.apply(x, layer.weight, layer.bias, layer.weight.detach(), layer.bias.detach())
+        return self.dconv[0].conv(x)
+
+
+def _sink_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semantichuman_b200.dp import GradSync, shard_batch
+
+    model = _ToySink()
+    sync = GradSync(model, sink_dtype=torch.float32)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 6, generator=g)
+    lo, hi = shard_batch(8, rank, world)
+    for _ in range(2):  # a sink is overwritten every step, never zeroed
+        sync.reset()
+        xs = x[lo:hi]
+        (model(xs) - xs).abs().mean().backward()
+        sync.finish()
+    gm = sync.grad_map()
+    grads = [(gm[p] if p in gm else p.grad).detach().clone().numpy() for p in model.parameters()]
+    no_pgrad = all(p.grad is None for p in gm)
+    q.put((rank, grads, len(sync.buckets), no_pgrad))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_sinks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sink_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    model = _Toy()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 6, generator=g)
+    (model(x) - x).abs().mean().backward()
+    full = [p.grad for p in model.parameters()]
+    for rank, grads, nb, no_pgrad in got:
+        assert nb == 6 and no_pgrad   # 4 flat buckets + one sink bucket per FC weight; a sink never becomes p.grad
+        for a, b in zip(grads, full):
+            assert torch.allclose(torch.from_numpy(a), b, atol=1e-6, rtol=1e-5)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

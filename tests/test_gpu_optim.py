@@ -46,6 +46,29 @@ def test_adam_trajectory_matches_torch(wd):
     assert float(opt2.step_count) == 25.0 and torch.equal(opt2.exp_avg[2], opt.exp_avg[2])
 
 
+def test_adam_takes_bf16_gradients_from_a_grad_map():
+    """The data-parallel gradient sinks (dp.GradSync) hand the optimizer bf16 tensors that are not p.grad."""
+    from semantichuman_b200.optim import Adam
+
+    shapes = [(256, 1031), (33, 5), (8200,)]
+    mine, ref = _params(5, shapes), _params(5, shapes)
+    opt, topt = Adam(mine, lr=1e-3, weight_decay=5e-5), torch.optim.Adam(ref, lr=1e-3, weight_decay=5e-5)
+    g = torch.Generator().manual_seed(6)
+    for _ in range(10):
+        gmap = {}
+        for i, (a, b) in enumerate(zip(mine, ref)):
+            gr = torch.randn(a.shape, generator=g).to(DEV)
+            if i != 1:   # tensors 0 and 2 arrive in bf16 through the map, tensor 1 through p.grad in fp32
+                gmap[a] = gr.bfloat16()
+                a.grad, b.grad = None, gr.bfloat16().float()
+            else:
+                a.grad, b.grad = gr.clone(), gr.clone()
+        opt.step(grads=gmap)
+        topt.step()
+    for a, b in zip(mine, ref):
+        assert relerr(a, b) < 1e-6
+
+
 def test_adam_step_replays_in_a_cuda_graph():
     from semantichuman_b200.optim import Adam
 
