@@ -189,6 +189,31 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
                    size_t workspace_bytes, int B, int rows_out, int S, int Cin, int Cin_p, int Cout, int Cout_p, int skip_last,
                    int planes, void* stream);
 
+/* ---- Shared-source groups of a SpiralConv pass (host, CPU).  `ptr` (rows_dst+1) / `ent` ((source row << 5) | slot) are the
+ * entry lists of a pass (forward: models.py:42's x[:, spiral_idx] per output row; input gradient: the inverse-spiral lists).
+ * Destination rows whose lists share sources are clustered (greedy, deterministic) into groups of <= R rows; per group the
+ * distinct sources are listed once, in ascending order, each with the (destination, slot) pairs that use it.  Output is the
+ * program shb_slab_gconv runs:
+ *   gptr  (n_groups+1)  record range of every group
+ *   recs  (n_records*48) records of <= SPS sources and <= 32 pairs:  [0] = n_src | n_pairs << 4 | first << 10 | last << 11,
+ *         [1..8] source rows, [16..47] pairs = slab-in-record | dest-in-group << 3 | first-pair-of-dest << 8 | slot << 9
+ *   gdst  (n_groups*R)  destination rows (-1: absent),  gmask (n_groups) bit i: destination i has no entries.
+ * Two calls: with gptr == recs == gdst == gmask == NULL it only returns the counts; the second call fills the arrays. */
+int shb_build_conv_groups(const int32_t* ptr, const int32_t* ent, int rows_dst, int rows_src, int R, int SPS, int32_t* n_groups,
+                          int32_t* n_records, int32_t* gptr, int32_t* recs, int32_t* gdst, uint32_t* gmask);
+
+/* ---- SpiralConv forward / input gradient with shared-source groups (shb_slab_gconv.cu): same contract as shb_slab_conv,
+ * driven by the group program of shb_build_conv_groups instead of per-row entry lists.  A tile is one group x one 128-sample
+ * chunk; every distinct source slab of the group is loaded once and feeds all (destination, slot) pairs that use it, each
+ * destination accumulating in its own TMEM columns.  shb_slab_gconv_plan reports the largest group size R and the slabs per
+ * record SPS the kernel's ring takes for a layer shape (SHB_E_UNSUPPORTED: use shb_slab_conv); the program passed to
+ * shb_slab_gconv must have been built with that SPS and R <= R_max. */
+int shb_slab_gconv_plan(int S, int Cs, int Cd, int planes, int* R_max, int* SPS);
+int shb_slab_gconv(const void* src, const int32_t* gptr, const int32_t* recs, const int32_t* gdst, const uint32_t* gmask,
+                   int n_groups, int R, int SPS, const void* w_img, const float* bias, void* dst, const void* ymul, int B,
+                   int rows_dst, int S, int Cs, int Cd, int Cd_real, int act, int act_mul, int zero_last, int planes,
+                   void* stream);
+
 /* ---- Optimizer step (main.py:262: torch.optim.Adam(params, lr, weight_decay), defaults betas (0.9, 0.999), eps 1e-8):
  * g += weight_decay * p;  m = lerp(m, g, 1-beta1);  v = beta2 v + (1-beta2) g^2;
  * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps),   t = *step (device scalar, advanced by shb_adam_tick

@@ -1,5 +1,6 @@
 """Time one SpiralConv layer of the slab path (fwd / wgrad / dgrad) at full size, L2 flushed between launches; also the
-target command for ncu captures.   LAYER=lvl,cin,cout  B=256  DT=bf16|fp32  REORDER=1  OUT=kept|all"""
+target command for ncu captures.   LAYER=lvl,cin,cout  B=256  DT=bf16|fp32  REORDER=1  GCONV=0 (row-per-tile kernel only)
+TRACE=fwd|all (library built with SHB_NVCC_FLAGS=-DSHB_GCONV_TRACE: role timeline of the last grouped-conv launch)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,6 +10,7 @@ from semantichuman_b200.indexing import locality_order, normalise_spiral
 from tests.golden.loader import Hierarchy
 
 dev = "cuda:0"
+slab.GCONV_ENABLED = os.environ.get("GCONV", "1") != "0"
 B = int(os.environ.get("B", "256")); reps = int(os.environ.get("REPS", "5"))
 planes = 1 if os.environ.get("DT", "bf16") == "bf16" else 2
 h = Hierarchy(os.environ.get("HIER", "2222"))
@@ -49,11 +51,13 @@ for spec in layers.split(";"):
         import ctypes
         from semantichuman_b200._capi import lib as _lib
         raw = ctypes.CDLL(_lib._name)
-        buf = (ctypes.c_longlong * (148 * 16))()
+        buf = (ctypes.c_longlong * (296 * 16))()
         torch.cuda.synchronize()
-        raw.shb_slab_trace_read(buf)
-        a = np.array(buf[:]).reshape(148, 16).astype(np.float64)
-        names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-tmem", "mma total", "epi wait-acc", "epi total", "tiles", "prod lb+sync", "prod expect", "prod bulk", "mma issue", "mma commit", "epi tmem-ld", "epi fence+arrive", "epi math+store"]
-        print("  trace of the LAST slab_conv launch, mean over CTAs, cycles per tile:")
+        raw.shb_gconv_trace_read(buf)
+        a = np.array(buf[:]).reshape(296, 16).astype(np.float64)
+        a = a[a[:, 7] > 0]
+        names = ["prod0 wait-empty", "prod0 total", "mma wait-full", "mma wait-acc-free", "mma total", "epi wait-acc", "epi total",
+                 "tiles", "mma issue", "prod0 records"]
+        print(f"  trace of the LAST slab_gconv launch ({len(a)} CTAs), mean cycles per CTA:")
         for i, n in enumerate(names):
-            print(f"    {n:18s} {a[:, i].mean() / max(a[:, 7].mean(), 1):10.0f}" if i != 7 else f"    {n:18s} {a[:, i].mean():10.1f}")
+            print(f"    {n:18s} {a[:, i].mean():10.0f}   (min {a[:, i].min():.0f}, max {a[:, i].max():.0f})")

@@ -42,6 +42,9 @@ SIGNATURES = {
     "shb_slab_weight_images": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
     "shb_slab_conv_supported": (c_int, [c_int] * 4),
     "shb_slab_conv": (c_int, [c_vp] * 7 + [c_int] * 10 + [c_vp]),
+    "shb_build_conv_groups": (c_int, [c_vp, c_vp] + [c_int] * 4 + [c_vp] * 6),
+    "shb_slab_gconv_plan": (c_int, [c_int] * 4 + [c_vp, c_vp]),
+    "shb_slab_gconv": (c_int, [c_vp] * 5 + [c_int] * 3 + [c_vp] * 4 + [c_int] * 10 + [c_vp]),
     "shb_slab_wgrad_supported": (c_int, [c_int] * 4),
     "shb_slab_wgrad_workspace": (c_size, [c_int] * 4),
     "shb_slab_wgrad": (c_int, [c_vp] * 6 + [c_size] + [c_int] * 9 + [c_vp]),

@@ -43,6 +43,39 @@ def build_inverse_spiral_csr(table, rows_in):
     return rowptr, slots
 
 
+def build_conv_groups(ptr, ent, rows_dst, rows_src, R, SPS):
+    """Shared-source group program of a SpiralConv pass (shb_build_conv_groups): host arrays (gptr, recs, gdst, gmask)."""
+    import ctypes
+
+    ptr, ent = _i32(ptr), _i32(ent)
+    ng, nr = ctypes.c_int32(0), ctypes.c_int32(0)
+    args = (ptr.ctypes.data, ent.ctypes.data, int(rows_dst), int(rows_src), int(R), int(SPS), ctypes.addressof(ng),
+            ctypes.addressof(nr))
+    check(lib.shb_build_conv_groups(*args, None, None, None, None), "shb_build_conv_groups")
+    gptr = np.empty(ng.value + 1, np.int32)
+    recs = np.empty(nr.value * 48, np.int32)
+    gdst = np.empty(ng.value * R, np.int32)
+    gmask = np.empty(ng.value, np.uint32)
+    check(lib.shb_build_conv_groups(*args, gptr.ctypes.data, recs.ctypes.data, gdst.ctypes.data, gmask.ctypes.data),
+          "shb_build_conv_groups")
+    return gptr, recs, gdst, gmask
+
+
+class GroupProgram:
+    """Device-resident group program of one pass of one geometry (see build_conv_groups)."""
+
+    __slots__ = ("gptr", "recs", "gdst", "gmask", "n_groups", "n_records", "R", "SPS", "n_loads")
+
+    def __init__(self, ptr, ent, rows_dst, rows_src, R, SPS, device):
+        gptr, recs, gdst, gmask = build_conv_groups(ptr, ent, rows_dst, rows_src, R, SPS)
+        self.n_groups, self.n_records, self.R, self.SPS = len(gmask), len(recs) // 48, int(R), int(SPS)
+        self.n_loads = int((recs.reshape(-1, 48)[:, 0] & 15).sum())  # slab loads per batch chunk (vs. one per entry ungrouped)
+        self.gptr = torch.from_numpy(gptr).to(device)
+        self.recs = torch.from_numpy(recs).to(device)
+        self.gdst = torch.from_numpy(gdst).to(device)
+        self.gmask = torch.from_numpy(gmask.view(np.int32)).to(device)
+
+
 def dense_to_csr(dense):
     """fp32 dense (rows, cols) -> (rowptr, colidx, vals) host arrays, exact zeros dropped."""
     d = np.ascontiguousarray(dense, dtype=np.float32)
@@ -120,8 +153,9 @@ class SpiralGeometry:
         # forward lists
         keep = np.ones(flat.shape, bool) if not self.src_dummy_zero else flat != dummy
         counts = keep.reshape(self.rows_out, S).sum(1)
-        self.ptr_f = self._dev(np.concatenate([[0], np.cumsum(counts)]))
-        self.ent_f = self._dev(((flat << 5) | slots)[keep])
+        self._host_f = (_i32(np.concatenate([[0], np.cumsum(counts)])), _i32(((flat << 5) | slots)[keep]))
+        self.ptr_f = self._dev(self._host_f[0])
+        self.ent_f = self._dev(self._host_f[1])
         # backward lists: the canonical inverse CSR (flat positions j*S+s, ascending per source row), then the dead
         # entries taken out
         rowptr, pos = build_inverse_spiral_csr(table, self.rows_in)
@@ -148,10 +182,26 @@ class SpiralGeometry:
             self.dummy_split = (T, self._dev(bounds), self._dev(ents), self._dev(np.array([0, T])), self._dev(np.arange(T)),
                                 torch.ones(T, dtype=torch.float32, device=self.device))
         counts_b = np.bincount(src_of[live], minlength=self.rows_in)
-        self.ptr_b = self._dev(np.concatenate([[0], np.cumsum(counts_b)]))
-        self.ent_b = self._dev(((jj << 5) | ss)[live])
+        self._host_b = (_i32(np.concatenate([[0], np.cumsum(counts_b)])), _i32(((jj << 5) | ss)[live]))
+        self.ptr_b = self._dev(self._host_b[0])
+        self.ent_b = self._dev(self._host_b[1])
+        self._programs = {}
         self.table = torch.from_numpy(table).to(self.device)
         self.n_fwd_entries, self.n_bwd_entries = int(counts.sum()), int(counts_b.sum())
+
+    def group_program(self, backward, R, SPS):
+        """Shared-source group program of the forward (destinations = output rows) or input-gradient (destinations = source
+        rows) pass for group size R and SPS slabs per record; built on first use, cached."""
+        key = (bool(backward), int(R), int(SPS))
+        prog = self._programs.get(key)
+        if prog is None:
+            if len(self._programs) > 8:
+                self._programs.clear()
+            ptr, ent = self._host_b if backward else self._host_f
+            rows_dst, rows_src = (self.rows_in, self.rows_out) if backward else (self.rows_out, self.rows_in)
+            prog = GroupProgram(ptr, ent, rows_dst, rows_src, R, SPS, self.device)
+            self._programs[key] = prog
+        return prog
 
     def _dev(self, a):
         a = np.ascontiguousarray(a, dtype=np.int64)

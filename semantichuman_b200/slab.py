@@ -173,6 +173,45 @@ def pool(s, pm):
     return Slab(t, pm.rows_out, s.B, s.C, s.Cp, s.planes, 0, False)
 
 
+def _gconv_program(geom, backward, S, Cs, Cd, planes, B):
+    """Group program for one pass if the grouped kernel (csrc/shb_slab_gconv.cu) takes this layer shape, else None.
+    Group size: the largest the accumulator allows (TMEM: 2 R pad16(Cd) <= 512 columns, 256 when two CTAs share an SM) that
+    still leaves every CTA a few tiles -- a group is one tile per 128-sample chunk."""
+    import ctypes
+
+    if not GCONV_ENABLED:
+        return None
+    rmax, sps = ctypes.c_int(0), ctypes.c_int(0)
+    if lib.shb_slab_gconv_plan(S, Cs, Cd, planes, ctypes.addressof(rmax), ctypes.addressof(sps)) != 0:
+        return None
+    R = rmax.value
+    rows_dst = geom.rows_in if backward else geom.rows_out
+    nb = (B + CHUNK - 1) // CHUNK
+    while R > 1 and (rows_dst + R - 1) // R * nb < _GCONV_MIN_TILES:
+        R //= 2
+    if R < 4:   # little sharing left to exploit, and the row-per-tile kernel has the leaner epilogue
+        return None
+    return geom.group_program(backward, R, sps.value)
+
+
+_GCONV_MIN_TILES = 592  # two tiles for each of 296 resident CTAs
+GCONV_ENABLED = True     # scripts/bench_slab_layer.py flips this to time the row-per-tile kernel on the same layers
+
+
+def _conv_pass(name, cmeta, geom, backward, src, img, bias, dst, ymul, B, rows_dst, S, Cs, Cd, Cd_real, act, act_mul,
+               zero_last, planes):
+    """One launch of the conv kernel family: the grouped kernel where it applies, else the row-per-tile kernel."""
+    prog = _gconv_program(geom, backward, S, Cs, Cd, planes, B)
+    if prog is not None:
+        _call(name, cmeta, lib.shb_slab_gconv, _p(src), _p(prog.gptr), _p(prog.recs), _p(prog.gdst), _p(prog.gmask),
+              prog.n_groups, prog.R, prog.SPS, _p(img), _p(bias), _p(dst), _p(ymul), B, rows_dst, S, Cs, Cd, Cd_real, act,
+              act_mul, zero_last, planes, _stream())
+    else:
+        ptr, ent = (geom.ptr_b, geom.ent_b) if backward else (geom.ptr_f, geom.ent_f)
+        _call(name, cmeta, lib.shb_slab_conv, _p(src), _p(ptr), _p(ent), _p(img), _p(bias), _p(dst), _p(ymul), B, rows_dst, S,
+              Cs, Cd, Cd_real, act, act_mul, zero_last, planes, _stream())
+
+
 class SlabConvFn(torch.autograd.Function):
     """y = mask * act(W . gather(x) + b) (models.py:34-53) on slab tensors.
 
@@ -206,8 +245,8 @@ class SlabConvFn(torch.autograd.Function):
         y = torch.empty(Slab.shape_for(geom.rows_out, B, cout_p, planes), dtype=torch.bfloat16, device=dev)
         tag = f"[{rows}>{geom.rows_out}x{S}x{C}>{cout}]"
         cmeta = fn._conv_meta(B, rows, geom.rows_out, S, C, cout, 2 * planes)
-        _call("slabconv_fwd" + tag, cmeta, lib.shb_slab_conv, _p(t), _p(geom.ptr_f), _p(geom.ent_f), _p(img_f), _p(b32), _p(y),
-              None, B, geom.rows_out, S, Cp, cout_p, cout, act, 0, int(geom.zero_last_row), planes, _stream())
+        _conv_pass("slabconv_fwd" + tag, cmeta, geom, False, t, img_f, b32, y, None, B, geom.rows_out, S, Cp, cout_p, cout, act,
+                   0, int(geom.zero_last_row), planes)
         _count(2)
         ctx.save_for_backward(t, img_b)
         ctx.geom, ctx.meta, ctx.tag, ctx.cmeta = geom, meta, tag, cmeta
@@ -238,8 +277,8 @@ class SlabConvFn(torch.autograd.Function):
                 gw = None
         if want_gx and ctx.needs_input_grad[0]:
             gx = torch.empty_like(t)
-            _call("slabconv_dgrad" + ctx.tag, ctx.cmeta, lib.shb_slab_conv, _p(gz), _p(geom.ptr_b), _p(geom.ent_b), _p(img_b), None,
-                  _p(gx), _p(t) if xact != 0 else None, B, rows, S, cout_p, Cp, C, 0, xact, int(xmasked), planes, _stream())
+            _conv_pass("slabconv_dgrad" + ctx.tag, ctx.cmeta, geom, True, gz, img_b, None, gx, t if xact != 0 else None, B, rows, S,
+                       cout_p, Cp, C, 0, xact, int(xmasked), planes)
             _count()
             if geom.dummy_split is not None and not xmasked:
                 T, sptr, sent, prow, pcol, pval = geom.dummy_split

@@ -24,8 +24,17 @@ class TrainStep:
         self.model = model
         if grad_comm_dtype == "auto":
             grad_comm_dtype = torch.bfloat16 if getattr(model, "compute_dtype", None) == torch.bfloat16 else None
-        self.sync = GradSync(model, comm_sms=comm_sms, sink_dtype=grad_comm_dtype)
         self.graph_enabled = bool(graph)
+        # The captured step runs on a side stream.  autograd's AccumulateGrad nodes (created, and kept alive, by the bucket
+        # hooks GradSync registers) remember the stream that was current at their creation and run there: created under the
+        # default stream they would fork every gradient accumulation -- and the all-reduce launched from its hook -- off the
+        # capture stream and join again at the end of backward.  So the hooks are registered under the capture stream.
+        self._side = torch.cuda.Stream() if (self.graph_enabled and next(model.parameters()).is_cuda) else None
+        if self._side is not None:
+            with torch.cuda.stream(self._side):
+                self.sync = GradSync(model, comm_sms=comm_sms, sink_dtype=grad_comm_dtype)
+        else:
+            self.sync = GradSync(model, comm_sms=comm_sms, sink_dtype=grad_comm_dtype)
         # own multi-tensor Adam (device-side step count: replayable; writes the bf16 weight shadows in the same pass)
         shadows = model.shadow_map() if hasattr(model, "shadow_map") else None
         self.optim = Adam(model.parameters(), lr=lr, weight_decay=weight_decay, shadows=shadows) if optimizer else None
@@ -54,7 +63,7 @@ class TrainStep:
         # warm-up and capture share one side stream: autograd's AccumulateGrad nodes (kept alive by the bucket hooks in
         # multi-process runs) remember the stream they were created on, and a mismatch would make the engine
         # synchronise with the default stream in the middle of the capture
-        side = torch.cuda.Stream()
+        side = self._side
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):

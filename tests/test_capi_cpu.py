@@ -231,3 +231,51 @@ def test_group_layout_host_logic():
         GroupLayout([np.array([7])], 7, 4, 8, True, "cpu")
     with pytest.raises(ValueError):
         enc.pack([torch.nn.Linear(5, 8)] * 3)
+
+
+@pytest.mark.parametrize("R,SPS", [(16, 4), (8, 8), (4, 2), (1, 1)])
+def test_conv_group_program_covers_every_entry_once(R, SPS):
+    """shb_build_conv_groups: the group program is a re-arrangement of the entry lists -- every (destination, slot, source)
+    triple exactly once, every destination in exactly one group, record limits and flags as the kernel expects them."""
+    from semantichuman_b200.indexing import build_conv_groups
+
+    rng = np.random.default_rng(R * 10 + SPS)
+    rows_dst, rows_src, S = 301, 280, 9
+    table = (np.arange(rows_dst)[:, None] * 7 // 8 + rng.integers(-6, 7, size=(rows_dst, S))).clip(0, rows_src - 1)
+    table[5] = rows_src - 1                       # one destination listing a single source S times
+    keep = rng.random((rows_dst, S)) < 0.85
+    keep[17] = False                              # a destination without entries
+    counts = keep.sum(1)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    slots = np.tile(np.arange(S), rows_dst).reshape(rows_dst, S)
+    ent = ((table.astype(np.int64) << 5) | slots)[keep].astype(np.int32)
+    gptr, recs, gdst, gmask = build_conv_groups(ptr, ent, rows_dst, rows_src, R, SPS)
+    rec = recs.reshape(-1, 48)
+    assert gptr[0] == 0 and gptr[-1] == len(rec) and (np.diff(gptr) >= 1).all()
+    got = []
+    for g in range(len(gmask)):
+        seen = set()
+        last_src = -1
+        for r in range(gptr[g], gptr[g + 1]):
+            w = rec[r]
+            ns, npair = w[0] & 15, (w[0] >> 4) & 63
+            assert ns <= SPS and npair <= 32
+            assert ((w[0] >> 10) & 1) == (r == gptr[g]) and ((w[0] >> 11) & 1) == (r == gptr[g + 1] - 1)
+            assert (np.diff(w[1:1 + ns]) >= 0).all() and (ns == 0 or w[1] >= last_src)   # ascending sources: fixed order
+            last_src = w[ns] if ns else last_src
+            used = set()
+            for pw in w[16:16 + npair]:
+                k, dl, first, sl = pw & 7, (pw >> 3) & 31, (pw >> 8) & 1, (pw >> 9) & 31
+                assert k < ns and dl < R and gdst[g * R + dl] >= 0
+                assert first == (dl not in seen)
+                seen.add(dl)
+                used.add(k)
+                got.append((int(gdst[g * R + dl]), int(sl), int(w[1 + k])))
+            assert used == set(range(ns))         # no slab is loaded without a pair that reads it
+        for i in range(R):
+            d = gdst[g * R + i]
+            if d >= 0:
+                assert bool((gmask[g] >> i) & 1) == (counts[d] == 0)
+    want = [(j, int(e & 31), int(e >> 5)) for j in range(rows_dst) for e in ent[ptr[j]:ptr[j + 1]]]
+    assert sorted(got) == sorted(want)
+    assert sorted(int(d) for d in gdst if d >= 0) == list(range(rows_dst))
