@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
-    ap.add_argument("--comm-sms", type=int, default=24,
+    ap.add_argument("--comm-sms", type=int, default=16,
                     help="N>1: CTAs NCCL may use = SMs the persistent kernels leave free while a gradient bucket is in flight; "
                          "0 = NCCL defaults, no reservation")
     ap.add_argument("--kernels-out", default=None, help="write the full per-kernel table of the instrumented pass here")

@@ -15,90 +15,127 @@ using namespace slab;
 
 // ---------------------------------------------------------------------------------------------- Pool
 // dst[r] = act'(ymul[r]) * sum_k vals[k] * src[colidx[k]]   for k in rowptr[r] .. rowptr[r+1];   dummy row optionally zeroed
-template <int P>
+//
+// A unit is one (row, chunk) slab (cut into nslice vector ranges when rows are few).  What bounds this kernel is the LENGTH OF
+// THE DEPENDENT LOAD CHAIN per unit, not bandwidth (first version: one entry at a time, index load -> data load, per vector:
+// 12 global-load latencies per unit, 30-40 % of HBM).  So: a unit's entries are fetched four at a time (indices and weights of
+// all four in flight together), the data loads of all four entries are issued back to back, and the next unit's row range is
+// requested before the current unit is processed: three latencies per unit (row range -> entries -> data).  One vector per
+// thread (VPT = 1): two per thread doubled the registers, halved the resident warps and measured 10 % slower.  Accumulation
+// stays in CSR order.
+template <int P, int VPT>
 __global__ void __launch_bounds__(256) slab_pool_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                         uint8_t* __restrict__ dst, const uint8_t* __restrict__ ymul, int NB,
                                                         int rows_out, int C, int act_mul, int zero_last, int nslice) {
-  const int nvec = C * 16;                  // 16-byte vectors per plane of a slab
-  const int vper = (nvec + nslice - 1) / nslice;   // a (row, chunk) unit is cut into nslice vector ranges when rows are few
+  const int nvec = C * 16;                         // 16-byte vectors per plane of a slab
+  const int vper = (nvec + nslice - 1) / nslice;   // vectors per slice
   const size_t slab_b = slab_bytes(C, P);
+  const size_t plane_b = (size_t)C * 256;
+  const size_t rstride = (size_t)NB * slab_b;
   const int units = rows_out * NB * nslice;
-  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+  int unit = blockIdx.x;
+  int k0 = 0, k1 = 0;
+  if (unit < units) {
+    const int r = unit / (nslice * NB);
+    k0 = __ldg(rowptr + r);
+    k1 = __ldg(rowptr + r + 1);
+  }
+  while (unit < units) {
     const int rq = unit / nslice, sl = unit - rq * nslice;
     const int r = rq / NB, q = rq - r * NB;
-    const int k0 = __ldg(rowptr + r), k1 = __ldg(rowptr + r + 1);
+    const int unit_n = unit + gridDim.x;
+    int n0 = 0, n1 = 0;
+    if (unit_n < units) {  // next unit's row range: in flight while this unit is processed
+      const int rn = unit_n / (nslice * NB);
+      n0 = __ldg(rowptr + rn);
+      n1 = __ldg(rowptr + rn + 1);
+    }
     const bool zero = zero_last && r == rows_out - 1;
-    uint8_t* d = dst + ((size_t)r * NB + q) * slab_b;
-    const uint8_t* y = ymul != nullptr ? ymul + ((size_t)r * NB + q) * slab_b : nullptr;
+    const size_t uoff = ((size_t)r * NB + q) * slab_b;
     const int v1 = (sl + 1) * vper < nvec ? (sl + 1) * vper : nvec;
-    for (int v = sl * vper + threadIdx.x; v < v1; v += blockDim.x) {
-      float acc[8];
+    for (int vb = sl * vper + threadIdx.x; vb < v1; vb += VPT * blockDim.x) {
+      const int vv[2] = {vb, vb + (int)blockDim.x};
+      const bool has2 = VPT == 2 && vv[1] < v1;
+      float acc[VPT][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int t = 0; t < VPT; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+      uint4 yraw[VPT][P];
+      if (ymul != nullptr && !zero) {  // act' operands: requested first, consumed last
+#pragma unroll
+        for (int t = 0; t < VPT; ++t)
+          if (t == 0 || has2) {
+            yraw[t][0] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + (size_t)vv[t] * 16));
+            if (P == 2) yraw[t][P - 1] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + plane_b + (size_t)vv[t] * 16));
+          }
+      }
       if (!zero) {
-        const uint8_t* sv = src + (size_t)q * slab_b + (size_t)v * 16;
-        const size_t rstride = (size_t)NB * slab_b;
-        int k = k0;
-        for (; k + 4 <= k1; k += 4) {  // four independent loads in flight per thread; accumulation stays in CSR order
-          uint4 raw[4][P];
+        const uint8_t* sq = src + (size_t)q * slab_b;
+        for (int kb = k0; kb < k1; kb += 4) {
+          int col[4];
           float w[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint8_t* s = sv + (size_t)__ldg(colidx + k + j) * rstride;
-            w[j] = __ldg(vals + k + j);
-            raw[j][0] = __ldg(reinterpret_cast<const uint4*>(s));
-            if (P == 2) raw[j][P - 1] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)C * 256));
+            const bool on = kb + j < k1;
+            col[j] = on ? __ldg(colidx + kb + j) : -1;
+            w[j] = on ? __ldg(vals + kb + j) : 0.f;
           }
+          uint4 raw[VPT][4][P];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x[8];
-            unpack8(raw[j][0], x);
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int t = 0; t < VPT; ++t)
+              if (col[j] >= 0 && (t == 0 || has2)) {
+                const uint8_t* s = sq + (size_t)col[j] * rstride + (size_t)vv[t] * 16;
+                raw[t][j][0] = __ldg(reinterpret_cast<const uint4*>(s));
+                if (P == 2) raw[t][j][P - 1] = __ldg(reinterpret_cast<const uint4*>(s + plane_b));
+              }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int t = 0; t < VPT; ++t)
+              if (col[j] >= 0 && (t == 0 || has2)) {
+                float x[8];
+                unpack8(raw[t][j][0], x);
+                if (P == 2) {
+                  float l[8];
+                  unpack8(raw[t][j][P - 1], l);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) x[i] += l[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(w[j], x[i], acc[t][i]);
+              }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < VPT; ++t)
+        if (t == 0 || has2) {
+          if (ymul != nullptr && !zero) {
+            float yy[8];
+            unpack8(yraw[t][0], yy);
             if (P == 2) {
               float l[8];
-              unpack8(raw[j][P - 1], l);
+              unpack8(yraw[t][P - 1], l);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] += l[i];
+              for (int i = 0; i < 8; ++i) yy[i] += l[i];
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[j], x[i], acc[i]);
+            act_bwd8(acc[t], yy, act_mul);
+          }
+          uint8_t* d = dst + uoff + (size_t)vv[t] * 16;
+          if (P == 1) {
+            *reinterpret_cast<uint4*>(d) = pack8(acc[t]);
+          } else {
+            uint4 hi, lo;
+            split8(acc[t], hi, lo);
+            *reinterpret_cast<uint4*>(d) = hi;
+            *reinterpret_cast<uint4*>(d + plane_b) = lo;
           }
         }
-        for (; k < k1; ++k) {
-          const float w = __ldg(vals + k);
-          const uint8_t* s = sv + (size_t)__ldg(colidx + k) * rstride;
-          float x[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(s)), x);
-          if (P == 2) {
-            float l[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(s + (size_t)C * 256)), l);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] += l[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, x[i], acc[i]);
-        }
-        if (y != nullptr) {
-          float yy[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(y + (size_t)v * 16)), yy);
-          if (P == 2) {
-            float l[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(y + (size_t)C * 256 + (size_t)v * 16)), l);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) yy[i] += l[i];
-          }
-          act_bwd8(acc, yy, act_mul);
-        }
-      }
-      if (P == 1) {
-        *reinterpret_cast<uint4*>(d + (size_t)v * 16) = pack8(acc);
-      } else {
-        uint4 hi, lo;
-        split8(acc, hi, lo);
-        *reinterpret_cast<uint4*>(d + (size_t)v * 16) = hi;
-        *reinterpret_cast<uint4*>(d + (size_t)C * 256 + (size_t)v * 16) = lo;
-      }
     }
+    unit = unit_n; k0 = n0; k1 = n1;
   }
 }
 
@@ -111,14 +148,23 @@ __global__ void __launch_bounds__(256) slab_from_rows_kernel(const T* __restrict
                                                              uint8_t* __restrict__ dst, const uint8_t* __restrict__ ymul, int B,
                                                              int R, int Cs, int Cp, int act_mul, int zero_last) {
   const int NB = num_chunks(B), ncc = Cp / 8;
-  const long long total = (long long)R * NB * ncc * CHUNK;
+  // Work item = (row r, channel group cc), cc fastest: consecutive items are consecutive in the caller's row-major tensor.
+  // A warp covers 8 items x 4 samples: row-major accesses are runs of 8 items (>= 96 B) per sample, slab accesses are runs
+  // of 4 samples (64 B) per item -- whole sectors on both sides (one thread per sample made the row-major side one
+  // 16-byte access per sector).
+  const long long items = (long long)R * ncc, iblocks = (items + 7) / 8;
+  const long long total = iblocks * 8 * CHUNK * NB;
   const size_t slab_b = slab_bytes(Cp, P);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int bl = (int)(i % CHUNK);
-    long long t = i / CHUNK;
-    const int cc = (int)(t % ncc);
-    t /= ncc;
-    const int q = (int)(t % NB), r = (int)(t / NB);
+    // (single-channel-group tensors -- the 3-channel ends -- keep one warp = 32 samples of one item: their row-major side is
+    // 12-byte pieces scattered by the vertex permutation either way, and the slab side then gets 512-byte runs)
+    const int il = ncc >= 8 ? (int)(i & 7) : (int)((i >> 7) & 7), bl = ncc >= 8 ? (int)((i >> 3) & (CHUNK - 1)) : (int)(i & (CHUNK - 1));
+    long long t = i >> 10;   // 8 items x 128 samples per block of work
+    const long long ib = t % iblocks;
+    const int q = (int)(t / iblocks);
+    const long long item = ib * 8 + il;
+    if (item >= items) continue;
+    const int r = (int)(item / ncc), cc = (int)(item - (long long)r * ncc);
     const int b = q * CHUNK + bl;
     float v[8];
 #pragma unroll
@@ -165,14 +211,18 @@ template <typename T, int P>
 __global__ void __launch_bounds__(256) slab_to_rows_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ perm,
                                                            T* __restrict__ dst, int B, int R, int Cp, int Cd) {
   const int NB = num_chunks(B), ncc = (Cd + 7) / 8;
-  const long long total = (long long)R * NB * ncc * CHUNK;
+  // same work decomposition as slab_from_rows_kernel: a warp = 8 (row, channel group) items x 4 samples
+  const long long items = (long long)R * ncc, iblocks = (items + 7) / 8;
+  const long long total = iblocks * 8 * CHUNK * NB;
   const size_t slab_b = slab_bytes(Cp, P);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int bl = (int)(i % CHUNK);
-    long long t = i / CHUNK;
-    const int cc = (int)(t % ncc);
-    t /= ncc;
-    const int q = (int)(t % NB), r = (int)(t / NB);
+    const int il = (int)(i & 7), bl = (int)((i >> 3) & (CHUNK - 1));
+    long long t = i >> 10;
+    const long long ib = t % iblocks;
+    const int q = (int)(t / iblocks);
+    const long long item = ib * 8 + il;
+    if (item >= items) continue;
+    const int r = (int)(item / ncc), cc = (int)(item - (long long)r * ncc);
     const int b = q * CHUNK + bl;
     if (b >= B) continue;
     const size_t soff = ((size_t)r * NB + q) * slab_b + (size_t)cc * PLANE_STRIDE + (size_t)bl * 16;
@@ -222,10 +272,10 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
   int grid = units < kNumSMs * 8 ? units : kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 1)
-    slab_pool_kernel<1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
+    slab_pool_kernel<1, 1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
                                                   NB, rows_out, C, act_mul, zero_last, nslice);
   else
-    slab_pool_kernel<2><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
+    slab_pool_kernel<2, 1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
                                                   NB, rows_out, C, act_mul, zero_last, nslice);
   SHB_LAUNCH_CHECK();
   return 0;
@@ -235,7 +285,7 @@ int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, void
                        int Cp, int act_mul, int zero_last, int planes, void* stream) {
   if (!src || !dst || B <= 0 || R <= 0 || Cs <= 0 || Cp < Cs || (Cp & 7) || planes < 1 || planes > 2) return SHB_E_ARG;
   if (src_dtype != SHB_F32 && src_dtype != SHB_BF16) return SHB_E_DTYPE;
-  const long long total = (long long)R * slab::num_chunks(B) * (Cp / 8) * CHUNK;
+  const long long total = (((long long)R * (Cp / 8) + 7) / 8) * 8 * CHUNK * slab::num_chunks(B);
   const int grid = stream_grid(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
 #define SHB_FR(T, PL)                                                                                                          \
@@ -252,7 +302,7 @@ int shb_slab_to_rows(const void* src, const int32_t* perm, void* dst, int dst_dt
                      void* stream) {
   if (!src || !dst || B <= 0 || R <= 0 || Cd <= 0 || Cp < Cd || (Cp & 7) || planes < 1 || planes > 2) return SHB_E_ARG;
   if (dst_dtype != SHB_F32 && dst_dtype != SHB_BF16) return SHB_E_DTYPE;
-  const long long total = (long long)R * slab::num_chunks(B) * ((Cd + 7) / 8) * CHUNK;
+  const long long total = (((long long)R * ((Cd + 7) / 8) + 7) / 8) * 8 * CHUNK * slab::num_chunks(B);
   const int grid = stream_grid(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
 #define SHB_TR(T, PL) slab_to_rows_kernel<T, PL><<<grid, 256, 0, st>>>((const uint8_t*)src, perm, (T*)dst, B, R, Cp, Cd)
