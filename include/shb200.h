@@ -167,6 +167,10 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
 size_t shb_slab_weight_image_bytes(int S, int Ck, int Cn, int planes);
 int shb_slab_weight_images(const float* w, void* img_fwd, void* img_bwd, int S, int Cin, int Cout, int Cin_p, int Cout_p,
                            int planes, void* stream);
+/* The same for `count` layers in one launch (HOST arrays of device pointers / dimensions): a model refreshes the images of
+ * all its conv layers at once after an optimizer step. */
+int shb_slab_weight_images_batch(int count, const float* const* w, void* const* img_fwd, void* const* img_bwd, const int* S,
+                                 const int* Cin, const int* Cout, const int* Cin_p, const int* Cout_p, int planes, void* stream);
 
 /* SpiralConv forward / input gradient (models.py:34-53 and the index_put_(accumulate) + mm of its autograd):
  *   dst[u] = mask(u) * act'(ymul[u]) * act( bias + sum_{e in ptr[u]..ptr[u+1]} src[entries[e] >> 5] . Wimg[slot entries[e] & 31] )

@@ -40,6 +40,7 @@ SIGNATURES = {
     "shb_slab_pool": (c_int, [c_vp] * 6 + [c_int] * 6 + [c_vp]),
     "shb_slab_weight_image_bytes": (c_size, [c_int] * 4),
     "shb_slab_weight_images": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_slab_weight_images_batch": (c_int, [c_int] + [c_vp] * 8 + [c_int, c_vp]),
     "shb_slab_conv_supported": (c_int, [c_int] * 4),
     "shb_slab_conv": (c_int, [c_vp] * 7 + [c_int] * 10 + [c_vp]),
     "shb_build_conv_groups": (c_int, [c_vp, c_vp] + [c_int] * 4 + [c_vp] * 6),

@@ -431,11 +431,30 @@ __global__ void __launch_bounds__(DUAL ? SC_DUAL_THREADS : SC_MAX_THREADS, DUAL 
 //   forward : N = pad16(Cout_p), K = S*Cin_p,   img[n][s*Cin_p + c]  = W[n][s*Cin + c]
 //   backward: N = pad16(Cin_p),  K = S*Cout_p,  img[n][s*Cout_p + o] = W[o][s*Cin + n]      (per-slot transpose)
 // Padded channels are zero.  planes == 2 adds the lo image (w - bf16(w)) behind the hi image.
-__global__ void slab_weight_image_kernel(const float* __restrict__ w, uint8_t* __restrict__ img_f, uint8_t* __restrict__ img_b,
-                                         int S, int Cin, int Cout, int Cin_p, int Cout_p, int planes) {
-  const int Nf = (Cout_p + 15) / 16 * 16, Qf = S * Cin_p / 8, Nb = (Cin_p + 15) / 16 * 16, Qb = S * Cout_p / 8;
-  const int nf = Nf * Qf, nb = Nb * Qb;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += gridDim.x * blockDim.x) {
+struct WeightImageJob {
+  const float* w;
+  uint8_t* img_f;
+  uint8_t* img_b;
+  int S, Cin, Cout, Cin_p, Cout_p;
+  int first_item;   // prefix sum of work items (one item = 8 consecutive k of one image row)
+};
+constexpr int WI_MAX_JOBS = 24;
+struct WeightImageTable {
+  WeightImageJob job[WI_MAX_JOBS];
+  int count, total_items;
+};
+
+// All conv layers of a model in ONE launch (they are tiny: nine launches cost more in launch latency than in work).
+__global__ void slab_weight_image_kernel(const WeightImageTable t, int planes) {
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < t.total_items; gi += gridDim.x * blockDim.x) {
+    int ji = 0;
+    while (ji + 1 < t.count && gi >= t.job[ji + 1].first_item) ++ji;
+    const WeightImageJob& jb = t.job[ji];
+    const float* __restrict__ w = jb.w;
+    const int S = jb.S, Cin = jb.Cin, Cout = jb.Cout, Cin_p = jb.Cin_p, Cout_p = jb.Cout_p;
+    const int i = gi - jb.first_item;
+    const int Nf = (Cout_p + 15) / 16 * 16, Qf = S * Cin_p / 8, Nb = (Cin_p + 15) / 16 * 16, Qb = S * Cout_p / 8;
+    const int nf = Nf * Qf;
     const bool fwd = i < nf;
     const int c = fwd ? i : i - nf;
     const int Q = fwd ? Qf : Qb, N = fwd ? Nf : Nb;
@@ -454,7 +473,7 @@ __global__ void slab_weight_image_kernel(const float* __restrict__ w, uint8_t* _
       }
       v[e] = x;
     }
-    uint8_t* img = fwd ? img_f : img_b;
+    uint8_t* img = fwd ? jb.img_f : jb.img_b;
     const size_t off = (((size_t)(n >> 3) * Q + q) * 8 + (n & 7)) * 16;
     if (planes == 1) {
       *reinterpret_cast<uint4*>(img + off) = pack8(v);
@@ -563,18 +582,34 @@ size_t shb_slab_weight_image_bytes(int S, int Ck, int Cn, int planes) {
   return (size_t)planes * pad16(Cn) * (S * Ck / 8) * 16;
 }
 
+int shb_slab_weight_images_batch(int count, const float* const* w, void* const* img_fwd, void* const* img_bwd, const int* S,
+                                 const int* Cin, const int* Cout, const int* Cin_p, const int* Cout_p, int planes, void* stream) {
+  if (count <= 0 || !w || !img_fwd || !img_bwd || !S || !Cin || !Cout || !Cin_p || !Cout_p || planes < 1 || planes > 2)
+    return SHB_E_ARG;
+  for (int base = 0; base < count; base += WI_MAX_JOBS) {
+    WeightImageTable t{};
+    t.count = count - base < WI_MAX_JOBS ? count - base : WI_MAX_JOBS;
+    int items = 0;
+    for (int i = 0; i < t.count; ++i) {
+      const int k = base + i;
+      if (!w[k] || !img_fwd[k] || !img_bwd[k] || S[k] <= 0 || S[k] > 32 || Cin[k] <= 0 || Cout[k] <= 0 || Cin_p[k] < Cin[k] ||
+          Cout_p[k] < Cout[k] || (Cin_p[k] & 7) || (Cout_p[k] & 7))
+        return SHB_E_ARG;
+      t.job[i] = WeightImageJob{w[k], (uint8_t*)img_fwd[k], (uint8_t*)img_bwd[k], S[k], Cin[k], Cout[k], Cin_p[k], Cout_p[k], items};
+      items += pad16(Cout_p[k]) * (S[k] * Cin_p[k] / 8) + pad16(Cin_p[k]) * (S[k] * Cout_p[k] / 8);
+    }
+    t.total_items = items;
+    int grid = ceil_div(items, 256);
+    if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+    slab_weight_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, planes);
+    SHB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 int shb_slab_weight_images(const float* w, void* img_fwd, void* img_bwd, int S, int Cin, int Cout, int Cin_p, int Cout_p, int planes,
                            void* stream) {
-  if (!w || !img_fwd || !img_bwd || S <= 0 || S > 32 || Cin <= 0 || Cout <= 0 || Cin_p < Cin || Cout_p < Cout || (Cin_p & 7) ||
-      (Cout_p & 7) || planes < 1 || planes > 2)
-    return SHB_E_ARG;
-  const int total = pad16(Cout_p) * (S * Cin_p / 8) + pad16(Cin_p) * (S * Cout_p / 8);
-  int grid = ceil_div(total, 256);
-  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
-  slab_weight_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)img_fwd, (uint8_t*)img_bwd, S, Cin, Cout, Cin_p,
-                                                                  Cout_p, planes);
-  SHB_LAUNCH_CHECK();
-  return 0;
+  return shb_slab_weight_images_batch(1, &w, &img_fwd, &img_bwd, &S, &Cin, &Cout, &Cin_p, &Cout_p, planes, stream);
 }
 
 int shb_slab_conv_supported(int S, int Cs, int Cd, int planes) {

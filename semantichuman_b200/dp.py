@@ -90,13 +90,22 @@ class GradSync:
         for p in self._params:  # a sink left by an earlier GradSync of this model must not outlive it
             if hasattr(p, "_shb_grad_sink"):
                 del p._shb_grad_sink
-        if self.world == 1:
-            return  # nothing to exchange: no flat buckets, gradients are plain per-parameter tensors (reset() drops them)
+        self._model = model
+        self.on_sink_ready = None   # callable(param, reduced-gradient tensor, all-reduce Work or None): see train.TrainStep
         direct = []
         if sink_dtype is not None and hasattr(model, "direct_grad_params"):
             if sink_dtype not in (torch.float32, torch.bfloat16):
                 raise TypeError("gradient sinks are float32 or bfloat16")
             direct = [p for p in model.direct_grad_params() if p.requires_grad]
+        if self.world == 1:
+            # nothing to exchange: no flat buckets, gradients are plain per-parameter tensors (reset() drops them) -- except
+            # the sinks, which exist for what they save locally (no accumulate pass) and for the early optimizer step
+            for p in direct:
+                flat = torch.zeros(p.numel(), dtype=sink_dtype, device=p.device)
+                bucket = {"flat": flat, "params": [p], "pending": 0, "work": None, "sink": True}
+                self.buckets.append(bucket)
+                self.sinks[p] = p._shb_grad_sink = _Sink(flat.view_as(p), self, bucket)
+            return
         for b in range(N_BUCKETS):
             for n, p in named:  # a sink is a bucket of its own, placed where its parameter's bucket would be
                 if _bucket_of(n) == b and any(p is q for q in direct):
@@ -122,10 +131,15 @@ class GradSync:
 
     def _launch(self, bucket):
         bucket["pending"] = 0
-        op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
-        bucket["work"] = dist.all_reduce(bucket["flat"], op=op, group=self.pg, async_op=True)
-        if self.comm_sms > 0 and bucket["flat"].numel() >= (1 << 20) and not self._capped:
-            self._cap(True)  # kernels enqueued from here to finish() leave room for NCCL's CTAs
+        if self.world > 1:
+            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+            bucket["work"] = dist.all_reduce(bucket["flat"], op=op, group=self.pg, async_op=True)
+            if self.comm_sms > 0 and bucket["flat"].numel() >= (1 << 20) and not self._capped:
+                self._cap(True)  # kernels enqueued from here to finish() leave room for NCCL's CTAs
+        if bucket["sink"] and self.on_sink_ready is not None and (self.world == 1 or self._avg_in_collective):
+            p = bucket["params"][0]
+            self.on_sink_ready(p, self.sinks[p].buf, bucket["work"])
+            bucket["work"] = None   # the callback joined the collective on its own stream
 
     def _make_hook(self, bucket):
         def hook(_param):
@@ -136,7 +150,7 @@ class GradSync:
 
     def grad_map(self):
         """{parameter: reduced gradient} of the sink parameters (for optim.Adam.step(grads=...)); empty without sinks."""
-        return {p: s.buf for p, s in self.sinks.items()}
+        return {p: s.buf for p, s in self.sinks.items() if not s._bucket.get("inactive", False)}
 
     def _cap(self, on):
         from ._capi import check, lib
@@ -146,9 +160,20 @@ class GradSync:
 
     def reset(self):
         """Call before each backward (instead of optimizer.zero_grad(set_to_none=True), which would drop the views)."""
+        # a sink only works while its parameter's gradient is produced by a kernel that knows about sinks (the model's current
+        # compute mode decides); otherwise the gradient arrives through autograd as p.grad
+        live = self._model.direct_grad_params() if self.sinks else []
+        for b in self.buckets:
+            if b["sink"]:
+                b["inactive"] = not any(b["params"][0] is q for q in live)
+                if b["inactive"] and self.world > 1:
+                    raise RuntimeError("the model's compute dtype changed after GradSync was built: its gradient sinks no longer "
+                                       "receive their gradients; construct a new GradSync / TrainStep")
         if self.world == 1:
             for p in self._params:
                 p.grad = None
+            for b in self.buckets:
+                b["pending"] = 0 if b["inactive"] else 1
             return
         for b in self.buckets:
             if not b["sink"]:
@@ -166,10 +191,11 @@ class GradSync:
                 b["work"] = None
                 if not self._avg_in_collective:
                     b["flat"].div_(self.world)
-            elif self.world > 1 and b["pending"] != 0:
+            elif b["pending"] != 0:
                 raise RuntimeError("GradSync.finish(): a bucket never completed -- was backward run, and reset() called?")
 
     def grad_bytes(self):
         if self.world == 1:
-            return sum(p.numel() * p.element_size() for p in self._params)
+            return sum((self.sinks[p].buf if p in self.sinks else p).numel() * (self.sinks[p].buf if p in self.sinks else p).element_size()
+                       for p in self._params)
         return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)

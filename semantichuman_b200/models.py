@@ -257,13 +257,26 @@ class _SpiralTrunk(nn.Module):
         self.compute_dtype = dtype
         return self
 
+    def _weight_images(self):
+        """Operand images of every conv weight, current as of now (one launch if any weight changed since the last call)."""
+        planes = self._planes()
+        wi = getattr(self, "_wimg", None)
+        weights = [c.conv.weight for c in list(self.conv) + list(self.dconv)]
+        if wi is None or wi.planes != planes or len(wi.layers) != len(weights) or any(
+                a is not b or a.device != wi.of(a)[0].device for (a, _), b in zip(wi.layers, weights)):
+            wi = self._wimg = slab.WeightImages([(c.conv.weight, c.spiral_size) for c in list(self.conv) + list(self.dconv)],
+                                                planes)
+        wi.refresh()
+        return wi
+
     def _encode_trunk(self, x):
         if not x.is_cuda:
             raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
+        wi = self._weight_images()
         s = slab.from_rows(x, self._perm_dev, self._planes())  # caller's vertex order -> internal order, slab layout
         for j, geom, pm in self._enc_plan:
             c = self.conv[j]
-            s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name)
+            s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name, images=wi.of(c.conv.weight))
             if pm is not None:
                 s = slab.pool(s, pm)
         return slab.to_rows(s, None, self.compute_dtype)  # last level: caller's order (FC layout of models.py:128)
@@ -271,12 +284,13 @@ class _SpiralTrunk(nn.Module):
     def _decode_trunk(self, x):
         if not x.is_cuda:
             raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
+        wi = self._weight_images()
         s = slab.from_rows(x, None, self._planes())
         for j, geom, pm in self._dec_plan:
             if pm is not None:
                 s = slab.pool(s, pm)
             c = self.dconv[j]
-            s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name)
+            s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name, images=wi.of(c.conv.weight))
         return slab.to_rows(s, self._perm_dev, torch.float32)  # internal order -> caller's order
 
 

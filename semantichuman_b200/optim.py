@@ -40,13 +40,23 @@ class Adam:
             elif p.grad is not None:
                 p.grad.zero_()
 
+    def tick(self):
+        """Advance the device-side step count on the current stream (for callers that split one optimizer step over several
+        ``step(..., tick=False)`` launches, e.g. an early launch for the FC weights beside the rest of the backward)."""
+        check(lib.shb_adam_tick(self.step_count.data_ptr(), _stream()), "shb_adam_tick")
+        _count()
+
     @torch.no_grad()
-    def step(self, grads=None):
+    def step(self, grads=None, only=None, skip=None, tick=True):
         """`grads`: optional {parameter: gradient tensor} that takes precedence over ``p.grad`` -- the data-parallel
-        gradient sinks of dp.GradSync (fp32 or bf16 buckets written by the producing GEMM and reduced in place)."""
+        gradient sinks of dp.GradSync (fp32 or bf16 buckets written by the producing GEMM and reduced in place).
+        `only` / `skip`: collections of parameters to restrict this launch to / leave out; `tick=False`: the step count was
+        advanced by tick() already."""
         k = 0
         live = []
         for i, p in enumerate(self.params):
+            if (only is not None and not any(p is q for q in only)) or (skip is not None and any(p is q for q in skip)):
+                continue
             g = grads.get(p) if grads else None
             if g is None:
                 g = p.grad
@@ -67,11 +77,12 @@ class Adam:
         if k == 0:
             return
         st = _stream()
-        check(lib.shb_adam_tick(self.step_count.data_ptr(), st), "shb_adam_tick")
+        if tick:
+            check(lib.shb_adam_tick(self.step_count.data_ptr(), st), "shb_adam_tick")
         check(lib.shb_adam_step_mixed(k, self._arr["p"], self._arr["g"], self._gbf16, self._arr["m"], self._arr["v"],
                                       self._arr["s"], self._numel, self.step_count.data_ptr(), self.lr, self.betas[0],
                                       self.betas[1], self.eps, self.weight_decay, st), "shb_adam_step_mixed")
-        _count(1 + (k + 31) // 32)
+        _count((1 if tick else 0) + (k + 31) // 32)
         for p, _ in live:  # the kernel wrote through raw pointers: tell autograd / the shadow cache
             torch.autograd.graph.increment_version(p)
             sh = self.shadows.get(p)

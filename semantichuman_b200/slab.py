@@ -221,7 +221,7 @@ class SlabConvFn(torch.autograd.Function):
               docstring)."""
 
     @staticmethod
-    def forward(ctx, t, weight, bias, geom, act, meta, want_gx):
+    def forward(ctx, t, weight, bias, geom, act, meta, want_gx, images=None):
         rows, B, C, Cp, planes, xact, xmasked = meta
         _cuda(t, weight, bias)
         cout, k = weight.shape
@@ -238,10 +238,14 @@ class SlabConvFn(torch.autograd.Function):
         w32 = weight.detach().float().contiguous()
         b32 = None if bias is None else bias.detach().float().contiguous()
         dev = t.device
-        img_f = torch.empty(lib.shb_slab_weight_image_bytes(S, Cp, cout_p, planes), dtype=torch.uint8, device=dev)
-        img_b = torch.empty(lib.shb_slab_weight_image_bytes(S, cout_p, Cp, planes), dtype=torch.uint8, device=dev)
-        _call("slab_weight_images", {"bytes": 4.0 * w32.numel() + img_f.numel() + img_b.numel()}, lib.shb_slab_weight_images,
-              _p(w32), _p(img_f), _p(img_b), S, C, cout, Cp, cout_p, planes, _stream())
+        if images is not None:   # kept current by the model (WeightImages): one launch for all layers, not one per call
+            img_f, img_b = images
+        else:
+            img_f = torch.empty(lib.shb_slab_weight_image_bytes(S, Cp, cout_p, planes), dtype=torch.uint8, device=dev)
+            img_b = torch.empty(lib.shb_slab_weight_image_bytes(S, cout_p, Cp, planes), dtype=torch.uint8, device=dev)
+            _call("slab_weight_images", {"bytes": 4.0 * w32.numel() + img_f.numel() + img_b.numel()}, lib.shb_slab_weight_images,
+                  _p(w32), _p(img_f), _p(img_b), S, C, cout, Cp, cout_p, planes, _stream())
+            _count()
         y = torch.empty(Slab.shape_for(geom.rows_out, B, cout_p, planes), dtype=torch.bfloat16, device=dev)
         tag = f"[{rows}>{geom.rows_out}x{S}x{C}>{cout}]"
         cmeta = fn._conv_meta(B, rows, geom.rows_out, S, C, cout, 2 * planes)
@@ -290,15 +294,65 @@ class SlabConvFn(torch.autograd.Function):
                       _p(part), _p(prow), _p(pcol), _p(pval), _p(gx) + off, (_p(t) + off) if xact != 0 else None, B, 1, Cp, xact,
                       0, planes, _stream())
                 _count(2)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
-def spiral_conv(s, weight, bias, geom, activation="elu", want_gx=True):
-    """Slab in, Slab out.  `want_gx=False` skips the input gradient (first layer of an encoder fed with data)."""
+class WeightImages:
+    """bf16 operand images of a set of SpiralConv weights, refreshed in ONE launch whenever a weight changed (its autograd
+    version or storage): a model calls ``refresh()`` at the start of a pass and hands ``of(weight)`` to spiral_conv.  The
+    images of a pass must not be overwritten before its backward has run: they are saved for the input-gradient kernel, and
+    a refresh after an optimizer step writes into the same buffers -- which is the order a training step has."""
+
+    def __init__(self, layers, planes):
+        """layers: [(weight Parameter (Cout, S*Cin), S)]"""
+        import ctypes
+
+        self.planes = planes
+        self.layers = list(layers)
+        self._state = None
+        self._img = {}
+        n = len(self.layers)
+        self._arr = [(ctypes.c_void_p * n)() for _ in range(3)]
+        self._dims = [(ctypes.c_int * n)() for _ in range(5)]
+        for k, (w, S) in enumerate(self.layers):
+            cout, kdim = w.shape
+            cin = kdim // S
+            cp, op = pad_channels(cin), pad_channels(cout)
+            img_f = torch.empty(lib.shb_slab_weight_image_bytes(S, cp, op, planes), dtype=torch.uint8, device=w.device)
+            img_b = torch.empty(lib.shb_slab_weight_image_bytes(S, op, cp, planes), dtype=torch.uint8, device=w.device)
+            self._img[w] = (img_f, img_b)
+            self._arr[1][k], self._arr[2][k] = img_f.data_ptr(), img_b.data_ptr()
+            for d, v in zip(self._dims, (S, cin, cout, cp, op)):
+                d[k] = v
+
+    def refresh(self):
+        state = tuple((w.data_ptr(), w._version) for w, _ in self.layers)
+        if state == self._state:
+            return
+        keep = []
+        for k, (w, _) in enumerate(self.layers):
+            w32 = w.detach()
+            if w32.dtype != torch.float32 or not w32.is_contiguous():
+                w32 = w32.float().contiguous()
+                keep.append(w32)
+            self._arr[0][k] = w32.data_ptr()
+        nbytes = float(sum(4 * w.numel() + a.numel() + b.numel() for (w, _), (a, b) in zip(self.layers, self._img.values())))
+        _call("slab_weight_images", {"bytes": nbytes}, lib.shb_slab_weight_images_batch, len(self.layers), self._arr[0],
+              self._arr[1], self._arr[2], *self._dims, self.planes, _stream())
+        _count()
+        self._state = state
+
+    def of(self, weight):
+        return self._img[weight]
+
+
+def spiral_conv(s, weight, bias, geom, activation="elu", want_gx=True, images=None):
+    """Slab in, Slab out.  `want_gx=False` skips the input gradient (first layer of an encoder fed with data); `images`:
+    prebuilt operand images of `weight` (WeightImages.of)."""
     if activation not in ACT_ENUM:
         raise NotImplementedError(activation)
     act = ACT_ENUM[activation]
-    t = SlabConvFn.apply(s.t, weight, bias, geom, act, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked), want_gx)
+    t = SlabConvFn.apply(s.t, weight, bias, geom, act, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked), want_gx, images)
     cout = weight.shape[0]
     return Slab(t, geom.rows_out, s.B, cout, pad_channels(cout), s.planes, act, geom.zero_last_row)
 

@@ -18,12 +18,14 @@ from .optim import Adam
 
 class TrainStep:
     def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False, comm_sms=0, grad_comm_dtype="auto"):
-        """`grad_comm_dtype` (multi-process runs only): dtype of the gradient sinks of the two FC weights (dp.GradSync) --
+        """`grad_comm_dtype`: dtype of the gradient sinks of the two FC weights (dp.GradSync) --
         "auto": bfloat16 when the model computes in bf16 (the compute dtype must be set before this constructor), none in
         fp32 mode (every gradient travels in fp32 through p.grad); or torch.float32 / torch.bfloat16 / None explicitly."""
         self.model = model
         if grad_comm_dtype == "auto":
             grad_comm_dtype = torch.bfloat16 if getattr(model, "compute_dtype", None) == torch.bfloat16 else None
+        if not optimizer and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            grad_comm_dtype = None   # gradients are the product (tests, inspection): leave them in p.grad
         self.graph_enabled = bool(graph)
         # The captured step runs on a side stream.  autograd's AccumulateGrad nodes (created, and kept alive, by the bucket
         # hooks GradSync registers) remember the stream that was current at their creation and run there: created under the
@@ -38,6 +40,15 @@ class TrainStep:
         # own multi-tensor Adam (device-side step count: replayable; writes the bf16 weight shadows in the same pass)
         shadows = model.shadow_map() if hasattr(model, "shadow_map") else None
         self.optim = Adam(model.parameters(), lr=lr, weight_decay=weight_decay, shadows=shadows) if optimizer else None
+        # Early optimizer launches: a gradient sink (the FC weights: 99 % of the parameters) is final in the middle of the
+        # backward pass, and nothing after its own backward node reads that weight again.  Its Adam update (HBM-bound) therefore
+        # runs on a side stream BESIDE the encoder backward (shared-memory-port-bound), after the sink's all-reduce where there
+        # is one; the launch after backward only covers the remaining parameters.
+        self._opt_stream = None
+        self._early = []
+        if self.optim is not None and self.sync.sinks:
+            self._opt_stream = torch.cuda.Stream()
+            self.sync.on_sink_ready = self._early_step
         self._copy_stream = None
         self._staged = None
         self._graph = None
@@ -45,14 +56,37 @@ class TrainStep:
         self._gloss = None
         self.launches_per_step = None
 
+    def _early_step(self, param, grad, work):
+        """GradSync callback (runs inside backward, on the stream of the node that produced `grad`)."""
+        if self.optim is None:   # optimizer removed after construction: just join the collective here
+            if work is not None:
+                work.wait()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._opt_stream):
+            self._opt_stream.wait_event(ev)      # the GEMM that wrote the sink (and everything before it, incl. the tick)
+            if work is not None:
+                work.wait()                      # ... and its all-reduce
+            self.optim.step(grads={param: grad}, only=[param], tick=False)
+        self._early.append(param)
+
     def _eager(self, x):
         self.sync.reset()
+        self._early = []
+        split = self._opt_stream is not None
+        if split:
+            self.optim.tick()   # before anything of this step: every optimizer launch below reads the advanced count
         xh, _z = self.model(x)
         loss = fn.l1_loss(x, xh)  # train_funcs.py:501  loss_fn(tx, tx_hat)
         loss.backward()
         self.sync.finish()
         if self.optim is not None:
-            self.optim.step(grads=self.sync.grad_map())
+            if split:
+                torch.cuda.current_stream().wait_stream(self._opt_stream)
+                self.optim.step(grads=self.sync.grad_map(), skip=self._early, tick=False)
+            else:
+                self.optim.step(grads=self.sync.grad_map())
         return loss
 
     def capture(self, example_x, warmup=3):
