@@ -31,9 +31,10 @@ METRIC = "train meshes/sec (6890-vert SpiralAE fwd+bwd)"
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can come out on top, from the
 # ncu --set full captures summarised under profiles/ (B=256, bf16).  key = the timer tag bench.py reports as roofline.kernel
 NCU_TRAFFIC_BYTES = {
-    "spiralconv_bwd_dgrad[6891>6891x14x32>16]": (57.34e6 + 59.71e6, "profiles/r01_g_ncu_final_l0.csv"),
-    "spiralconv_fwd[6891>6891x14x32>16]": (113.38e6 + 33.43e6, "profiles/r01_g_ncu_final_l0.csv"),
-    "spiralconv_bwd_wgrad[6891>6891x14x32>16]": (324.22e6 + 4.81e6, "profiles/r01_g_ncu_final_l0.csv"),
+    "slabconv_wgrad[6891>6891x14x32>16]": (169.78e6 + 3.84e6, "profiles/r02_ncu_gconv_wgrad_l0.csv"),
+    "slabconv_fwd[6891>6891x14x32>16]": (116.15e6 + 31.62e6, "profiles/r02_ncu_gconv_wgrad_l0.csv"),
+    "slabconv_dgrad[6891>6891x14x32>16]": (171.88e6 + 78.58e6, "profiles/r02_ncu_gconv_wgrad_l0.csv"),
+    "slabconv_wgrad[863>863x8x128>64]": (84.94e6 + 3.78e6, "profiles/r02_ncu_conv_wgrad_l3.csv"),
 }
 N_INPUT_BATCHES = 8  # distinct resident batches rotated through the timed loop
 

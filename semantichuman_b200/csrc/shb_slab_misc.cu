@@ -21,9 +21,49 @@ using namespace slab;
 // 12 global-load latencies per unit, 30-40 % of HBM).  So: a unit's entries are fetched four at a time (indices and weights of
 // all four in flight together), the data loads of all four entries are issued back to back, and the next unit's row range is
 // requested before the current unit is processed: three latencies per unit (row range -> entries -> data).  One vector per
-// thread (VPT = 1): two per thread doubled the registers, halved the resident warps and measured 10 % slower.  Accumulation
-// stays in CSR order.
-template <int P, int VPT>
+// thread (two doubled the registers, halved the resident warps and measured 10 % slower).  The kernel is also instruction-
+// bound (IPC 0.5 at half occupancy, ~150 instructions per 16-byte vector with four predicated entries): the entry count of a
+// row is uniform over the block, so the accumulation is specialised on it (no predicated-off work).  CSR order is kept.
+// N entries (1..4) of one row into acc: the N index / weight loads, then the N data loads, all unconditional and back to back.
+// FIRST: acc is written (first chunk of a row), not accumulated into.
+template <int P, int N, bool FIRST>
+__device__ __forceinline__ void pool_accum(const uint8_t* __restrict__ sv, size_t rstride, size_t plane_b,
+                                           const int32_t* __restrict__ colidx, const float* __restrict__ vals, int kb, float* acc) {
+  int col[N];
+  float w[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    col[j] = __ldg(colidx + kb + j);
+    w[j] = __ldg(vals + kb + j);
+  }
+  uint4 raw[N][P];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const uint8_t* s = sv + (size_t)col[j] * rstride;
+    raw[j][0] = __ldg(reinterpret_cast<const uint4*>(s));
+    if (P == 2) raw[j][P - 1] = __ldg(reinterpret_cast<const uint4*>(s + plane_b));
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float x[8];
+    unpack8(raw[j][0], x);
+    if (P == 2) {
+      float l[8];
+      unpack8(raw[j][P - 1], l);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += l[i];
+    }
+    if (FIRST && j == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = w[0] * x[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[j], x[i], acc[i]);
+    }
+  }
+}
+
+template <int P>
 __global__ void __launch_bounds__(256) slab_pool_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                         uint8_t* __restrict__ dst, const uint8_t* __restrict__ ymul, int NB,
@@ -54,86 +94,56 @@ __global__ void __launch_bounds__(256) slab_pool_kernel(const uint8_t* __restric
     const bool zero = zero_last && r == rows_out - 1;
     const size_t uoff = ((size_t)r * NB + q) * slab_b;
     const int v1 = (sl + 1) * vper < nvec ? (sl + 1) * vper : nvec;
-    for (int vb = sl * vper + threadIdx.x; vb < v1; vb += VPT * blockDim.x) {
-      const int vv[2] = {vb, vb + (int)blockDim.x};
-      const bool has2 = VPT == 2 && vv[1] < v1;
-      float acc[VPT][8];
-#pragma unroll
-      for (int t = 0; t < VPT; ++t)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
-      uint4 yraw[VPT][P];
-      if (ymul != nullptr && !zero) {  // act' operands: requested first, consumed last
-#pragma unroll
-        for (int t = 0; t < VPT; ++t)
-          if (t == 0 || has2) {
-            yraw[t][0] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + (size_t)vv[t] * 16));
-            if (P == 2) yraw[t][P - 1] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + plane_b + (size_t)vv[t] * 16));
-          }
+    const int n = zero ? 0 : k1 - k0;   // the whole block works on one row: the branches below are uniform
+    for (int v = sl * vper + threadIdx.x; v < v1; v += blockDim.x) {
+      float acc[8];
+      uint4 yraw[P];
+      if (ymul != nullptr && n > 0) {  // act' operand: requested first, consumed last
+        yraw[0] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + (size_t)v * 16));
+        if (P == 2) yraw[P - 1] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + plane_b + (size_t)v * 16));
       }
-      if (!zero) {
-        const uint8_t* sq = src + (size_t)q * slab_b;
-        for (int kb = k0; kb < k1; kb += 4) {
-          int col[4];
-          float w[4];
+      const uint8_t* sv = src + (size_t)q * slab_b + (size_t)v * 16;
+      // first (usually only) chunk of up to four entries, specialised on its length; longer rows continue four at a time
+      switch (n < 4 ? n : 4) {
+        case 0:
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool on = kb + j < k1;
-            col[j] = on ? __ldg(colidx + kb + j) : -1;
-            w[j] = on ? __ldg(vals + kb + j) : 0.f;
-          }
-          uint4 raw[VPT][4][P];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int t = 0; t < VPT; ++t)
-              if (col[j] >= 0 && (t == 0 || has2)) {
-                const uint8_t* s = sq + (size_t)col[j] * rstride + (size_t)vv[t] * 16;
-                raw[t][j][0] = __ldg(reinterpret_cast<const uint4*>(s));
-                if (P == 2) raw[t][j][P - 1] = __ldg(reinterpret_cast<const uint4*>(s + plane_b));
-              }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int t = 0; t < VPT; ++t)
-              if (col[j] >= 0 && (t == 0 || has2)) {
-                float x[8];
-                unpack8(raw[t][j][0], x);
-                if (P == 2) {
-                  float l[8];
-                  unpack8(raw[t][j][P - 1], l);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) x[i] += l[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(w[j], x[i], acc[t][i]);
-              }
+          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          break;
+        case 1: pool_accum<P, 1, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
+        case 2: pool_accum<P, 2, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
+        case 3: pool_accum<P, 3, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
+        default: pool_accum<P, 4, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
+      }
+      int kb = k0 + 4;
+      for (; kb + 4 <= k1 && n > 4; kb += 4) pool_accum<P, 4, false>(sv, rstride, plane_b, colidx, vals, kb, acc);
+      if (n > 4) {
+        switch (k1 - kb) {
+          case 1: pool_accum<P, 1, false>(sv, rstride, plane_b, colidx, vals, kb, acc); break;
+          case 2: pool_accum<P, 2, false>(sv, rstride, plane_b, colidx, vals, kb, acc); break;
+          case 3: pool_accum<P, 3, false>(sv, rstride, plane_b, colidx, vals, kb, acc); break;
+          default: break;
         }
       }
+      if (ymul != nullptr && n > 0) {
+        float yy[8];
+        unpack8(yraw[0], yy);
+        if (P == 2) {
+          float l[8];
+          unpack8(yraw[P - 1], l);
 #pragma unroll
-      for (int t = 0; t < VPT; ++t)
-        if (t == 0 || has2) {
-          if (ymul != nullptr && !zero) {
-            float yy[8];
-            unpack8(yraw[t][0], yy);
-            if (P == 2) {
-              float l[8];
-              unpack8(yraw[t][P - 1], l);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) yy[i] += l[i];
-            }
-            act_bwd8(acc[t], yy, act_mul);
-          }
-          uint8_t* d = dst + uoff + (size_t)vv[t] * 16;
-          if (P == 1) {
-            *reinterpret_cast<uint4*>(d) = pack8(acc[t]);
-          } else {
-            uint4 hi, lo;
-            split8(acc[t], hi, lo);
-            *reinterpret_cast<uint4*>(d) = hi;
-            *reinterpret_cast<uint4*>(d + plane_b) = lo;
-          }
+          for (int i = 0; i < 8; ++i) yy[i] += l[i];
         }
+        act_bwd8(acc, yy, act_mul);
+      }
+      uint8_t* d = dst + uoff + (size_t)v * 16;
+      if (P == 1) {
+        *reinterpret_cast<uint4*>(d) = pack8(acc);
+      } else {
+        uint4 hi, lo;
+        split8(acc, hi, lo);
+        *reinterpret_cast<uint4*>(d) = hi;
+        *reinterpret_cast<uint4*>(d + plane_b) = lo;
+      }
     }
     unit = unit_n; k0 = n0; k1 = n1;
   }
@@ -272,10 +282,10 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
   int grid = units < kNumSMs * 8 ? units : kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 1)
-    slab_pool_kernel<1, 1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
+    slab_pool_kernel<1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
                                                   NB, rows_out, C, act_mul, zero_last, nslice);
   else
-    slab_pool_kernel<2, 1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
+    slab_pool_kernel<2><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
                                                   NB, rows_out, C, act_mul, zero_last, nslice);
   SHB_LAUNCH_CHECK();
   return 0;
