@@ -16,43 +16,41 @@ using namespace slab;
 // ---------------------------------------------------------------------------------------------- Pool
 // dst[r] = act'(ymul[r]) * sum_k vals[k] * src[colidx[k]]   for k in rowptr[r] .. rowptr[r+1];   dummy row optionally zeroed
 //
-// A unit is one (row, chunk) slab (cut into nslice vector ranges when rows are few).  What bounds this kernel is the LENGTH OF
-// THE DEPENDENT LOAD CHAIN per unit, not bandwidth (first version: one entry at a time, index load -> data load, per vector:
-// 12 global-load latencies per unit, 30-40 % of HBM).  So: a unit's entries are fetched four at a time (indices and weights of
-// all four in flight together), the data loads of all four entries are issued back to back, and the next unit's row range is
-// requested before the current unit is processed: three latencies per unit (row range -> entries -> data).  One vector per
-// thread (two doubled the registers, halved the resident warps and measured 10 % slower).  The kernel is also instruction-
-// bound (IPC 0.5 at half occupancy, ~150 instructions per 16-byte vector with four predicated entries): the entry count of a
-// row is uniform over the block, so the accumulation is specialised on it (no predicated-off work).  CSR order is kept.
-// N entries (1..4) of one row into acc: the N index / weight loads, then the N data loads, all unconditional and back to back.
-// FIRST: acc is written (first chunk of a row), not accumulated into.
-template <int P, int N, bool FIRST>
-__device__ __forceinline__ void pool_accum(const uint8_t* __restrict__ sv, size_t rstride, size_t plane_b,
-                                           const int32_t* __restrict__ colidx, const float* __restrict__ vals, int kb, float* acc) {
-  int col[N];
-  float w[N];
+// A unit is one (row, chunk) slab, cut into nslice vector ranges when rows are few; ONE WARP owns a unit and streams its
+// vectors, lane l taking vectors l, l + 32, ... of the range.  Two earlier versions (one thread per vector; a 256-thread
+// block per unit) were bound by instruction issue and by the dependent load chain of a unit, not by bandwidth: ncu showed
+// ~235 warp instructions per 16-byte output vector (unit decoding with three integer divisions, the row's indices and
+// weights re-loaded and 64-bit addresses re-formed for every vector) at IPC 0.68, DRAM 30 %, L2 22 %.  Here everything that
+// belongs to the ROW is done once per unit -- row range, indices, weights (one entry per lane, handed out by shuffles), the
+// source pointers -- and is requested one unit ahead (row range: two units ahead), so the steady state of a warp is the
+// vector loop alone: N + 1 independent 512-byte loads per vector (two vectors unrolled), 8 N fused multiply-adds, one store,
+// pointers advanced by a constant.  The loop is specialised on the row's entry count N = 1..4 (rows of U have one or three
+// entries; rows of a transpose have a handful); longer rows take four entries at a time.  CSR order is kept.
+template <int P>
+__device__ __forceinline__ void pool_load(const uint8_t* s, size_t plane_b, uint4* raw) {
+  raw[0] = __ldg(reinterpret_cast<const uint4*>(s));
+  if (P == 2) raw[P - 1] = __ldg(reinterpret_cast<const uint4*>(s + plane_b));
+}
+template <int P>
+__device__ __forceinline__ void pool_value(const uint4* raw, float* x) {
+  unpack8(raw[0], x);
+  if (P == 2) {
+    float l[8];
+    unpack8(raw[P - 1], l);
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    col[j] = __ldg(colidx + kb + j);
-    w[j] = __ldg(vals + kb + j);
+    for (int i = 0; i < 8; ++i) x[i] += l[i];
   }
+}
+// acc (+)= sum_j w[j] * x_j for N entries whose data pointers are s[j] (+ off)
+template <int P, int N, bool FIRST>
+__device__ __forceinline__ void pool_accum(const uint8_t* const* s, const float* w, size_t off, size_t plane_b, float* acc) {
   uint4 raw[N][P];
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const uint8_t* s = sv + (size_t)col[j] * rstride;
-    raw[j][0] = __ldg(reinterpret_cast<const uint4*>(s));
-    if (P == 2) raw[j][P - 1] = __ldg(reinterpret_cast<const uint4*>(s + plane_b));
-  }
+  for (int j = 0; j < N; ++j) pool_load<P>(s[j] + off, plane_b, raw[j]);
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     float x[8];
-    unpack8(raw[j][0], x);
-    if (P == 2) {
-      float l[8];
-      unpack8(raw[j][P - 1], l);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] += l[i];
-    }
+    pool_value<P>(raw[j], x);
     if (FIRST && j == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = w[0] * x[i];
@@ -62,90 +60,201 @@ __device__ __forceinline__ void pool_accum(const uint8_t* __restrict__ sv, size_
     }
   }
 }
+// the same for two consecutive vectors of a lane (off, off + 512): all 2 N loads first
+template <int P, int N>
+__device__ __forceinline__ void pool_accum2(const uint8_t* const* s, const float* w, size_t off, size_t plane_b, float (*acc)[8]) {
+  uint4 raw[2][N][P];
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int j = 0; j < N; ++j) pool_load<P>(s[j] + off + v * 512, plane_b, raw[v][j]);
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float x[8];
+      pool_value<P>(raw[v][j], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[v][i] = fmaf(w[j], x[i], acc[v][i]);
+    }
+}
+template <int P, int ACT>
+__device__ __forceinline__ void pool_finish(float* acc, const uint4* yraw, uint8_t* d, size_t plane_b) {
+  if (ACT != SHB_ACT_IDENTITY) {
+    float yy[8];
+    pool_value<P>(yraw, yy);
+    act_bwd8_as<ACT>(acc, yy);
+  }
+  if (P == 1) {
+    *reinterpret_cast<uint4*>(d) = pack8(acc);
+  } else {
+    uint4 hi, lo;
+    split8(acc, hi, lo);
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + plane_b) = lo;
+  }
+}
+// All `iters` vectors of a lane for a row of exactly N entries (N = 1..4): a branch-free body (the activation is a template
+// parameter), unrolled twice so that the 2 (N + 1) loads of two vectors are in flight together.
+template <int P, int ACT, int N>
+__device__ __forceinline__ void pool_unit_fixed(const uint8_t* sv, size_t rstride, size_t plane_b, int col_l, float w_l,
+                                                const uint8_t* yv, uint8_t* dv, int iters) {
+  const uint8_t* s[N];
+  float w[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    s[j] = sv + (size_t)__shfl_sync(0xffffffffu, col_l, j) * rstride;
+    w[j] = __shfl_sync(0xffffffffu, w_l, j);
+  }
+#pragma unroll 2
+  for (int i = 0; i < iters; ++i) {
+    const size_t off = (size_t)i * 512;
+    uint4 yraw[P];
+    if (ACT != SHB_ACT_IDENTITY) pool_load<P>(yv + off, plane_b, yraw);
+    float acc[8];
+    pool_accum<P, N, true>(s, w, off, plane_b, acc);
+    pool_finish<P, ACT>(acc, yraw, dv + off, plane_b);
+  }
+}
+// Rows of 5..32 entries: four entries at a time, the indices / weights handed out by shuffles from the lanes that hold them;
+// two vectors per pass so that eight loads are in flight (`iters` is even: host).
+template <int P, int ACT>
+__device__ __forceinline__ void pool_unit_long(const uint8_t* sv, size_t rstride, size_t plane_b, int col_l, float w_l, int n,
+                                               const uint8_t* yv, uint8_t* dv, int iters) {
+#pragma unroll 1
+  for (int i = 0; i < iters; i += 2) {
+    const size_t off = (size_t)i * 512;
+    uint4 yraw[2][P];
+    if (ACT != SHB_ACT_IDENTITY) {
+      pool_load<P>(yv + off, plane_b, yraw[0]);
+      pool_load<P>(yv + off + 512, plane_b, yraw[1]);
+    }
+    float acc[2][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < n; kb += 4) {
+      const uint8_t* s[4];
+      float w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] = sv + (size_t)__shfl_sync(0xffffffffu, col_l, (kb + j) & 31) * rstride;
+        w[j] = __shfl_sync(0xffffffffu, w_l, (kb + j) & 31);
+      }
+      switch (n - kb) {
+        case 1: pool_accum2<P, 1>(s, w, off, plane_b, acc); break;
+        case 2: pool_accum2<P, 2>(s, w, off, plane_b, acc); break;
+        case 3: pool_accum2<P, 3>(s, w, off, plane_b, acc); break;
+        default: pool_accum2<P, 4>(s, w, off, plane_b, acc); break;
+      }
+    }
+    pool_finish<P, ACT>(acc[0], yraw[0], dv + off, plane_b);
+    pool_finish<P, ACT>(acc[1], yraw[1], dv + off + 512, plane_b);
+  }
+}
+// Rows longer than a warp (no matrix of the models has one): entries fetched inside the vector loop, no overlap.
+template <int P, int ACT>
+__device__ __forceinline__ void pool_unit_huge(const uint8_t* sv, size_t rstride, size_t plane_b,
+                                               const int32_t* __restrict__ colidx, const float* __restrict__ vals, int k0, int n,
+                                               const uint8_t* yv, uint8_t* dv, int iters) {
+  constexpr bool with_y = ACT != SHB_ACT_IDENTITY;
+  for (int i = 0; i < iters; ++i) {
+    const size_t off = (size_t)i * 512;
+    uint4 yraw[P];
+    if (with_y) pool_load<P>(yv + off, plane_b, yraw);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k = 0; k < n; ++k) {
+      uint4 raw[P];
+      pool_load<P>(sv + (size_t)__ldg(colidx + k0 + k) * rstride + off, plane_b, raw);
+      const float w = __ldg(vals + k0 + k);
+      float x[8];
+      pool_value<P>(raw, x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, x[e], acc[e]);
+    }
+    pool_finish<P, ACT>(acc, yraw, dv + off, plane_b);
+  }
+}
 
-template <int P>
-__global__ void __launch_bounds__(256) slab_pool_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ rowptr,
-                                                        const int32_t* __restrict__ colidx, const float* __restrict__ vals,
-                                                        uint8_t* __restrict__ dst, const uint8_t* __restrict__ ymul, int NB,
-                                                        int rows_out, int C, int act_mul, int zero_last, int nslice) {
-  const int nvec = C * 16;                         // 16-byte vectors per plane of a slab
-  const int vper = (nvec + nslice - 1) / nslice;   // vectors per slice
+constexpr int POOL_WARPS = 8;   // per block
+
+template <int P, int ACT>
+__global__ void __launch_bounds__(POOL_WARPS * 32, P == 1 ? 3 : 2) slab_pool_kernel(const uint8_t* __restrict__ src,
+                                                                    const int32_t* __restrict__ rowptr,
+                                                                    const int32_t* __restrict__ colidx,
+                                                                    const float* __restrict__ vals, uint8_t* __restrict__ dst,
+                                                                    const uint8_t* __restrict__ ymul, int NB, int rows_out, int C,
+                                                                    int zero_last, int nslice) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C * 16;              // 16-byte vectors per plane of a slab
+  const int vper = nvec / nslice;       // vectors per slice: a multiple of 32 (host)
+  const int iters = vper >> 5;
   const size_t slab_b = slab_bytes(C, P);
   const size_t plane_b = (size_t)C * 256;
   const size_t rstride = (size_t)NB * slab_b;
-  const int units = rows_out * NB * nslice;
-  int unit = blockIdx.x;
-  int k0 = 0, k1 = 0;
-  if (unit < units) {
-    const int r = unit / (nslice * NB);
-    k0 = __ldg(rowptr + r);
-    k1 = __ldg(rowptr + r + 1);
+  const int per_row = NB * nslice;
+  const int units = rows_out * per_row;
+  const int stride = gridDim.x * POOL_WARPS;
+  int unit = blockIdx.x * POOL_WARPS + (threadIdx.x >> 5);
+  if (unit >= units) return;
+  // software pipeline over this warp's units: row range two units ahead, entries (one per lane) one unit ahead
+  int r = unit / per_row;
+  int k0 = __ldg(rowptr + r), k1 = __ldg(rowptr + r + 1);
+  int r_n = 0, n0 = 0, n1 = 0;
+  if (unit + stride < units) {
+    r_n = (unit + stride) / per_row;
+    n0 = __ldg(rowptr + r_n);
+    n1 = __ldg(rowptr + r_n + 1);
   }
-  while (unit < units) {
-    const int rq = unit / nslice, sl = unit - rq * nslice;
-    const int r = rq / NB, q = rq - r * NB;
-    const int unit_n = unit + gridDim.x;
-    int n0 = 0, n1 = 0;
-    if (unit_n < units) {  // next unit's row range: in flight while this unit is processed
-      const int rn = unit_n / (nslice * NB);
-      n0 = __ldg(rowptr + rn);
-      n1 = __ldg(rowptr + rn + 1);
+  int col_l = 0;
+  float w_l = 0.f;
+  if (lane < k1 - k0) {
+    col_l = __ldg(colidx + k0 + lane);
+    w_l = __ldg(vals + k0 + lane);
+  }
+  while (true) {
+    const int unit_n = unit + stride, unit_nn = unit_n + stride;
+    int r_nn = 0, m0 = 0, m1 = 0;
+    if (unit_nn < units) {
+      r_nn = unit_nn / per_row;
+      m0 = __ldg(rowptr + r_nn);
+      m1 = __ldg(rowptr + r_nn + 1);
     }
+    int col_n = 0;
+    float w_n = 0.f;
+    if (unit_n < units && lane < n1 - n0) {
+      col_n = __ldg(colidx + n0 + lane);
+      w_n = __ldg(vals + n0 + lane);
+    }
+    const int rem = unit - r * per_row, q = rem / nslice, sl = rem - q * nslice;
     const bool zero = zero_last && r == rows_out - 1;
-    const size_t uoff = ((size_t)r * NB + q) * slab_b;
-    const int v1 = (sl + 1) * vper < nvec ? (sl + 1) * vper : nvec;
-    const int n = zero ? 0 : k1 - k0;   // the whole block works on one row: the branches below are uniform
-    for (int v = sl * vper + threadIdx.x; v < v1; v += blockDim.x) {
-      float acc[8];
-      uint4 yraw[P];
-      if (ymul != nullptr && n > 0) {  // act' operand: requested first, consumed last
-        yraw[0] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + (size_t)v * 16));
-        if (P == 2) yraw[P - 1] = __ldg(reinterpret_cast<const uint4*>(ymul + uoff + plane_b + (size_t)v * 16));
-      }
-      const uint8_t* sv = src + (size_t)q * slab_b + (size_t)v * 16;
-      // first (usually only) chunk of up to four entries, specialised on its length; longer rows continue four at a time
-      switch (n < 4 ? n : 4) {
-        case 0:
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-          break;
-        case 1: pool_accum<P, 1, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
-        case 2: pool_accum<P, 2, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
-        case 3: pool_accum<P, 3, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
-        default: pool_accum<P, 4, true>(sv, rstride, plane_b, colidx, vals, k0, acc); break;
-      }
-      int kb = k0 + 4;
-      for (; kb + 4 <= k1 && n > 4; kb += 4) pool_accum<P, 4, false>(sv, rstride, plane_b, colidx, vals, kb, acc);
-      if (n > 4) {
-        switch (k1 - kb) {
-          case 1: pool_accum<P, 1, false>(sv, rstride, plane_b, colidx, vals, kb, acc); break;
-          case 2: pool_accum<P, 2, false>(sv, rstride, plane_b, colidx, vals, kb, acc); break;
-          case 3: pool_accum<P, 3, false>(sv, rstride, plane_b, colidx, vals, kb, acc); break;
-          default: break;
+    const int n = zero ? 0 : k1 - k0;
+    const size_t voff = ((size_t)sl * vper + lane) * 16;
+    const size_t uoff = ((size_t)r * NB + q) * slab_b + voff;
+    const uint8_t* sv = src + (size_t)q * slab_b + voff;
+    const uint8_t* yv = ymul + uoff;   // read only when ACT != identity
+    uint8_t* dv = dst + uoff;
+    switch (n) {
+      case 0:
+        for (int i = 0; i < iters; ++i) {
+          *reinterpret_cast<uint4*>(dv + (size_t)i * 512) = make_uint4(0, 0, 0, 0);
+          if (P == 2) *reinterpret_cast<uint4*>(dv + (size_t)i * 512 + plane_b) = make_uint4(0, 0, 0, 0);
         }
-      }
-      if (ymul != nullptr && n > 0) {
-        float yy[8];
-        unpack8(yraw[0], yy);
-        if (P == 2) {
-          float l[8];
-          unpack8(yraw[P - 1], l);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) yy[i] += l[i];
-        }
-        act_bwd8(acc, yy, act_mul);
-      }
-      uint8_t* d = dst + uoff + (size_t)v * 16;
-      if (P == 1) {
-        *reinterpret_cast<uint4*>(d) = pack8(acc);
-      } else {
-        uint4 hi, lo;
-        split8(acc, hi, lo);
-        *reinterpret_cast<uint4*>(d) = hi;
-        *reinterpret_cast<uint4*>(d + plane_b) = lo;
-      }
+        break;
+      case 1: pool_unit_fixed<P, ACT, 1>(sv, rstride, plane_b, col_l, w_l, yv, dv, iters); break;
+      case 2: pool_unit_fixed<P, ACT, 2>(sv, rstride, plane_b, col_l, w_l, yv, dv, iters); break;
+      case 3: pool_unit_fixed<P, ACT, 3>(sv, rstride, plane_b, col_l, w_l, yv, dv, iters); break;
+      case 4: pool_unit_fixed<P, ACT, 4>(sv, rstride, plane_b, col_l, w_l, yv, dv, iters); break;
+      default:
+        if (n <= 32) pool_unit_long<P, ACT>(sv, rstride, plane_b, col_l, w_l, n, yv, dv, iters);
+        else pool_unit_huge<P, ACT>(sv, rstride, plane_b, colidx, vals, k0, n, yv, dv, iters);
+        break;
     }
-    unit = unit_n; k0 = n0; k1 = n1;
+    if (unit_n >= units) break;
+    unit = unit_n; r = r_n; k0 = n0; k1 = n1; col_l = col_n; w_l = w_n;
+    r_n = r_nn; n0 = m0; n1 = m1;
   }
 }
 
@@ -274,19 +383,35 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
   if (!src || !rowptr || !colidx || !vals || !dst || B <= 0 || rows_out <= 0 || C <= 0 || (C & 7)) return SHB_E_ARG;
   if (planes < 1 || planes > 2) return SHB_E_ARG;
   const int NB = slab::num_chunks(B), nvec = C * 16;
-  int nslice = 1;  // few, long rows (the per-slot sums of the dummy-row gradient): spread a unit's vectors over several CTAs
-  while (rows_out * NB * nslice < 4 * kNumSMs && nvec / (nslice * 2) >= 32) nslice *= 2;
-  const int units = rows_out * NB * nslice;
-  const int per = nvec / nslice;
-  const int threads = per >= 256 ? 256 : (per >= 128 ? 128 : (per >= 64 ? 64 : 32));
-  int grid = units < kNumSMs * 8 ? units : kNumSMs * 8;
+  // one warp per unit; a unit's vectors are cut into slices (>= 128 vectors: four per lane, an even count) until every
+  // resident warp has a few units (few, long rows -- the per-slot sums of the dummy-row gradient -- are what needs the cut)
+  int nslice = 1;
+  const long long want = 4LL * kNumSMs * 24;
+  while ((long long)rows_out * NB * nslice < want && nvec / (nslice * 2) >= 128 && (nvec / (nslice * 2)) % 64 == 0) nslice *= 2;
+  if ((nvec / nslice) % 64) return SHB_E_ARG;   // cannot happen: nvec is a multiple of 128 and the loop keeps slices multiples of 64
+  const long long units = (long long)rows_out * NB * nslice;
+  if (units >= (1LL << 31)) return SHB_E_ARG;
+  const long long blocks = (units + POOL_WARPS - 1) / POOL_WARPS;
+  const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+  const int threads = POOL_WARPS * 32;
   cudaStream_t st = (cudaStream_t)stream;
-  if (planes == 1)
-    slab_pool_kernel<1><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
-                                                  NB, rows_out, C, act_mul, zero_last, nslice);
-  else
-    slab_pool_kernel<2><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst, (const uint8_t*)ymul,
-                                                  NB, rows_out, C, act_mul, zero_last, nslice);
+  const int act = ymul ? act_mul : SHB_ACT_IDENTITY;   // the kernel is compiled per activation: no switch inside the vector loop
+  if (act < SHB_ACT_IDENTITY || act > SHB_ACT_TANH) return SHB_E_ARG;
+#define SHB_POOL(PL, ACT)                                                                                                     \
+  slab_pool_kernel<PL, ACT><<<grid, threads, 0, st>>>((const uint8_t*)src, rowptr, colidx, vals, (uint8_t*)dst,               \
+                                                      (const uint8_t*)ymul, NB, rows_out, C, zero_last, nslice)
+#define SHB_POOL_ACT(PL)                                           \
+  switch (act) {                                                   \
+    case SHB_ACT_RELU: SHB_POOL(PL, SHB_ACT_RELU); break;          \
+    case SHB_ACT_ELU: SHB_POOL(PL, SHB_ACT_ELU); break;            \
+    case SHB_ACT_LEAKY_RELU: SHB_POOL(PL, SHB_ACT_LEAKY_RELU); break; \
+    case SHB_ACT_SIGMOID: SHB_POOL(PL, SHB_ACT_SIGMOID); break;    \
+    case SHB_ACT_TANH: SHB_POOL(PL, SHB_ACT_TANH); break;          \
+    default: SHB_POOL(PL, SHB_ACT_IDENTITY); break;                \
+  }
+  if (planes == 1) { SHB_POOL_ACT(1) } else { SHB_POOL_ACT(2) }
+#undef SHB_POOL_ACT
+#undef SHB_POOL
   SHB_LAUNCH_CHECK();
   return 0;
 }
