@@ -150,11 +150,14 @@ size_t shb_slab_tensor_bytes(int rows, int B, int C, int planes);
  *   channels Cs..Cp-1 and samples B..128*NB-1 are written as zeros; if ymul != NULL (slab tensor shaped like dst) the result
  *   is multiplied by act'(ymul) -- the activation derivative expressed through the layer OUTPUT (act_mul = SHB_ACT_*);
  *   zero_last zeroes row R-1 (the mask of models.py:48-51 on the gradient path).
- * to_rows: dst row-major (B, R, Cd), Cd <= Cp; the caller's row perm[i] receives internal row i. */
-int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, void* dst, const void* ymul, int B, int R, int Cs,
-                       int Cp, int act_mul, int zero_last, int planes, void* stream);
-int shb_slab_to_rows(const void* src, const int32_t* perm, void* dst, int dst_dtype, int B, int R, int Cp, int Cd, int planes,
-                     void* stream);
+ * to_rows: dst row-major (B, R, Cd), Cd <= Cp; the caller's row perm[i] receives internal row i.
+ * perm_inv (optional; NULL allowed): the inverse permutation, perm_inv[perm[i]] = i.  With it the 8-channel (3-channel ends)
+ *   conversions walk the row-major tensor in the caller's order -- contiguous reads / writes -- and scatter on the slab side,
+ *   where a row is 2 KB; without it they fall back to the item-per-thread kernels. */
+int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, const int32_t* perm_inv, void* dst, const void* ymul,
+                       int B, int R, int Cs, int Cp, int act_mul, int zero_last, int planes, void* stream);
+int shb_slab_to_rows(const void* src, const int32_t* perm, const int32_t* perm_inv, void* dst, int dst_dtype, int B, int R, int Cp,
+                     int Cd, int planes, void* stream);
 
 /* Pool (models.py:127,148: torch.matmul(D[i] | U[i], x)) on slab tensors: dst[r] = sum_k vals[k] * src[colidx[k]],
  * k in rowptr[r]..rowptr[r+1].  Optional epilogue for the gradient path: times act'(ymul[r]) and/or zero the last row. */

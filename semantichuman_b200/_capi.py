@@ -35,8 +35,8 @@ SIGNATURES = {
     "shb_adam_step_mixed": (c_int, [c_int] + [c_vp] * 8 + [ctypes.c_double] * 3 + [c_float] * 2 + [c_vp]),
     "shb_cast_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "shb_slab_tensor_bytes": (c_size, [c_int] * 4),
-    "shb_slab_from_rows": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
-    "shb_slab_to_rows": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_slab_from_rows": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
+    "shb_slab_to_rows": (c_int, [c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
     "shb_slab_pool": (c_int, [c_vp] * 6 + [c_int] * 6 + [c_vp]),
     "shb_slab_weight_image_bytes": (c_size, [c_int] * 4),
     "shb_slab_weight_images": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),

@@ -366,6 +366,241 @@ __global__ void __launch_bounds__(256) slab_to_rows_kernel(const uint8_t* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------- tiled conversions
+// The two kernels above touch whole sectors on both sides but spend ~300 instructions of 64-bit index arithmetic per 16-byte
+// item and move 64-byte runs; at the FC boundary (432 rows x 128 channels) and at the 3-channel ends they ran at 1.2-2.9 TB/s.
+// The kernels below take a TILE through shared memory instead, so that both sides see long contiguous runs and the index
+// arithmetic is per tile:
+//   wide   (Cs == Cp in {16, 32, 64, 128, 256}): tile = one (row, chunk) x <= 128 channels, staged as fp32
+//          [channel group][sample][8] (group stride padded by 16 B); row-major side: (<= 256 B) x 128 samples per tile,
+//          slab side: 2 KB per channel group;
+//   narrow (Cp == 8, a few channels, any vertex permutation): tile = 32 consecutive rows IN THE CALLER'S NUMBERING x one
+//          chunk, staged as [sample][row x channel]; row-major side: 32 rows x Cs contiguous elements per sample (coalesced
+//          4-byte accesses), slab side: 2 KB per row, scattered by the inverse permutation.
+constexpr int CV_THREADS = 256;
+constexpr int CV_GROUP_STRIDE = CHUNK * 32 + 16;   // bytes between channel groups of a wide tile (fp32 x 8 per sample, + pad)
+
+template <int P> __device__ __forceinline__ void cv_load_slab8(const uint8_t* p, size_t plane_b, float* v) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), v);
+  if (P == 2) {
+    float l[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p + plane_b)), l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += l[e];
+  }
+}
+template <int P> __device__ __forceinline__ void cv_store_slab8(uint8_t* p, size_t plane_b, const float* v) {
+  if (P == 1) {
+    *reinterpret_cast<uint4*>(p) = pack8(v);
+  } else {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + plane_b) = lo;
+  }
+}
+
+// LG = log2(channel groups per tile) (1..4); tiles = R * NB * nsl, nsl = Cp / (8 << LG)
+template <typename T, int P, int LG>
+__global__ void __launch_bounds__(CV_THREADS) slab_from_rows_wide_kernel(const T* __restrict__ src, const int32_t* __restrict__ perm,
+                                                                         uint8_t* __restrict__ dst,
+                                                                         const uint8_t* __restrict__ ymul, int B, int R, int Cp,
+                                                                         int act_mul, int zero_last, int nsl) {
+  extern __shared__ __align__(16) uint8_t cv_smem[];
+  constexpr int G = 1 << LG;                       // channel groups per tile
+  constexpr int ITEMS = CHUNK * G / CV_THREADS;    // (group, sample) items per thread and phase
+  const int NB = num_chunks(B), tid = threadIdx.x;
+  const size_t slab_b = slab_bytes(Cp, P), plane_b = (size_t)Cp * 256;
+  const int tiles = R * NB * nsl;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int sl = tile % nsl, rq = tile / nsl, q = rq % NB, r = rq / NB;
+    const bool zero = zero_last && r == R - 1;
+    const int rs = perm != nullptr ? __ldg(perm + r) : r;
+    // phase 1: row-major side, channel group fastest (a sample's channels are contiguous)
+    {
+      const int cc = tid & (G - 1);
+      float v[ITEMS][8];
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int bl = (tid >> LG) + k * (CV_THREADS >> LG), b = q * CHUNK + bl;
+        if (b < B && !zero) {
+          Io<T>::ld8(src + ((size_t)b * R + rs) * Cp + (size_t)(sl * G + cc) * 8, v[k]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int bl = (tid >> LG) + k * (CV_THREADS >> LG);
+        float4* d = reinterpret_cast<float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
+        d[0] = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+        d[1] = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
+      }
+    }
+    __syncthreads();
+    // phase 2: slab side, sample fastest
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int it = tid + k * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
+      const float4* t4 = reinterpret_cast<const float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
+      const float4 a = t4[0], c = t4[1];
+      float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      const size_t doff = ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16;
+      if (ymul != nullptr && !zero && q * CHUNK + bl < B) {
+        float y[8];
+        cv_load_slab8<P>(ymul + doff, plane_b, y);
+        act_bwd8(v, y, act_mul);
+      }
+      cv_store_slab8<P>(dst + doff, plane_b, v);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int P, int LG>
+__global__ void __launch_bounds__(CV_THREADS) slab_to_rows_wide_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ perm,
+                                                                       T* __restrict__ dst, int B, int R, int Cp, int nsl) {
+  extern __shared__ __align__(16) uint8_t cv_smem[];
+  constexpr int G = 1 << LG;
+  constexpr int ITEMS = CHUNK * G / CV_THREADS;
+  const int NB = num_chunks(B), tid = threadIdx.x;
+  const size_t slab_b = slab_bytes(Cp, P), plane_b = (size_t)Cp * 256;
+  const int tiles = R * NB * nsl;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int sl = tile % nsl, rq = tile / nsl, q = rq % NB, r = rq / NB;
+    const int rd = perm != nullptr ? __ldg(perm + r) : r;
+    {
+      float v[ITEMS][8];
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int it = tid + k * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
+        cv_load_slab8<P>(src + ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16, plane_b, v[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int it = tid + k * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
+        float4* d = reinterpret_cast<float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
+        d[0] = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+        d[1] = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
+      }
+    }
+    __syncthreads();
+    const int cc = tid & (G - 1);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int bl = (tid >> LG) + k * (CV_THREADS >> LG), b = q * CHUNK + bl;
+      if (b < B) {
+        const float4* t4 = reinterpret_cast<const float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
+        const float4 a = t4[0], c = t4[1];
+        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        T* d = dst + ((size_t)b * R + rd) * Cp + (size_t)(sl * G + cc) * 8;
+        Io<T>::st4(d, v);
+        Io<T>::st4(d + 4, v + 4);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int CV_ROWS = 32;   // rows (caller's numbering) per narrow tile
+
+// pos[c] = internal row of the caller's row c (the inverse of perm; null: identity).  Cs <= 8 channels, Cp == 8.
+template <typename T, int P>
+__global__ void __launch_bounds__(CV_THREADS) slab_from_rows_narrow_kernel(const T* __restrict__ src, const int32_t* __restrict__ pos,
+                                                                           uint8_t* __restrict__ dst,
+                                                                           const uint8_t* __restrict__ ymul, int B, int R, int Cs,
+                                                                           int act_mul, int zero_last) {
+  extern __shared__ __align__(16) uint8_t cv_smem[];
+  float* t = reinterpret_cast<float*>(cv_smem);
+  const int NB = num_chunks(B), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stride = (CV_ROWS * Cs) | 1;            // floats per sample in the tile: odd, so that a warp's samples hit 32 banks
+  const size_t slab_b = slab_bytes(8, P), plane_b = 8 * 256;
+  const int rblocks = (R + CV_ROWS - 1) / CV_ROWS, tiles = rblocks * NB;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int q = tile / rblocks, c0 = (tile - q * rblocks) * CV_ROWS;
+    const int nrows = R - c0 < CV_ROWS ? R - c0 : CV_ROWS, len = nrows * Cs;
+    // phase 1: a warp takes samples warp, warp + 8, ...; its lanes walk the len contiguous elements of a sample, the loads of
+    // all 16 samples of the warp in flight together
+    for (int e = lane; e < len; e += 32) {
+      float tmp[CHUNK / (CV_THREADS / 32)];
+#pragma unroll
+      for (int k = 0; k < CHUNK / (CV_THREADS / 32); ++k) {
+        const int b = q * CHUNK + warp + k * (CV_THREADS / 32);
+        tmp[k] = b < B ? Io<T>::ld(src + ((size_t)b * R + c0) * Cs + e) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < CHUNK / (CV_THREADS / 32); ++k) t[(warp + k * (CV_THREADS / 32)) * stride + e] = tmp[k];
+    }
+    __syncthreads();
+    // phase 2: one item = (row, sample), sample fastest: 2 KB contiguous per row on the slab side
+    for (int it = tid; it < nrows * CHUNK; it += CV_THREADS) {
+      const int j = it >> 7, bl = it & (CHUNK - 1);
+      const int ri = pos != nullptr ? __ldg(pos + c0 + j) : c0 + j;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      const size_t doff = ((size_t)ri * NB + q) * slab_b + (size_t)bl * 16;
+      if (q * CHUNK + bl < B && !(zero_last && ri == R - 1)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e < Cs) v[e] = t[bl * stride + j * Cs + e];
+        if (ymul != nullptr) {
+          float y[8];
+          cv_load_slab8<P>(ymul + doff, plane_b, y);
+          act_bwd8(v, y, act_mul);
+        }
+      }
+      cv_store_slab8<P>(dst + doff, plane_b, v);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int P>
+__global__ void __launch_bounds__(CV_THREADS) slab_to_rows_narrow_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ pos,
+                                                                         T* __restrict__ dst, int B, int R, int Cd) {
+  extern __shared__ __align__(16) uint8_t cv_smem[];
+  float* t = reinterpret_cast<float*>(cv_smem);
+  const int NB = num_chunks(B), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stride = (CV_ROWS * Cd) | 1;
+  const size_t slab_b = slab_bytes(8, P), plane_b = 8 * 256;
+  const int rblocks = (R + CV_ROWS - 1) / CV_ROWS, tiles = rblocks * NB;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int q = tile / rblocks, c0 = (tile - q * rblocks) * CV_ROWS;
+    const int nrows = R - c0 < CV_ROWS ? R - c0 : CV_ROWS, len = nrows * Cd;
+#pragma unroll 4
+    for (int it = tid; it < nrows * CHUNK; it += CV_THREADS) {
+      const int j = it >> 7, bl = it & (CHUNK - 1);
+      const int ri = pos != nullptr ? __ldg(pos + c0 + j) : c0 + j;
+      float v[8];
+      cv_load_slab8<P>(src + ((size_t)ri * NB + q) * slab_b + (size_t)bl * 16, plane_b, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e < Cd) t[bl * stride + j * Cd + e] = v[e];
+    }
+    __syncthreads();
+    for (int bl = warp; bl < CHUNK; bl += CV_THREADS / 32) {
+      const int b = q * CHUNK + bl;
+      if (b < B) {
+        T* d = dst + ((size_t)b * R + c0) * Cd;
+        for (int e = lane; e < len; e += 32) Io<T>::st(d + e, t[bl * stride + e]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static inline int cv_log2_groups(int Cp) {   // wide tiles: 2, 4, 8 or 16 channel groups (Cp = 256: two tiles per slab)
+  switch (Cp) {
+    case 16: return 1;
+    case 32: return 2;
+    case 64: return 3;
+    case 128: case 256: return 4;
+    default: return 0;
+  }
+}
+
 static inline int stream_grid(long long work_items, int per_block) {
   long long g = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * 16;
@@ -416,13 +651,67 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
   return 0;
 }
 
-int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, void* dst, const void* ymul, int B, int R, int Cs,
-                       int Cp, int act_mul, int zero_last, int planes, void* stream) {
+int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, const int32_t* perm_inv, void* dst, const void* ymul,
+                       int B, int R, int Cs, int Cp, int act_mul, int zero_last, int planes, void* stream) {
   if (!src || !dst || B <= 0 || R <= 0 || Cs <= 0 || Cp < Cs || (Cp & 7) || planes < 1 || planes > 2) return SHB_E_ARG;
   if (src_dtype != SHB_F32 && src_dtype != SHB_BF16) return SHB_E_DTYPE;
-  const long long total = (((long long)R * (Cp / 8) + 7) / 8) * 8 * CHUNK * slab::num_chunks(B);
-  const int grid = stream_grid(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  const int NB = slab::num_chunks(B);
+  const int lg = Cs == Cp ? cv_log2_groups(Cp) : 0;
+  if (Cp == 8 && (perm == nullptr || perm_inv != nullptr) && (long long)((R + CV_ROWS - 1) / CV_ROWS) * NB < (1LL << 31)) {
+    // tiles in the caller's numbering
+    const int tiles = (R + CV_ROWS - 1) / CV_ROWS * NB;
+    const size_t smem = (size_t)CHUNK * ((CV_ROWS * Cs) | 1) * sizeof(float);
+    const int per_sm = (int)(200 * 1024 / smem) < 8 ? (int)(200 * 1024 / smem) : 8;
+    const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
+#define SHB_FRN(T, PL)                                                                                                        \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) {                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(slab_from_rows_narrow_kernel<T, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           (int)smem);                                                                        \
+      if (e != cudaSuccess) return (int)e;                                                                                    \
+    }                                                                                                                         \
+    slab_from_rows_narrow_kernel<T, PL><<<grid, CV_THREADS, smem, st>>>((const T*)src, perm_inv, (uint8_t*)dst,               \
+                                                                        (const uint8_t*)ymul, B, R, Cs, act_mul, zero_last);  \
+  } while (0)
+    if (src_dtype == SHB_F32) { if (planes == 1) SHB_FRN(float, 1); else SHB_FRN(float, 2); }
+    else { if (planes == 1) SHB_FRN(__nv_bfloat16, 1); else SHB_FRN(__nv_bfloat16, 2); }
+#undef SHB_FRN
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
+  if (lg > 0 && (long long)R * NB * (Cp / (8 << lg)) < (1LL << 31)) {
+    const int nsl = Cp / (8 << lg), tiles = R * NB * nsl;
+    const size_t smem = (size_t)(1 << lg) * CV_GROUP_STRIDE;
+    const int per_sm = (int)(200 * 1024 / smem) < 8 ? (int)(200 * 1024 / smem) : 8;
+    const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
+#define SHB_FRW(T, PL, LG)                                                                                                    \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) {                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(slab_from_rows_wide_kernel<T, PL, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize,\
+                                           (int)smem);                                                                        \
+      if (e != cudaSuccess) return (int)e;                                                                                    \
+    }                                                                                                                         \
+    slab_from_rows_wide_kernel<T, PL, LG><<<grid, CV_THREADS, smem, st>>>((const T*)src, perm, (uint8_t*)dst,                 \
+                                                                          (const uint8_t*)ymul, B, R, Cp, act_mul, zero_last, \
+                                                                          nsl);                                               \
+  } while (0)
+#define SHB_FRW_LG(T, PL)                   \
+  switch (lg) {                             \
+    case 1: SHB_FRW(T, PL, 1); break;       \
+    case 2: SHB_FRW(T, PL, 2); break;       \
+    case 3: SHB_FRW(T, PL, 3); break;       \
+    default: SHB_FRW(T, PL, 4); break;      \
+  }
+    if (src_dtype == SHB_F32) { if (planes == 1) { SHB_FRW_LG(float, 1) } else { SHB_FRW_LG(float, 2) } }
+    else { if (planes == 1) { SHB_FRW_LG(__nv_bfloat16, 1) } else { SHB_FRW_LG(__nv_bfloat16, 2) } }
+#undef SHB_FRW_LG
+#undef SHB_FRW
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
+  const long long total = (((long long)R * (Cp / 8) + 7) / 8) * 8 * CHUNK * NB;
+  const int grid = stream_grid(total, 256);
 #define SHB_FR(T, PL)                                                                                                          \
   slab_from_rows_kernel<T, PL><<<grid, 256, 0, st>>>((const T*)src, perm, (uint8_t*)dst, (const uint8_t*)ymul, B, R, Cs, Cp, \
                                                      act_mul, zero_last)
@@ -433,13 +722,63 @@ int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, void
   return 0;
 }
 
-int shb_slab_to_rows(const void* src, const int32_t* perm, void* dst, int dst_dtype, int B, int R, int Cp, int Cd, int planes,
-                     void* stream) {
+int shb_slab_to_rows(const void* src, const int32_t* perm, const int32_t* perm_inv, void* dst, int dst_dtype, int B, int R, int Cp,
+                     int Cd, int planes, void* stream) {
   if (!src || !dst || B <= 0 || R <= 0 || Cd <= 0 || Cp < Cd || (Cp & 7) || planes < 1 || planes > 2) return SHB_E_ARG;
   if (dst_dtype != SHB_F32 && dst_dtype != SHB_BF16) return SHB_E_DTYPE;
-  const long long total = (((long long)R * ((Cd + 7) / 8) + 7) / 8) * 8 * CHUNK * slab::num_chunks(B);
-  const int grid = stream_grid(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  const int NB = slab::num_chunks(B);
+  const int lg = Cd == Cp ? cv_log2_groups(Cp) : 0;
+  if (Cp == 8 && (perm == nullptr || perm_inv != nullptr) && (long long)((R + CV_ROWS - 1) / CV_ROWS) * NB < (1LL << 31)) {
+    const int tiles = (R + CV_ROWS - 1) / CV_ROWS * NB;
+    const size_t smem = (size_t)CHUNK * ((CV_ROWS * Cd) | 1) * sizeof(float);
+    const int per_sm = (int)(200 * 1024 / smem) < 8 ? (int)(200 * 1024 / smem) : 8;
+    const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
+#define SHB_TRN(T, PL)                                                                                                       \
+  do {                                                                                                                       \
+    if (smem > 48 * 1024) {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(slab_to_rows_narrow_kernel<T, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem);                                                                       \
+      if (e != cudaSuccess) return (int)e;                                                                                   \
+    }                                                                                                                        \
+    slab_to_rows_narrow_kernel<T, PL><<<grid, CV_THREADS, smem, st>>>((const uint8_t*)src, perm_inv, (T*)dst, B, R, Cd);     \
+  } while (0)
+    if (dst_dtype == SHB_F32) { if (planes == 1) SHB_TRN(float, 1); else SHB_TRN(float, 2); }
+    else { if (planes == 1) SHB_TRN(__nv_bfloat16, 1); else SHB_TRN(__nv_bfloat16, 2); }
+#undef SHB_TRN
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
+  if (lg > 0 && (long long)R * NB * (Cp / (8 << lg)) < (1LL << 31)) {
+    const int nsl = Cp / (8 << lg), tiles = R * NB * nsl;
+    const size_t smem = (size_t)(1 << lg) * CV_GROUP_STRIDE;
+    const int per_sm = (int)(200 * 1024 / smem) < 8 ? (int)(200 * 1024 / smem) : 8;
+    const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
+#define SHB_TRW(T, PL, LG)                                                                                                   \
+  do {                                                                                                                       \
+    if (smem > 48 * 1024) {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(slab_to_rows_wide_kernel<T, PL, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem);                                                                       \
+      if (e != cudaSuccess) return (int)e;                                                                                   \
+    }                                                                                                                        \
+    slab_to_rows_wide_kernel<T, PL, LG><<<grid, CV_THREADS, smem, st>>>((const uint8_t*)src, perm, (T*)dst, B, R, Cp, nsl);  \
+  } while (0)
+#define SHB_TRW_LG(T, PL)                   \
+  switch (lg) {                             \
+    case 1: SHB_TRW(T, PL, 1); break;       \
+    case 2: SHB_TRW(T, PL, 2); break;       \
+    case 3: SHB_TRW(T, PL, 3); break;       \
+    default: SHB_TRW(T, PL, 4); break;      \
+  }
+    if (dst_dtype == SHB_F32) { if (planes == 1) { SHB_TRW_LG(float, 1) } else { SHB_TRW_LG(float, 2) } }
+    else { if (planes == 1) { SHB_TRW_LG(__nv_bfloat16, 1) } else { SHB_TRW_LG(__nv_bfloat16, 2) } }
+#undef SHB_TRW_LG
+#undef SHB_TRW
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
+  const long long total = (((long long)R * ((Cd + 7) / 8) + 7) / 8) * 8 * CHUNK * NB;
+  const int grid = stream_grid(total, 256);
 #define SHB_TR(T, PL) slab_to_rows_kernel<T, PL><<<grid, 256, 0, st>>>((const uint8_t*)src, perm, (T*)dst, B, R, Cp, Cd)
   if (dst_dtype == SHB_F32) { if (planes == 1) SHB_TR(float, 1); else SHB_TR(float, 2); }
   else { if (planes == 1) SHB_TR(__nv_bfloat16, 1); else SHB_TR(__nv_bfloat16, 2); }

@@ -162,6 +162,7 @@ class _SpiralTrunk(nn.Module):
             self._pD = [self._pD[i].permuted(full[i + 1], full[i]) for i in range(n_levels)]
             self._pU = [self._pU[i].permuted(full[i], full[i + 1]) for i in range(n_levels)]
         self._perm_dev = None if self._perm is None else torch.as_tensor(full[0], dtype=torch.int32, device=dev)
+        slab.inverse_perm(self._perm_dev)   # built now (and kept on the tensor): never inside a graph capture
         # a pool keeps the dummy row zero only if its last row is exactly e_dummy (main.py:190-191 builds it that way)
         d_ok = [pm.dummy_preserving for pm in self._pD]
         u_ok = [pm.dummy_preserving for pm in self._pU]

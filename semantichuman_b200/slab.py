@@ -74,11 +74,25 @@ def _dt(t):
     raise TypeError(f"semantichuman_b200 supports float32 and bfloat16 tensors, got {t.dtype}")
 
 
+def inverse_perm(perm):
+    """perm_inv[perm[i]] = i, made once per permutation tensor and kept on it (the 3-channel conversions walk the caller's
+    tensor in the caller's order and need the inverse map; built eagerly by the models, so never inside a graph capture)."""
+    if perm is None:
+        return None
+    inv = getattr(perm, "_shb_inv", None)
+    if inv is None or inv.device != perm.device:
+        inv = torch.empty_like(perm)
+        inv[perm.long()] = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
+        perm._shb_inv = inv
+    return inv
+
+
 def _from_rows_raw(x, perm, Cp, planes, ymul=None, act_mul=0, zero_last=False):
     B, R, Cs = x.shape
     out = torch.empty(Slab.shape_for(R, B, Cp, planes), dtype=torch.bfloat16, device=x.device)
     _call(f"slab_from_rows[{R}x{Cs}>{Cp}]", {"bytes": float(B) * R * (Cs * x.element_size() + Cp * 2 * planes)},
-          lib.shb_slab_from_rows, _p(x), _dt(x), _p(perm), _p(out), _p(ymul), B, R, Cs, Cp, int(act_mul), int(bool(zero_last)),
+          lib.shb_slab_from_rows, _p(x), _dt(x), _p(perm), _p(inverse_perm(perm)), _p(out), _p(ymul), B, R, Cs, Cp, int(act_mul),
+          int(bool(zero_last)),
           planes, _stream())
     _count()
     return out
@@ -87,7 +101,7 @@ def _from_rows_raw(x, perm, Cp, planes, ymul=None, act_mul=0, zero_last=False):
 def _to_rows_raw(t, perm, B, R, Cp, Cd, planes, dtype):
     out = torch.empty((B, R, Cd), dtype=dtype, device=t.device)
     _call(f"slab_to_rows[{R}x{Cp}>{Cd}]", {"bytes": float(B) * R * (Cd * out.element_size() + Cp * 2 * planes)},
-          lib.shb_slab_to_rows, _p(t), _p(perm), _p(out), _dt(out), B, R, Cp, Cd, planes, _stream())
+          lib.shb_slab_to_rows, _p(t), _p(perm), _p(inverse_perm(perm)), _p(out), _dt(out), B, R, Cp, Cd, planes, _stream())
     _count()
     return out
 

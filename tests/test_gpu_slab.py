@@ -33,10 +33,10 @@ def _bf16(t):
 
 
 @pytest.mark.parametrize("B", [1, 3, 130, 256])
-@pytest.mark.parametrize("C", [3, 16, 24, 128])
+@pytest.mark.parametrize("C", [3, 8, 16, 24, 32, 64, 128, 256])
 @pytest.mark.parametrize("planes", [1, 2])
 def test_rows_slab_round_trip(sl, B, C, planes):
-    R = 37
+    R = 37 if C < 256 else 5
     g = torch.Generator().manual_seed(B * 1000 + C)
     x = torch.randn(B, R, C, generator=g)
     perm = torch.randperm(R, generator=g).to(torch.int32)
@@ -53,6 +53,46 @@ def test_rows_slab_round_trip(sl, B, C, planes):
     assert relerr(back, x) <= tol
     if planes == 1:
         assert torch.equal(back.cpu(), _bf16(x))
+
+
+def _slab_values(s):
+    """Slab tensor -> (rows, NB*128, Cp) fp32 on the CPU (planes summed)."""
+    raw = s.t.detach().float().cpu()  # (R, NB, P, Cp/8, 128, 8)
+    return raw.sum(2).permute(0, 1, 3, 2, 4).reshape(s.rows, -1, s.Cp)
+
+
+@pytest.mark.parametrize("C", [3, 32, 128])
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("use_perm", [False, True])
+def test_rows_slab_conversions_bf16_rows_and_gradient_path(sl, C, planes, use_perm):
+    """The tiled conversion kernels with bf16 row tensors, without a permutation, over several row tiles and a ragged batch
+    chunk, and the gradient path of to_rows: incoming gradient times act'(y) of the slab's producer, dummy row masked."""
+    R, B = 70, 131
+    g = torch.Generator().manual_seed(C * 7 + planes)
+    x = torch.randn(B, R, C, generator=g)
+    perm = torch.randperm(R, generator=g).to(torch.int32).to(DEV) if use_perm else None
+    pl = perm.long().cpu() if use_perm else torch.arange(R)
+    xb = x.bfloat16()
+    s = sl.from_rows(xb.to(DEV), perm, planes)
+    val = _slab_values(s)
+    assert torch.equal(val[:, :B, :C], xb.float()[:, pl, :].permute(1, 0, 2))
+    assert (val[:, B:, :] == 0).all() and (val[:, :, C:] == 0).all()
+    back = sl.to_rows(s, perm, torch.bfloat16)
+    assert back.dtype == torch.bfloat16 and torch.equal(back.cpu(), xb)
+    # gradient path: y = the slab above taken as an ELU layer's masked output
+    s.t.requires_grad_(True)
+    s.act, s.masked = 2, True
+    out = sl.to_rows(s, perm, torch.float32)
+    go = torch.randn(B, R, C, generator=g)
+    out.backward(go.to(DEV))
+    gs = sl.Slab(s.t.grad, s.rows, s.B, s.C, s.Cp, s.planes, 0, False)
+    got = _slab_values(gs)
+    y = val[:, :B, :C]
+    want = go[:, pl, :].permute(1, 0, 2) * (torch.clamp(y, max=0.0) + 1.0)
+    want[-1] = 0
+    tol = 2.0 ** -8 if planes == 1 else 2.0 ** -15
+    assert relerr(got[:, :B, :C], want) <= tol
+    assert (got[:, B:, :] == 0).all() and (got[:, :, C:] == 0).all() and (got[-1] == 0).all()
 
 
 def _conv_case(g, k):
