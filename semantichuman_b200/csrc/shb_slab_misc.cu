@@ -621,13 +621,16 @@ int shb_slab_pool(const void* src, const int32_t* rowptr, const int32_t* colidx,
   // one warp per unit; a unit's vectors are cut into slices (>= 128 vectors: four per lane, an even count) until every
   // resident warp has a few units (few, long rows -- the per-slot sums of the dummy-row gradient -- are what needs the cut)
   int nslice = 1;
-  const long long want = 4LL * kNumSMs * 24;
+  const long long want = 8LL * kNumSMs * 24;
   while ((long long)rows_out * NB * nslice < want && nvec / (nslice * 2) >= 128 && (nvec / (nslice * 2)) % 64 == 0) nslice *= 2;
   if ((nvec / nslice) % 64) return SHB_E_ARG;   // cannot happen: nvec is a multiple of 128 and the loop keeps slices multiples of 64
   const long long units = (long long)rows_out * NB * nslice;
   if (units >= (1LL << 31)) return SHB_E_ARG;
   const long long blocks = (units + POOL_WARPS - 1) / POOL_WARPS;
-  const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+  // as many blocks as are resident (launch bounds of the kernel): every warp walks its units with the requests of the next
+  // one and two units in flight (measured against 8 blocks per SM: step 1.810 -> 1.799 ms)
+  const long long resident = (long long)kNumSMs * (planes == 1 ? 3 : 2);
+  const int grid = (int)(blocks < resident ? blocks : resident);
   const int threads = POOL_WARPS * 32;
   cudaStream_t st = (cudaStream_t)stream;
   const int act = ymul ? act_mul : SHB_ACT_IDENTITY;   // the kernel is compiled per activation: no switch inside the vector loop
