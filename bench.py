@@ -381,7 +381,7 @@ def run_own(args):
         oms = o0.elapsed_time(o1) / n_other
         other = {"dtype": "f32" if odt == torch.float32 else "bf16", "ms_per_step": oms, "value": B / (oms * 1e-3),
                  "unit": "meshes/s", "steps": n_other,
-                 "note": "fp32 mode: activations and weights as bf16 hi + lo, four tcgen05 products per term, fp32 accumulation; "
+                 "note": "fp32 mode: activations and weights as bf16 hi + lo, three tcgen05 products per term (hi.hi + lo.hi + hi.lo), fp32 accumulation; "
                          "1e-4 parity (the reference's own precision)" if odt == torch.float32 else
                          "bf16 mode: bf16 operands, fp32 accumulation and master weights; 2e-2 parity"}
         model.set_compute_dtype(dtype)
@@ -421,7 +421,7 @@ def main():
     ap.add_argument("--impl", default="shb200", choices=["shb200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"],
                     help="bf16 (default): bf16 operands / fp32 accumulate on the tcgen05 kernels, north_star's 2e-2 mode; "
-                         "fp32: bf16 hi + lo operands (four products per term) on the same kernels, the 1e-4 mode")
+                         "fp32: bf16 hi + lo operands (three products per term) on the same kernels, the 1e-4 mode")
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")

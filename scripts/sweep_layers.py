@@ -51,7 +51,7 @@ def row(tag, op, shape, v):
     print(f"| {tag} | {op} | {shape} | {ms:.4f} | {gbs:.0f} | {100 * gbs / hbm:.1f} % | {tfs:.1f} | {100 * tfs / tf:.1f} % |", flush=True)
 
 
-print(f"B = {B}, {a.dtype} mode ({'bf16 operands' if planes == 1 else 'bf16 hi + lo operands, 4 products'}), vertex order: "
+print(f"B = {B}, {a.dtype} mode ({'bf16 operands' if planes == 1 else 'bf16 hi + lo operands, 3 products'}), vertex order: "
       f"{'mesh numbering' if a.no_reorder else 'locality order (as in the models)'}; peaks: HBM {hbm:.0f} GB/s, bf16 {tf:.0f} TFLOP/s (measured)\n")
 print("| hierarchy / spirals | op | shape (rows_in > rows_out x S x Cin > Cout) | ms | GB/s (algorithmic) | of HBM peak | TFLOP/s | of bf16 peak |")
 print("|---|---|---|---|---|---|---|---|")

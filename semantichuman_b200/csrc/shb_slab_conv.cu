@@ -280,10 +280,9 @@ __global__ void __launch_bounds__(DUAL ? SC_DUAL_THREADS : SC_MAX_THREADS, DUAL 
               for (uint32_t kk = 0; kk < (uint32_t)NK; ++kk) {
                 mma_bf16(tmem_d, hi_a | la, hi_b | lb, idesc, acc);
                 acc = 1;
-                if (P == 2) {  // x ~ xh + xl, w ~ wh + wl: all four partial products (the tensor pipe is far from the bound)
+                if (P == 2) {  // x ~ xh + xl, w ~ wh + wl: xh.wh + xl.wh + xh.wl; xl.wl (<= 2^-18 of the term) is dropped
                   mma_bf16(tmem_d, hi_a | (la + plane_a), hi_b | lb, idesc, 1);
                   mma_bf16(tmem_d, hi_a | la, hi_b | (lb + plane_b), idesc, 1);
-                  mma_bf16(tmem_d, hi_a | (la + plane_a), hi_b | (lb + plane_b), idesc, 1);
                 }
                 la += 2 * PLANE_STRIDE >> 4;
                 lb += 16;

@@ -410,10 +410,9 @@ __global__ void __launch_bounds__(DUAL ? GC_DUAL_THREADS : GC_MAX_THREADS, DUAL 
             if (pi + 1 < np) nxt = mp[0];  // the next pair's words are on their way while this pair's MMAs issue
             uint32_t la = m.x, lb = m.y;
             mma_bf16(m.z, hi_a | la, hi_b | lb, idesc, m.w);
-            if (P == 2) {  // x ~ xh + xl, w ~ wh + wl: all four partial products
+            if (P == 2) {  // x ~ xh + xl, w ~ wh + wl: xh.wh + xl.wh + xh.wl; xl.wl (<= 2^-18 of the term) is dropped
               mma_bf16(m.z, hi_a | (la + plane_a), hi_b | lb, idesc, 1);
               mma_bf16(m.z, hi_a | la, hi_b | (lb + plane_b), idesc, 1);
-              mma_bf16(m.z, hi_a | (la + plane_a), hi_b | (lb + plane_b), idesc, 1);
             }
 #pragma unroll
             for (uint32_t kk = 1; kk < (uint32_t)NK; ++kk) {
@@ -423,7 +422,6 @@ __global__ void __launch_bounds__(DUAL ? GC_DUAL_THREADS : GC_MAX_THREADS, DUAL 
               if (P == 2) {
                 mma_bf16(m.z, hi_a | (la + plane_a), hi_b | lb, idesc, 1);
                 mma_bf16(m.z, hi_a | la, hi_b | (lb + plane_b), idesc, 1);
-                mma_bf16(m.z, hi_a | (la + plane_a), hi_b | (lb + plane_b), idesc, 1);
               }
             }
           }

@@ -156,10 +156,9 @@ __global__ void __launch_bounds__(SW_THREADS, DUAL ? 2 : 1) slab_wgrad_kernel(co
           for (uint32_t kk = 0; kk < 8; ++kk) {  // 16 samples per MMA: 2 x 128 B
             const uint32_t la = lo_a + kk * 16, lg = lo_g + kk * 16;
             mma_bf16(tmem_d, hi | la, hi | lg, idesc, (tcount > 0 || kk > 0) ? 1u : 0u);
-            if (P == 2) {  // xh.gh + xl.gh + xh.gl + xl.gl
+            if (P == 2) {  // xh.gh + xl.gh + xh.gl; xl.gl (<= 2^-18 of the term) is dropped
               mma_bf16(tmem_d, hi | (la + (SW_GROUP_BYTES >> 4)), hi | lg, idesc, 1);
               mma_bf16(tmem_d, hi | la, hi | (lg + (gz_plane_b >> 4)), idesc, 1);
-              mma_bf16(tmem_d, hi | (la + (SW_GROUP_BYTES >> 4)), hi | (lg + (gz_plane_b >> 4)), idesc, 1);
             }
           }
           mma_commit_u32(empty0 + slot * 8);
