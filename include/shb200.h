@@ -122,9 +122,12 @@ int shb_group_linear_scatter_bwd(const float* zz, const int32_t* idx, const int3
  * fwd writes the loss and keeps the per-part normalisers in the workspace (parts must not overlap).  Fixed-order reductions.
  * kps (B, NK, 3); idx, gptr, bone (G,3), wmode (G) int32 and part_weight (G), scale (B,G) fp32 are device arrays. */
 size_t shb_pair_loss_workspace(int B, int G, int max_part_rows);
-/* grad_acc: (B, V, 3) fp32 or NULL.  When given, the forward pass also leaves the unscaled per-vertex gradient there, and
- * shb_pair_loss_bwd (same idx / gptr / workspace) only scales it: grec = 2 * coef[part] * gscale[0] * grad_acc, zero for
- * vertices outside every part.  One walk over the pairs serves loss and gradient. */
+/* grad_acc: a buffer of shb_pair_loss_grad_acc_bytes(B, G, max_part_rows) bytes, or NULL.  When given, the forward pass also
+ * leaves the unscaled gradient there -- every unordered vertex pair is evaluated once and credited to both of its vertices,
+ * per 128-vertex tile pair -- and shb_pair_loss_bwd (same idx / gptr / workspace) only sums a vertex's tile-pair slots in a
+ * fixed order and scales: grec = 2 * coef[part] * gscale[0] * sum, zero for vertices outside every part.  One walk over HALF
+ * the pairs serves loss and gradient. */
+size_t shb_pair_loss_grad_acc_bytes(int B, int G, int max_part_rows);
 int shb_pair_loss_fwd(const float* tx, const float* rec, const float* kps, const int32_t* idx, const int32_t* gptr,
                       const int32_t* bone, const int32_t* wmode, const float* part_weight, const float* scale,
                       float w_threshold, int relative, float* loss_out, float* grad_acc, void* workspace, size_t workspace_bytes,

@@ -24,6 +24,7 @@ SIGNATURES = {
     "shb_l1_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
     "shb_partnorm_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
     "shb_pair_loss_workspace": (c_size, [c_int] * 3),
+    "shb_pair_loss_grad_acc_bytes": (c_size, [c_int] * 3),
     "shb_pair_loss_fwd": (c_int, [c_vp] * 9 + [c_float, c_int, c_vp, c_vp, c_vp, c_size] + [c_int] * 5 + [c_vp]),
     "shb_pair_loss_bwd": (c_int, [c_vp] * 6 + [c_size] + [c_int] * 4 + [c_vp]),
     "shb_group_linear_gather_fwd": (c_int, [c_vp] * 8 + [c_int] * 5 + [c_vp]),

@@ -44,7 +44,6 @@ struct SlabConvParams {
   int act, act_mul, zero_last;
   int P;
   int nstage, SPS;
-  int dbg;                 // trace builds only: 1 = skip epilogue stores, 2 = skip activation math
   int cpw, EG;             // accumulator columns per epilogue warp (8/16/32), epilogue groups (threads = 96 + 128*EG)
   int num_tiles;
   uint32_t tmem_cols;
@@ -368,10 +367,7 @@ __global__ void __launch_bounds__(DUAL ? SC_DUAL_THREADS : SC_MAX_THREADS, DUAL 
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = (empty_tile ? 0.f : __uint_as_float(r[g][i])) + bias_s[col0 + 8 * g + i];
-#ifdef SHB_SLAB_TRACE
-        if (!(p.dbg & 2))
-#endif
-          act_fwd8(v, p.act);
+        act_fwd8(v, p.act);
         if (p.ymul != nullptr) {
           float y[8];
           unpack8(yv[g][0], y);
@@ -387,9 +383,6 @@ __global__ void __launch_bounds__(DUAL ? SC_DUAL_THREADS : SC_MAX_THREADS, DUAL 
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = 0.f;
         }
-#ifdef SHB_SLAB_TRACE
-        if ((p.dbg & 1) && v[0] != 12345.678f) continue;
-#endif
         if (P == 1) {
           *reinterpret_cast<uint4*>(drow + (size_t)g * PLANE_STRIDE) = pack8(v);
         } else {
@@ -498,7 +491,7 @@ static bool slab_conv_plan(int S, int CS, int NPt, int P, SlabConvPlan* out, siz
   const int Q = S * CS / 8;
   const size_t slab_b = (size_t)P * CS * 256;
   const size_t zero_b = CS == 8 ? PLANE_STRIDE : 0;
-  static const size_t stage_cap = [] { const char* e = getenv("SHB_SLAB_STAGE_KB"); return (size_t)(e ? atoi(e) : 64) * 1024; }();
+  constexpr size_t stage_cap = 64 * 1024;
   for (int NP = NPt > 256 ? 256 : NPt; NP >= 16; NP -= 16) {
     if (NPt % NP != 0 && NP != NPt) continue;  // equal passes
     const size_t img_region = (((size_t)P * NP * Q * 16 + (CS == 8 ? 128 : 0) + 1023) / 1024) * 1024;
@@ -630,9 +623,8 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
   slab_conv_plan(S, Cs, NPt, planes, &plan);
   // two CTAs per SM when the whole weight image and a >= 3-stage ring fit in half an SM and two epilogue groups cover the
   // accumulator (<= 64 columns)
-  static const bool allow_dual = [] { const char* e = getenv("SHB_SLAB_NO_DUAL"); return !(e && atoi(e)); }();
   SlabConvPlan dplan;
-  const bool dual = allow_dual && Cd <= 64 && slab_conv_plan(S, Cs, NPt, planes, &dplan, SC_SMEM_DUAL) && dplan.NP == NPt &&
+  const bool dual = Cd <= 64 && slab_conv_plan(S, Cs, NPt, planes, &dplan, SC_SMEM_DUAL) && dplan.NP == NPt &&
                     dplan.nstage >= 3;
   if (dual) plan = dplan;
   SlabConvParams p{};
@@ -648,14 +640,10 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
     p.NP = plan.NP; p.n0 = n0;
     p.ncols = Cd - n0 < plan.NP ? Cd - n0 : plan.NP;
     p.w_img = (const uint8_t*)w_img + (size_t)(n0 / 8) * p.Q * 128;
-    { static const int dbg = [] { const char* e = getenv("SHB_SLAB_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
     p.cpw = p.ncols >= 128 ? 32 : (p.ncols >= 64 ? 16 : 8);
     if (dual) p.cpw = p.ncols >= 64 ? 32 : (p.ncols >= 32 ? 16 : 8);
     p.EG = p.ncols / p.cpw;
-    {
-      static const int eg_cap = [] { const char* e = getenv("SHB_SLAB_EG"); return e ? atoi(e) : 4; }();  // tuning knob
-      while (p.EG > eg_cap && p.cpw < 32) { p.cpw *= 2; p.EG /= 2; }
-    }
+    while (p.EG > 4 && p.cpw < 32) { p.cpw *= 2; p.EG /= 2; }   // at most four epilogue groups (measured best)
     p.bias = bias ? bias + n0 : nullptr;
     p.nbias = Cd_real - n0 < p.ncols ? (Cd_real - n0 > 0 ? Cd_real - n0 : 0) : p.ncols;  // bias holds Cd_real entries
     uint32_t cols = 32;

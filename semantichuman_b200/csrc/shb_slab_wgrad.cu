@@ -370,11 +370,10 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
   slab_wgrad_plan(S, Cin_p, Cout_p, planes, &plan);
   cudaStream_t st = (cudaStream_t)stream;
   // two CTAs per SM when a >= 3-stage ring fits in half an SM and the whole accumulator in half of TMEM, in one pass
-  static const bool allow_dual = [] { const char* e = getenv("SHB_SLAB_NO_DUAL"); return !(e && atoi(e)); }();
   SlabWgradPlan dplan;
   // (only where a CTA has many tiles: every CTA costs one partial in the fixed-order reduction)
   const long long tiles_all = (long long)(skip_last ? rows_out - 1 : rows_out) * slab::num_chunks(B);
-  const bool dual = allow_dual && tiles_all >= 40LL * kNumSMs &&
+  const bool dual = tiles_all >= 40LL * kNumSMs &&
                     slab_wgrad_plan(S, Cin_p, Cout_p, planes, &dplan, SW_SMEM_DUAL, 256) && dplan.nstage >= 3 &&
                     dplan.Gp == dplan.G && dplan.N == pad16w(Cout_p);
   if (dual) plan = dplan;

@@ -345,9 +345,11 @@ class PairLossFn(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=tx.device)
         loss = torch.empty((), dtype=torch.float32, device=tx.device)
         # the gradient w.r.t. rec is accumulated (unscaled) by the same walk over the pairs when it will be needed
-        gacc = torch.empty_like(rec) if ctx.needs_input_grad[1] else None
+        gacc = None
+        if ctx.needs_input_grad[1]:   # per tile-pair slots: every unordered pair is evaluated once, credited to both vertices
+            gacc = torch.empty(lib.shb_pair_loss_grad_acc_bytes(B, lay.G, lay.max_rows) // 4, dtype=torch.float32, device=tx.device)
         pairs = float(B) * lay.pairs_per_sample
-        _call("pair_loss", {"bytes": 24.0 * tx.numel() / 3, "flops": 55.0 * pairs}, lib.shb_pair_loss_fwd, _p(tx), _p(rec),
+        _call("pair_loss", {"bytes": 24.0 * tx.numel() / 3, "flops": 27.5 * pairs}, lib.shb_pair_loss_fwd, _p(tx), _p(rec),
               _p(kps), _p(lay.idx), _p(lay.gptr), _p(lay.bone), _p(lay.wmode), _p(lay.pw), _p(scale), float(w_threshold),
               int(bool(relative)), _p(loss), _p(gacc), _p(ws), nbytes, B, V, kps.shape[1], lay.G, lay.max_rows, _stream())
         _count(2)
@@ -362,7 +364,7 @@ class PairLossFn(torch.autograd.Function):
         B, V = ctx.shape
         grec = None
         if ctx.needs_input_grad[1]:
-            grec = torch.empty_like(gacc)
+            grec = torch.empty((B, V, 3), dtype=torch.float32, device=gacc.device)
             gs = g.detach().float().contiguous()
             _call("pair_loss_bwd", {"bytes": 24.0 * B * V}, lib.shb_pair_loss_bwd, _p(gacc), _p(lay.idx), _p(lay.gptr), _p(gs),
                   _p(grec), _p(ws), ws.numel(), B, V, lay.G, lay.max_rows, _stream())
