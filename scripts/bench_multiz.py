@@ -81,6 +81,16 @@ for grouped in (True, False):
             res["bone_guided_step_graph" if use_graph else "bone_guided_step_eager"] = {
                 "ms": ms, "meshes_per_s": 3 * 256 / ms * 1e3, "loss": float(loss),
                 "note": "3 x 256 meshes per step (reconstruction, interpolation and exchange batches)"}
+    if grouped:
+        # per-entry-point CUDA-event times of one eager bone-guided step (families; the remainder is torch glue)
+        import collections, re
+        fn.TIMER = fn.KernelTimer()
+        bg(*data, meas)
+        fam = collections.defaultdict(float)
+        for k, v in fn.TIMER.summary().items():
+            fam[re.sub(r"\[.*", "", k)] += v["ms"]
+        fn.TIMER = None
+        res["bone_guided_step_families_ms"] = {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
     # ---- one training step (recon + part-norm loss), B = 256, eager
     from semantichuman_b200.optim import Adam
     opt = Adam(model.parameters(), lr=1e-3)
