@@ -34,6 +34,21 @@ struct PLParams {
 //   |d| = dd * rsqrt(dd),   cos = |d . k| * rsqrt(dd) / |k|,   Der / De = (rr * rsqrt(rr)) * rsqrt(dd) / sc.
 // abs_e = |e_ij|; q = sign(e) (w [/ De]) / Der, the factor of (r_i - r_j) in d|e|/d r_i (0 when the reconstructed points
 // coincide: the reference's sqrt'(0) gives NaN; 0 here).
+// acos on [0, 1]: sqrt(1 - x) * P7(x) (Abramowitz & Stegun 4.4.46, |error| <= 2e-8 before rounding) -- the library acosf is
+// ~25 instructions of the ~120 a pair costs.  acos(1) == 0 exactly (the mask (w * De) != 0 depends on it).
+__device__ __forceinline__ float pl_acos01(float x) {
+  float p = -0.0012624911f;
+  p = fmaf(p, x, 0.0066700901f);
+  p = fmaf(p, x, -0.0170881256f);
+  p = fmaf(p, x, 0.0308918810f);
+  p = fmaf(p, x, -0.0501743046f);
+  p = fmaf(p, x, 0.0889789874f);
+  p = fmaf(p, x, -0.2145988016f);
+  p = fmaf(p, x, 1.5707963050f);
+  const float om = 1.f - x;
+  return om > 0.f ? om * rsqrtf(om) * p : 0.f;
+}
+
 __device__ __forceinline__ bool pl_pair(const float3 vi, const float3 vj, const float3 ri, const float3 rj, const float3 kd,
                                         float inv_km, int mode, float thr, float sc, float inv_sc, int relative, float& abs_e,
                                         float& q, float& rx, float& ry, float& rz) {
@@ -49,11 +64,10 @@ __device__ __forceinline__ bool pl_pair(const float3 vi, const float3 vj, const 
     float c = fabsf(dx * kd.x + dy * kd.y + dz * kd.z) * inv_dm * inv_km;
     if (c != c) c = 1.f;  // NaN (zero-length bone) -> 1, utils_SH.py:462
     c = fminf(fmaxf(c, 0.f), 1.f);
-    const float ang = acosf(c) * (180.f / 3.14159265358979323846f);
     if (mode == 2) {
-      w = sinf(ang / 180.f * 3.14159265358979323846f);
+      w = sqrtf(fmaxf(1.f - c * c, 0.f));   // sin(acos(c)): the reference's sin(angle / 180 * pi) of the angle in degrees
     } else {
-      w = ang / 90.f;
+      w = pl_acos01(c) * (2.f / 3.14159265358979323846f);   // angle / 90 with the angle in degrees
       if (mode == 3 && w < thr) w = 0.f;
     }
   }
