@@ -279,3 +279,16 @@ def test_conv_group_program_covers_every_entry_once(R, SPS):
     want = [(j, int(e & 31), int(e >> 5)) for j in range(rows_dst) for e in ent[ptr[j]:ptr[j + 1]]]
     assert sorted(got) == sorted(want)
     assert sorted(int(d) for d in gdst if d >= 0) == list(range(rows_dst))
+
+
+def test_inverse_permutation_helper_is_cached_on_the_tensor():
+    """slab.inverse_perm (the perm_inv argument of shb_slab_from_rows / shb_slab_to_rows): perm_inv[perm[i]] = i, built once."""
+    import torch
+
+    from semantichuman_b200 import slab
+
+    g = torch.Generator().manual_seed(3)
+    perm = torch.randperm(101, generator=g).to(torch.int32)
+    inv = slab.inverse_perm(perm)
+    assert inv.dtype == torch.int32 and torch.equal(inv[perm.long()].long(), torch.arange(101))
+    assert slab.inverse_perm(perm) is inv and slab.inverse_perm(None) is None
