@@ -192,12 +192,14 @@ int shb_slab_conv(const void* src, const int32_t* ptr, const int32_t* entries, c
 
 /* SpiralConv weight / bias gradient (the two mm of models.py:45's autograd), K = batch on tcgen05:
  *   gw[o][s*Cin + c] = sum_{j,b} x[table[j,s]][b][c] * gz[j][b][o],   gb[o] = sum_{j,b} gz[j][b][o]   (gb may be NULL)
- * x (rows_in, B, Cin_p), gz (rows_out, B, Cout_p) slab tensors; per-CTA partials in `workspace`, added in CTA order. */
+ * x (rows_in, B, Cin_p), gz (rows_out, B, Cout_p) slab tensors; per-CTA partials in `workspace`, added in CTA order.
+ * zero_src_row: a row of x known to be all zero (the dummy vertex behind padded spiral slots, when its producer masked it), or
+ * -1; trailing 128-channel operand groups of a vertex that read nothing else are neither loaded nor multiplied. */
 int shb_slab_wgrad_supported(int S, int Cin_p, int Cout_p, int planes);
 size_t shb_slab_wgrad_workspace(int S, int Cin_p, int Cout_p, int planes);
 int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, float* gb, void* workspace,
                    size_t workspace_bytes, int B, int rows_out, int S, int Cin, int Cin_p, int Cout, int Cout_p, int skip_last,
-                   int planes, void* stream);
+                   int zero_src_row, int planes, void* stream);
 
 /* ---- Shared-source groups of a SpiralConv pass (host, CPU).  `ptr` (rows_dst+1) / `ent` ((source row << 5) | slot) are the
  * entry lists of a pass (forward: models.py:42's x[:, spiral_idx] per output row; input gradient: the inverse-spiral lists).

@@ -13,4 +13,6 @@ timeout 600 python scripts/bench_multiz.py > gpurun_out/ev_multiz.log 2>&1
 timeout 600 python scripts/bench_stress.py gpurun_out/ev_stress.json > gpurun_out/ev_stress.log 2>&1
 timeout 300 python scripts/bench_slab_pool.py > gpurun_out/ev_pool_bench.log 2>&1
 timeout 300 python scripts/bench_pair_loss.py > gpurun_out/ev_pair_loss.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gl_ --csv --log-file gpurun_out/ev_heads_launches.csv python scripts/profile_heads.py > /dev/null 2>&1
+DT=fp32 timeout 300 python scripts/bench_slab_pool.py > gpurun_out/ev_pool_bench_fp32.log 2>&1
 ls -la gpurun_out/ev_*

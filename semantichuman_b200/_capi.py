@@ -49,7 +49,7 @@ SIGNATURES = {
     "shb_slab_gconv": (c_int, [c_vp] * 5 + [c_int] * 3 + [c_vp] * 4 + [c_int] * 10 + [c_vp]),
     "shb_slab_wgrad_supported": (c_int, [c_int] * 4),
     "shb_slab_wgrad_workspace": (c_size, [c_int] * 4),
-    "shb_slab_wgrad": (c_int, [c_vp] * 6 + [c_size] + [c_int] * 9 + [c_vp]),
+    "shb_slab_wgrad": (c_int, [c_vp] * 6 + [c_size] + [c_int] * 10 + [c_vp]),
 }
 
 ACT_ENUM = {"identity": 0, "relu": 1, "elu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5}

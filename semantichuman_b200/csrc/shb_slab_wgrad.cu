@@ -39,8 +39,20 @@ struct SlabWgradParams {
   int ncols_gz;          // gz channels that exist in [n0, n0+N): min(N, Cout_p - n0)
   int PC, PPS, PPG;      // channels per piece (min(Cin,128)), pieces per slab, pieces per 128-channel group
   int P, nstage, num_tiles;
+  int zero_row;          // source row known to be all zero (the dummy vertex behind padded spiral slots), or -1
   uint32_t tmem_cols;
 };
+
+// Operand groups of this pass a tile needs: trailing groups whose slots all read the known-zero source row contribute nothing
+// and are neither loaded nor multiplied (level 0-1 spirals: 22 % of the 4-slot groups).  `mine` = the tile's table row, one
+// entry per lane.  A CTA's FIRST tile always runs every group: it is what zero-initialises the TMEM accumulators.
+__device__ __forceinline__ int wgrad_groups(const SlabWgradParams& p, int mine, int lane, bool first) {
+  if (first || p.zero_row < 0) return p.Gp;
+  const uint32_t real = __ballot_sync(0xFFFFFFFFu, lane < p.S && mine != p.zero_row);
+  const int slots = 32 - __clz(real);                         // 1 + last slot with a live source (0: none)
+  int g = (slots * p.PPS + p.PPG - 1) / p.PPG - p.g0;         // groups of the whole operand, minus the passes before this one
+  return g < 0 ? 0 : (g > p.Gp ? p.Gp : g);
+}
 
 // DUAL: two CTAs per SM (half the ring each) -- the sibling fills the issue slots the dependent role chains leave idle.
 template <int P, bool DUAL>
@@ -110,7 +122,8 @@ __global__ void __launch_bounds__(SW_THREADS, DUAL ? 2 : 1) slab_wgrad_kernel(co
         for (int pl = 0; pl < P; ++pl)
           bulk_load(gz0 + buf * gz_buf_b + pl * gz_plane_b, g + (size_t)pl * p.Cout_p * 256, gz_load_b, gfull0 + buf * 8);
       }
-      for (int gi = 0; gi < p.Gp; ++gi) {
+      const int ng = wgrad_groups(p, mine, lane, tcount == 0);
+      for (int gi = 0; gi < ng; ++gi) {
         if (((stage_no++) & 1u) != pw) {  // the other producer warp's stage
           if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
           continue;
@@ -135,19 +148,28 @@ __global__ void __launch_bounds__(SW_THREADS, DUAL ? 2 : 1) slab_wgrad_kernel(co
       mine = mine_n;
     }
   } else if (warp == 2) {
-    // ================================================================ MMA issuer (one elected thread: warp-uniform operands)
-    if (elect_one()) {
-      const uint32_t idesc = idesc_bf16_f32(CHUNK, p.N, 1, 1);
-      // MN-major, un-swizzled: LBO = 128 B (next 8 samples), SBO = 2048 B (next 8 channels)
-      const uint64_t hi = ((uint64_t)((uint32_t)PLANE_STRIDE >> 4) << 32) | ((uint64_t)1 << 46);
-      const uint32_t lbo = (128u >> 4) << 16;
-      uint32_t slot = 0, ph = 0;
-      int tcount = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+    // ================================================================ MMA issuer (one elected thread: warp-uniform operands;
+    // the whole warp reads the tile's table row, a tile ahead, to know how many operand groups the producers send)
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16_f32(CHUNK, p.N, 1, 1);
+    // MN-major, un-swizzled: LBO = 128 B (next 8 samples), SBO = 2048 B (next 8 channels)
+    const uint64_t hi = ((uint64_t)((uint32_t)PLANE_STRIDE >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t lbo = (128u >> 4) << 16;
+    uint32_t slot = 0, ph = 0;
+    int tcount = 0;
+    int mine = 0;
+    if ((int)blockIdx.x < p.num_tiles && lane < p.S && p.zero_row >= 0)
+      mine = __ldg(p.table + (size_t)(blockIdx.x / p.NB) * p.S + lane);
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+      const int tn = t + gridDim.x;
+      int mine_n = 0;
+      if (tn < p.num_tiles && lane < p.S && p.zero_row >= 0) mine_n = __ldg(p.table + (size_t)(tn / p.NB) * p.S + lane);
+      const int ng = wgrad_groups(p, mine, lane, tcount == 0);
+      if (leader) {
         const int buf = tcount & 1;
         mbar_wait_parked(gfull0 + buf * 8, (tcount >> 1) & 1, 1000);
         const uint32_t lo_g = (((gz0 + buf * gz_buf_b) & 0x3FFFFu) >> 4) | lbo;
-        for (int gi = 0; gi < p.Gp; ++gi) {
+        for (int gi = 0; gi < ng; ++gi) {
           mbar_wait_parked(full0 + slot * 8, ph, 1000);
           tc_fence_after();
           const uint32_t lo_a = (((smem0 + slot * stage_b) & 0x3FFFFu) >> 4) | lbo;
@@ -166,8 +188,10 @@ __global__ void __launch_bounds__(SW_THREADS, DUAL ? 2 : 1) slab_wgrad_kernel(co
         }
         mma_commit_u32(gempty0 + buf * 8);  // gz buffer reusable once the MMAs above have read it
       }
-      mma_commit_u32(smem_u32(&done_bar));
+      mine = mine_n;
+      __syncwarp();
     }
+    if (leader) mma_commit_u32(smem_u32(&done_bar));
     __syncwarp();
   } else {
     // ================================================================ warps 3-6: bias column sums, then the read-out
@@ -358,10 +382,12 @@ size_t shb_slab_wgrad_workspace(int S, int Cin, int Cout_p, int planes) {
 }
 
 /* x: slab tensor (rows_in, B, Cin_p); gz: slab tensor (rows_out, B, Cout_p); table (rows_out, S).
- * gw (Cout, S*Cin) fp32, gb (Cout) fp32 or null.  skip_last: the last output row's gz is zero by construction (mask). */
+ * gw (Cout, S*Cin) fp32, gb (Cout) fp32 or null.  skip_last: the last output row's gz is zero by construction (mask).
+ * zero_src_row: a row of x known to be all zero (the dummy vertex behind padded spiral slots), or -1: trailing operand groups
+ * that read nothing else are skipped. */
 int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* gw, float* gb, void* workspace,
                    size_t workspace_bytes, int B, int rows_out, int S, int Cin, int Cin_p, int Cout, int Cout_p, int skip_last,
-                   int planes, void* stream) {
+                   int zero_src_row, int planes, void* stream) {
   if (!x || !table || !gz || !workspace || B <= 0 || rows_out <= 0 || Cin <= 0 || Cin > Cin_p || Cout <= 0 || Cout > Cout_p)
     return SHB_E_ARG;
   if (!shb_slab_wgrad_supported(S, Cin_p, Cout_p, planes)) return SHB_E_UNSUPPORTED;
@@ -395,6 +421,7 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
   p.NB = slab::num_chunks(B); p.S = S; p.Cin = Cin_p; p.Cout_p = Cout_p; p.NPt = NPt;
   p.G = plan.G; p.PC = plan.PC; p.PPS = plan.PPS; p.PPG = plan.PPG;
   p.P = planes; p.nstage = plan.nstage;
+  p.zero_row = zero_src_row >= 0 ? zero_src_row : -1;
   const int rows_eff = skip_last ? rows_out - 1 : rows_out;
   p.num_tiles = rows_eff * p.NB;
   float* partial = (float*)workspace;

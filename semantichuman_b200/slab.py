@@ -287,7 +287,8 @@ class SlabConvFn(torch.autograd.Function):
             gw = torch.empty((cout, S * C), dtype=torch.float32, device=dev)
             gb = torch.empty((cout,), dtype=torch.float32, device=dev) if (has_bias and ctx.needs_input_grad[2]) else None
             _call("slabconv_wgrad" + ctx.tag, ctx.cmeta, lib.shb_slab_wgrad, _p(t), _p(geom.table), _p(gz), _p(gw), _p(gb),
-                  _p(ws), nbytes, B, geom.rows_out, S, C, Cp, cout, cout_p, int(geom.zero_last_row), planes, _stream())
+                  _p(ws), nbytes, B, geom.rows_out, S, C, Cp, cout, cout_p, int(geom.zero_last_row),
+                  geom.rows_in - 1 if geom.src_dummy_zero else -1, planes, _stream())
             _count(2)
             if wdtype != torch.float32:
                 gw = gw.to(wdtype)

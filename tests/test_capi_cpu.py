@@ -36,7 +36,7 @@ def test_argument_errors_are_reported_not_crashed():
     # null pointers are rejected before any launch (no GPU needed)
     assert _capi.lib.shb_slab_conv(None, None, None, None, None, None, None, 1, 1, 9, 16, 16, 16, 0, 0, 0, 1, None) == -1
     assert _capi.lib.shb_slab_pool(None, None, None, None, None, None, 1, 1, 16, 0, 0, 1, None) == -1
-    assert _capi.lib.shb_slab_wgrad(None, None, None, None, None, None, 0, 1, 1, 9, 16, 16, 16, 16, 0, 1, None) == -1
+    assert _capi.lib.shb_slab_wgrad(None, None, None, None, None, None, 0, 1, 1, 9, 16, 16, 16, 16, 0, -1, 1, None) == -1
     assert _capi.lib.shb_adam_step(0, None, None, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
     # shapes the kernels cannot take are refused loudly (no silent fallback): spiral length, channel counts, planes
     assert _capi.lib.shb_slab_conv_supported(33, 16, 16, 1) == 0 and _capi.lib.shb_slab_conv_supported(9, 24, 16, 1) == 0

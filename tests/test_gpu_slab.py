@@ -218,6 +218,41 @@ def test_slab_pool_matches_reference_goldens(shb, sl, planes):
         assert relerr(y, g[pre + "y"]) < tol and relerr(x.grad, g[pre + "gx"]) < tol
 
 
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("C,B", [(32, 130), (8, 256), (128, 5)])
+def test_slab_pool_every_row_length(shb, sl, planes, C, B):
+    """Pool on a random matrix whose rows have 0, 1..4 (the specialised loops), 5..32 (four entries at a time) and more than
+    32 entries (entries re-fetched per block), and whose transpose has its own mix: forward and backward against the dense
+    product, the backward with the act'(y) factor and the dummy-row mask of the producer."""
+    g = torch.Generator().manual_seed(11 * C + planes)
+    rows_out, rows_in = 60, 75
+    lens = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 16, 17, 31, 32, 33, 40, 64, 75] + [1, 3] * 20
+    lens = (lens + [2] * rows_out)[:rows_out]
+    dense = torch.zeros(rows_out, rows_in)
+    for r, n in enumerate(lens):
+        cols = torch.randperm(rows_in, generator=g)[:n]
+        dense[r, cols] = torch.randn(n, generator=g)
+    pm = shb.PoolMatrix.from_dense(dense.to(DEV))
+    x = torch.randn(B, rows_in, C, generator=g)
+    s = sl.from_rows(x.to(DEV), None, planes)
+    s.t.requires_grad_(True)
+    s.act, s.masked = 2, True   # as if x were a masked ELU layer's output
+    y = sl.pool(s, pm)
+    yr = sl.to_rows(y, None, torch.float32)
+    xq = _slab_values(s)[:, :B, :C].permute(1, 0, 2)   # what the kernels read (bf16 or hi + lo)
+    want = torch.einsum("rk,bkc->brc", dense, xq)
+    tol = 3e-5 if planes == 2 else TOL_BF16
+    assert relerr(yr, want) < tol
+    gy = torch.randn(B, rows_out, C, generator=g)
+    y.t.backward(sl.from_rows(gy.to(DEV), None, planes).t)
+    gq = _slab_values(sl.from_rows(gy.to(DEV), None, planes))[:, :B, :C].permute(1, 0, 2)
+    gwant = torch.einsum("rk,brc->bkc", dense, gq) * (torch.clamp(xq, max=0.0) + 1.0)
+    gwant[:, -1] = 0
+    got = _slab_values(sl.Slab(s.t.grad, s.rows, s.B, s.C, s.Cp, s.planes, 0, False))[:, :B, :C].permute(1, 0, 2)
+    assert relerr(got, gwant) < tol
+    assert (got[:, -1] == 0).all()
+
+
 def test_slab_backward_is_bit_reproducible(sl):
     g = torch.Generator().manual_seed(5)
     R, S, cin, cout, B = 300, 9, 32, 16, 200
