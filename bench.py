@@ -31,10 +31,13 @@ METRIC = "train meshes/sec (6890-vert SpiralAE fwd+bwd)"
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can come out on top, from the
 # ncu --set full captures summarised under profiles/ (B=256, bf16).  key = the timer tag bench.py reports as roofline.kernel
 NCU_TRAFFIC_BYTES = {
-    "slabconv_wgrad[6891>6891x14x32>16]": (169.78e6 + 3.84e6, "profiles/r02_ncu_gconv_wgrad_l0.csv"),
-    "slabconv_fwd[6891>6891x14x32>16]": (116.15e6 + 31.62e6, "profiles/r02_ncu_gconv_wgrad_l0.csv"),
-    "slabconv_dgrad[6891>6891x14x32>16]": (171.88e6 + 78.58e6, "profiles/r02_ncu_gconv_wgrad_l0.csv"),
-    "slabconv_wgrad[863>863x8x128>64]": (84.94e6 + 3.78e6, "profiles/r02_ncu_conv_wgrad_l3.csv"),
+    "slabconv_wgrad[6891>6891x14x32>16]": (169.78e6 + 4.53e6, "profiles/r02z_ncu_l0.csv"),
+    "slabconv_fwd[6891>6891x14x32>16]": (116.14e6 + 32.75e6, "profiles/r02z_ncu_l0.csv"),
+    "slabconv_dgrad[6891>6891x14x32>16]": (171.88e6 + 77.82e6, "profiles/r02z_ncu_l0.csv"),
+    "slabconv_wgrad[863>863x8x128>64]": (84.95e6 + 3.54e6, "profiles/r02z_ncu_l3.csv"),
+    "slabconv_fwd[863>863x8x128>64]": (56.72e6 + 8.20e6, "profiles/r02z_ncu_l3.csv"),
+    "slab_pool[3446>6891x32]": (86.11e6 + 74.89e6, "profiles/r02z_ncu_pool.csv"),
+    "slab_pool_bwd[6891>3446x32]": (209.94e6 + 42.82e6, "profiles/r02z_ncu_pool.csv"),
 }
 N_INPUT_BATCHES = 8  # distinct resident batches rotated through the timed loop
 
