@@ -110,6 +110,7 @@ def base_config(args, world):
             "params": 28559811, "optimizer": "Adam(lr=1e-3, wd=5e-5)", "parallelism": f"dp{world}",
             "comm_sms": (getattr(args, "comm_sms", 0) if world > 1 else 0),
             "cuda_graph": bool(not getattr(args, "no_graph", False)),
+            "host_bound_to_gpu_numa_node": bool(getattr(args, "host_cpus", None)),
             "cache": f"{N_INPUT_BATCHES} distinct input batches rotated; per-step working set (activations + 114 MB "
                      "weights + Adam state) exceeds the 126 MB L2"}
 
@@ -230,11 +231,12 @@ def run_own(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    from semantichuman_b200.dp import bind_host_to_device, init_data_parallel
+
+    args.host_cpus = None if args.no_numa_bind else bind_host_to_device(local)  # before any pinned allocation
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        from semantichuman_b200.dp import init_data_parallel
-
         init_data_parallel(dev, comm_sms=args.comm_sms)
     dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
 
@@ -428,14 +430,18 @@ def main():
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
-    ap.add_argument("--comm-sms", type=int, default=16,
+    ap.add_argument("--comm-sms", type=int, default=-1,
                     help="N>1: CTAs NCCL may use = SMs the persistent kernels leave free while a gradient bucket is in flight; "
-                         "0 = NCCL defaults, no reservation")
+                         "0 = NCCL defaults, no reservation; -1 (default) = dp.default_comm_sms(world)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the process to the CPUs of the GPU's NUMA node (dp.bind_host_to_device)")
     ap.add_argument("--kernels-out", default=None, help="write the full per-kernel table of the instrumented pass here")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the in-run cpu_baseline sample (10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.comm_sms < 0:
+        args.comm_sms = 32 if args.gpus >= 8 else 16  # == semantichuman_b200.dp.default_comm_sms (the reference arm imports no product code)
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

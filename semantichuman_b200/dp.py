@@ -33,12 +33,51 @@ def shard_batch(global_batch, rank, world):
 N_BUCKETS = 4
 
 
-def init_data_parallel(device, comm_sms=24):
+def default_comm_sms(world):
+    """CTAs for NCCL / SMs left free of the persistent kernels while a large bucket is in flight.  Measured on one 8 x B200 box
+    (profiles/README.md, round 2 scaling): 16 is as good as NCCL's defaults at 2 and 4 ranks and 8 is worse; at 8 ranks 16 starves
+    the all-reduce (2.16 ms/step) and 32 is best (2.01 ms; NCCL's defaults 2.03)."""
+    return 32 if world >= 8 else 16
+
+
+def bind_host_to_device(device_index):
+    """Pin the calling process to the CPUs of the GPU's own NUMA node (sysfs local_cpulist of its PCI function) BEFORE it
+    allocates pinned staging buffers: a process scheduled on the other socket stages every batch across the socket link, and the
+    per-step host-to-device copy (21 MB at batch 256) then no longer hides behind the 1.8 ms step.  Returns the CPU set used,
+    or None when the topology is not exposed or the allowed CPUs do not include any local one (nothing is changed then)."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            text = f.read().strip()
+        local = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            local.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = local & allowed
+        if not use or use == allowed:
+            return None
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except (OSError, AttributeError, ValueError):
+        return None
+
+
+def init_data_parallel(device, comm_sms=None):
     """Create the NCCL process group of a data-parallel run with NCCL limited to `comm_sms` CTAs (0: NCCL's defaults).
     GradSync(model, comm_sms=...) then keeps that many SMs free of the persistent SpiralConv kernels WHILE a large gradient
     bucket is in flight (measured on 2 B200: with all 148 SMs -- and all of their shared memory -- held by one-CTA-per-SM
     kernels the all-reduce cannot start beside them and its 0.3 ms stay exposed; reserving SMs for the whole step costs more
-    than it hides)."""
+    than it hides).  comm_sms=None: default_comm_sms(world size from the environment)."""
+    if comm_sms is None:
+        import os
+
+        comm_sms = default_comm_sms(int(os.environ.get("WORLD_SIZE", "1")))
     if comm_sms and comm_sms > 0:
         opts = dist.ProcessGroupNCCL.Options()
         opts.config.max_ctas = int(comm_sms)
