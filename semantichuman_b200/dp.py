@@ -64,7 +64,7 @@ def bind_host_to_device(device_index):
             return None
         os.sched_setaffinity(0, use)
         return sorted(use)
-    except (OSError, AttributeError, ValueError):
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):  # no such device / no sysfs topology
         return None
 
 

@@ -160,3 +160,15 @@ def test_shard_batch():
     assert [shard_batch(2048, r, 8) for r in (0, 7)] == [(0, 256), (1792, 2048)]
     with pytest.raises(ValueError):
         shard_batch(10, 0, 4)
+
+
+def test_default_comm_sms_and_host_binding_without_gpu():
+    import os
+
+    from semantichuman_b200.dp import bind_host_to_device, default_comm_sms
+
+    assert [default_comm_sms(w) for w in (1, 2, 4, 8, 16)] == [16, 16, 16, 32, 32]
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert bind_host_to_device(0) is None   # no device, no topology: nothing is changed, nothing raises
+        assert os.sched_getaffinity(0) == before
