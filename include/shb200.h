@@ -79,6 +79,11 @@ int shb_l1_loss_fwd(const void* a, const void* b, int64_t n, void* partials, siz
 int shb_l1_loss_bwd(const void* a, const void* b, int64_t n, const float* gscale, void* ga, void* gb, int dtype,
                     void* stream);
 
+/* out[c] = sum over b of x[b][c]: the bias gradient of the two latent nn.Linear layers (models.py:129,142; autograd's
+ * sum over the batch), x row-major (B, N) of `dtype`, out fp32 (N).  Fixed summation order (16-byte vector loads when N is a
+ * multiple of 8, one column per thread otherwise). */
+int shb_colsum(const void* x, int dtype, int B, int N, float* out, void* stream);
+
 /* Part-measure latent loss (train_funcs.py:145-152): m[b,p] = ||z[b,p,:]||_2;
  *   relative != 0:  loss = mean_{b,i} | m[b,P[i]] / measure[b,Q[i]] - 1 |
  *   relative == 0:  loss = mean_{b,i} | m[b,P[i]] - measure[b,Q[i]] |
@@ -161,6 +166,21 @@ int shb_slab_from_rows(const void* src, int src_dtype, const int32_t* perm, cons
                        int B, int R, int Cs, int Cp, int act_mul, int zero_last, int planes, void* stream);
 int shb_slab_to_rows(const void* src, const int32_t* perm, const int32_t* perm_inv, void* dst, int dst_dtype, int B, int R, int Cp,
                      int Cd, int planes, void* stream);
+
+/* L1 reconstruction loss straight from the slab tensor of the last decoder SpiralConv (train_funcs.py:501 / main.py:296
+ * F.l1_loss on the output of models.py:159): rec = slab tensor (R, B, 8 channels padded, Cs <= 8 real), target = row-major
+ * (B, R, Cs) of `target_dtype` in the CALLER's row order, perm_inv[c] = internal row of the caller's row c (NULL: identity).
+ *   fwd: *loss_out = mean over B*R*Cs elements of |rec - target|; fixed-order two-stage reduction; partials = fp32 workspace
+ *        of shb_slab_l1_workspace() bytes.
+ *   bwd: grad_slab (shaped like rec) = *gscale / (B*R*Cs) * sign(rec - target), multiplied by act'(rec) (act_mul, the
+ *        producer's activation, derivative through its output) and with row R-1 zeroed when zero_last (the producer's
+ *        dummy-row mask, models.py:48-51) -- i.e. already in the trunk's gradient convention; padded channels / samples zero.
+ * Replaces slab_to_rows + l1_loss_fwd + l1_loss_bwd + slab_from_rows of a training step with two passes over the slab. */
+size_t shb_slab_l1_workspace(void);
+int shb_slab_l1_fwd(const void* rec, const void* target, int target_dtype, const int32_t* perm_inv, void* partials,
+                    size_t partials_bytes, float* loss_out, int B, int R, int Cs, int planes, void* stream);
+int shb_slab_l1_bwd(const void* rec, const void* target, int target_dtype, const int32_t* perm_inv, const float* gscale,
+                    void* grad_slab, int B, int R, int Cs, int act_mul, int zero_last, int planes, void* stream);
 
 /* Pool (models.py:127,148: torch.matmul(D[i] | U[i], x)) on slab tensors: dst[r] = sum_k vals[k] * src[colidx[k]],
  * k in rowptr[r]..rowptr[r+1].  Optional epilogue for the gradient path: times act'(ymul[r]) and/or zero the last row. */

@@ -22,6 +22,7 @@ SIGNATURES = {
     "shb_l1_loss_workspace": (c_size, [c_i64]),
     "shb_l1_loss_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_size, c_vp, c_int, c_vp]),
     "shb_l1_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "shb_colsum": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "shb_partnorm_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
     "shb_pair_loss_workspace": (c_size, [c_int] * 3),
     "shb_pair_loss_grad_acc_bytes": (c_size, [c_int] * 3),
@@ -38,6 +39,9 @@ SIGNATURES = {
     "shb_slab_tensor_bytes": (c_size, [c_int] * 4),
     "shb_slab_from_rows": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
     "shb_slab_to_rows": (c_int, [c_vp, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
+    "shb_slab_l1_workspace": (c_size, []),
+    "shb_slab_l1_fwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_size, c_vp] + [c_int] * 4 + [c_vp]),
+    "shb_slab_l1_bwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
     "shb_slab_pool": (c_int, [c_vp] * 6 + [c_int] * 6 + [c_vp]),
     "shb_slab_weight_image_bytes": (c_size, [c_int] * 4),
     "shb_slab_weight_images": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),

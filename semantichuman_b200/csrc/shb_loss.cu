@@ -41,6 +41,70 @@ __global__ void __launch_bounds__(256) l1_bwd_kernel(const T* __restrict__ a, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ column sums
+// out[c] = sum_b x[b][c] (the bias gradient of an nn.Linear: models.py:129,142), x row-major (B, N), fp32 result.
+// A CTA owns 256 columns: thread (v = tid & 31, rg = tid >> 5) adds rows rg, rg + 8, ... of the 8-column vector v (16-byte
+// loads for bf16, coalesced across the warp, eight in flight), the eight row groups are added in index order through shared
+// memory.  Fixed order, no atomics.  (ATen's reduce kernel ran this with 2 CTAs for N = 256: 15 us of latency.)
+constexpr int CS_ROWGROUPS = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int B, int N, float* __restrict__ out) {
+  __shared__ float part[CS_ROWGROUPS][32][9];
+  const int v = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + v) * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < N) {
+    int b = rg;
+    for (; b + 7 * CS_ROWGROUPS < B; b += 8 * CS_ROWGROUPS) {
+      float r[8][8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) Io<T>::ld8(x + (size_t)(b + k * CS_ROWGROUPS) * N + c0, r[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += r[k][e];
+    }
+    for (; b < B; b += CS_ROWGROUPS) {
+      float r[8];
+      Io<T>::ld8(x + (size_t)b * N + c0, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += r[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[rg][v][e] = acc[e];
+  __syncthreads();
+  const int col = threadIdx.x, cv = col >> 3, ce = col & 7;
+  const int c = blockIdx.x * 256 + col;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CS_ROWGROUPS; ++k) s += part[k][cv][ce];
+    out[c] = s;
+  }
+}
+
+// any N: a CTA owns 32 columns (lane = column: coalesced), the same eight row groups
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict__ x, int B, int N, float* __restrict__ out) {
+  __shared__ float part[CS_ROWGROUPS][32];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (c < N)
+    for (int b = rg; b < B; b += CS_ROWGROUPS) acc += Io<T>::ld(x + (size_t)b * N + c);
+  part[rg][lane] = acc;
+  __syncthreads();
+  if (rg == 0 && c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CS_ROWGROUPS; ++k) s += part[k][lane];
+    out[c] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ part-norm loss
 // One CTA: (b, i) terms strided over threads, fixed-order block reduction.  gz is zero-filled first.
 __global__ void __launch_bounds__(256) partnorm_kernel(const float* __restrict__ z, const float* __restrict__ measure,
@@ -112,6 +176,24 @@ int shb_partnorm_loss_fwd_bwd(const float* z, const float* measure, const int32_
   if (!z || !measure || !P || !Q || !loss_out || !gz) return SHB_E_ARG;
   if (B <= 0 || n_parts <= 0 || L <= 0 || n_measure <= 0 || n_sel <= 0) return SHB_E_ARG;
   partnorm_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(z, measure, P, Q, loss_out, gz, B, n_parts, L, n_measure, n_sel, relative);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_colsum(const void* x, int dtype, int B, int N, float* out, void* stream) {
+  if (!x || !out || B <= 0 || N <= 0) return SHB_E_ARG;
+  if (dtype != SHB_F32 && dtype != SHB_BF16) return SHB_E_DTYPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N % 8 != 0) {   // rows not 16-byte aligned: one column per thread
+    const int grid = (N + 31) / 32;
+    if (dtype == SHB_F32) colsum_scalar_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, N, out);
+    else colsum_scalar_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, N, out);
+    SHB_LAUNCH_CHECK();
+    return 0;
+  }
+  const int grid = (N + 255) / 256;
+  if (dtype == SHB_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, N, out);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, N, out);
   SHB_LAUNCH_CHECK();
   return 0;
 }

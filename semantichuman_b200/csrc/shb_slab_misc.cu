@@ -591,6 +591,90 @@ __global__ void __launch_bounds__(CV_THREADS) slab_to_rows_narrow_kernel(const u
   }
 }
 
+// ---------------------------------------------------------------------------------------------- L1 loss on a slab tensor
+// loss = mean |rec - target| (train_funcs.py:501 on the output of models.py:159) with rec still in the slab layout (Cp == 8,
+// Cs <= 8 real channels) and target row-major (B, R, Cs) in the caller's row order: the row-major reconstruction, its
+// gradient and the two conversions between them never touch memory.  Tiles as in the narrow conversions (32 caller rows x
+// one chunk, target staged in shared memory).  MODE 0: per-CTA partial sums of |d| (fixed order: a CTA's tiles in
+// ascending order, block_sum; slab_l1_final_kernel adds the CTA partials in index order).  MODE 1: the gradient slab
+// gscale / n * sign(d), times act'(rec) of the producer, dummy row zeroed when the producer masks it.
+template <typename T, int P, int MODE>
+__global__ void __launch_bounds__(CV_THREADS) slab_l1_kernel(const uint8_t* __restrict__ rec, const T* __restrict__ target,
+                                                             const int32_t* __restrict__ pos, float* __restrict__ partials,
+                                                             const float* __restrict__ gscale, uint8_t* __restrict__ gdst, int B,
+                                                             int R, int Cs, float n_elems, int act, int zero_last) {
+  extern __shared__ __align__(16) uint8_t cv_smem[];
+  __shared__ float red[CV_THREADS / 32];
+  float* t = reinterpret_cast<float*>(cv_smem);
+  const int NB = num_chunks(B), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stride = (CV_ROWS * Cs) | 1;
+  const size_t slab_b = slab_bytes(8, P), plane_b = 8 * 256;
+  const int rblocks = (R + CV_ROWS - 1) / CV_ROWS, tiles = rblocks * NB;
+  const float g = MODE == 1 ? __ldg(gscale) / n_elems : 0.f;   // as shb_l1_loss_bwd forms it: the two paths agree to the bit
+  float acc = 0.f;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int q = tile / rblocks, c0 = (tile - q * rblocks) * CV_ROWS;
+    const int nrows = R - c0 < CV_ROWS ? R - c0 : CV_ROWS, len = nrows * Cs;
+    for (int e = lane; e < len; e += 32) {
+      float tmp[CHUNK / (CV_THREADS / 32)];
+#pragma unroll
+      for (int k = 0; k < CHUNK / (CV_THREADS / 32); ++k) {
+        const int b = q * CHUNK + warp + k * (CV_THREADS / 32);
+        tmp[k] = b < B ? Io<T>::ld(target + ((size_t)b * R + c0) * Cs + e) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < CHUNK / (CV_THREADS / 32); ++k) t[(warp + k * (CV_THREADS / 32)) * stride + e] = tmp[k];
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int it = tid; it < nrows * CHUNK; it += CV_THREADS) {
+      const int j = it >> 7, bl = it & (CHUNK - 1);
+      const int ri = pos != nullptr ? __ldg(pos + c0 + j) : c0 + j;
+      const size_t off = ((size_t)ri * NB + q) * slab_b + (size_t)bl * 16;
+      const bool live = q * CHUNK + bl < B;
+      float y[8];
+      cv_load_slab8<P>(rec + off, plane_b, y);
+      if (MODE == 0) {
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < Cs) acc += fabsf(y[e] - t[bl * stride + j * Cs + e]);
+        }
+      } else {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (live && !(zero_last && ri == R - 1)) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < Cs) {
+              const float d = y[e] - t[bl * stride + j * Cs + e];
+              v[e] = d > 0.f ? g : (d < 0.f ? -g : 0.f);
+            }
+          if (act != SHB_ACT_IDENTITY) act_bwd8(v, y, act);
+        }
+        cv_store_slab8<P>(gdst + off, plane_b, v);
+      }
+    }
+    __syncthreads();
+  }
+  if (MODE == 0) {
+    acc = block_sum<CV_THREADS>(acc, red);
+    if (tid == 0) partials[blockIdx.x] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) slab_l1_final_kernel(const float* __restrict__ partials, int np, float inv_n,
+                                                            float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < np; i += 256) s += partials[i];
+  s = block_sum<256>(s, red);
+  if (threadIdx.x == 0) *out = s * inv_n;
+}
+
+constexpr int SL1_MAX_GRID = 8 * kNumSMs;
+
 static inline int cv_log2_groups(int Cp) {   // wide tiles: 2, 4, 8 or 16 channel groups (Cp = 256: two tiles per slab)
   switch (Cp) {
     case 16: return 1;
@@ -788,6 +872,64 @@ int shb_slab_to_rows(const void* src, const int32_t* perm, const int32_t* perm_i
 #undef SHB_TR
   SHB_LAUNCH_CHECK();
   return 0;
+}
+
+size_t shb_slab_l1_workspace(void) { return (size_t)SL1_MAX_GRID * sizeof(float); }
+
+static int slab_l1_launch(int mode, const void* rec, const void* target, int target_dtype, const int32_t* perm_inv, float* partials,
+                          const float* gscale, void* gdst, int B, int R, int Cs, int act, int zero_last, int planes, int* grid_out,
+                          cudaStream_t st) {
+  const int NB = slab::num_chunks(B);
+  const long long tiles_ll = (long long)((R + CV_ROWS - 1) / CV_ROWS) * NB;
+  if (tiles_ll >= (1LL << 31)) return SHB_E_SHAPE;
+  const int tiles = (int)tiles_ll;
+  const size_t smem = (size_t)CHUNK * ((CV_ROWS * Cs) | 1) * sizeof(float);
+  const int per_sm = (int)(200 * 1024 / smem) < 8 ? (int)(200 * 1024 / smem) : 8;
+  const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
+  const float n_elems = (float)((long long)B * R * Cs);
+#define SHB_SL1(T, PL, MODE)                                                                                                  \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) {                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(slab_l1_kernel<T, PL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return (int)e;                                                                                    \
+    }                                                                                                                         \
+    slab_l1_kernel<T, PL, MODE><<<grid, CV_THREADS, smem, st>>>((const uint8_t*)rec, (const T*)target, perm_inv, partials, gscale, \
+                                                                (uint8_t*)gdst, B, R, Cs, n_elems, act, zero_last);           \
+  } while (0)
+#define SHB_SL1_M(T, PL) do { if (mode == 0) SHB_SL1(T, PL, 0); else SHB_SL1(T, PL, 1); } while (0)
+  if (target_dtype == SHB_F32) { if (planes == 1) SHB_SL1_M(float, 1); else SHB_SL1_M(float, 2); }
+  else { if (planes == 1) SHB_SL1_M(__nv_bfloat16, 1); else SHB_SL1_M(__nv_bfloat16, 2); }
+#undef SHB_SL1_M
+#undef SHB_SL1
+  SHB_LAUNCH_CHECK();
+  *grid_out = grid;
+  return 0;
+}
+
+int shb_slab_l1_fwd(const void* rec, const void* target, int target_dtype, const int32_t* perm_inv, void* partials,
+                    size_t partials_bytes, float* loss_out, int B, int R, int Cs, int planes, void* stream) {
+  if (!rec || !target || !partials || !loss_out || B <= 0 || R <= 0 || Cs <= 0 || Cs > 8 || planes < 1 || planes > 2) return SHB_E_ARG;
+  if (target_dtype != SHB_F32 && target_dtype != SHB_BF16) return SHB_E_DTYPE;
+  if (partials_bytes < shb_slab_l1_workspace()) return SHB_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = 0;
+  const int rc = slab_l1_launch(0, rec, target, target_dtype, perm_inv, (float*)partials, nullptr, nullptr, B, R, Cs, 0, 0, planes,
+                                &grid, st);
+  if (rc != 0) return rc;
+  slab_l1_final_kernel<<<1, 256, 0, st>>>((const float*)partials, grid, 1.0f / (float)((long long)B * R * Cs), loss_out);
+  SHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int shb_slab_l1_bwd(const void* rec, const void* target, int target_dtype, const int32_t* perm_inv, const float* gscale,
+                    void* grad_slab, int B, int R, int Cs, int act_mul, int zero_last, int planes, void* stream) {
+  if (!rec || !target || !gscale || !grad_slab || B <= 0 || R <= 0 || Cs <= 0 || Cs > 8 || planes < 1 || planes > 2)
+    return SHB_E_ARG;
+  if (target_dtype != SHB_F32 && target_dtype != SHB_BF16) return SHB_E_DTYPE;
+  if (act_mul < SHB_ACT_IDENTITY || act_mul > SHB_ACT_TANH) return SHB_E_ARG;
+  int grid = 0;
+  return slab_l1_launch(1, rec, target, target_dtype, perm_inv, nullptr, gscale, grad_slab, B, R, Cs, act_mul, zero_last, planes,
+                        &grid, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -397,6 +397,18 @@ def cast_bf16(src, dst):
     return dst
 
 
+def column_sums(g):
+    """sum over the batch of a (B, N) float32 / bfloat16 CUDA tensor, in fp32 (shb_colsum): an nn.Linear's bias gradient."""
+    _cuda(g)
+    B, N = g.shape
+    g = g.contiguous()
+    out = torch.empty((N,), dtype=torch.float32, device=g.device)
+    _call(f"colsum[{B}x{N}]", {"bytes": float(B) * N * g.element_size()}, lib.shb_colsum, _p(g),
+          _DT[g.dtype], B, N, _p(out), _stream())
+    _count()
+    return out
+
+
 class LinearShadowFn(torch.autograd.Function):
     """y = x W^T + b with bf16 operands taken from the weight SHADOWS (kept current by optim.Adam), gradients delivered to
     the fp32 master parameters in fp32 (cuBLAS accumulates in fp32 anyway; no bf16 gradient tensor, no cast kernels).
@@ -428,7 +440,7 @@ class LinearShadowFn(torch.autograd.Function):
             else:
                 gw = torch.mm(g.t(), x, out_dtype=torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = torch.sum(g, 0, dtype=torch.float32)
+            gb = column_sums(g)
         return gx, gw, gb, None, None
 
 

@@ -282,7 +282,7 @@ class _SpiralTrunk(nn.Module):
                 s = slab.pool(s, pm)
         return slab.to_rows(s, None, self.compute_dtype)  # last level: caller's order (FC layout of models.py:128)
 
-    def _decode_trunk(self, x):
+    def _decode_slab(self, x):
         if not x.is_cuda:
             raise RuntimeError("semantichuman_b200 models need CUDA tensors; there is no CPU fallback")
         wi = self._weight_images()
@@ -292,7 +292,10 @@ class _SpiralTrunk(nn.Module):
                 s = slab.pool(s, pm)
             c = self.dconv[j]
             s = slab.spiral_conv(s, c.conv.weight, c.conv.bias, geom, c.activation_name, images=wi.of(c.conv.weight))
-        return slab.to_rows(s, self._perm_dev, torch.float32)  # internal order -> caller's order
+        return s
+
+    def _decode_trunk(self, x):
+        return slab.to_rows(self._decode_slab(x), self._perm_dev, torch.float32)  # internal order -> caller's order
 
 
 class SpiralAutoencoder(_SpiralTrunk):
@@ -336,6 +339,21 @@ class SpiralAutoencoder(_SpiralTrunk):
     def forward(self, x):
         z = self.encode(x, self.VAE_flag)
         return self.decode(z), z
+
+    def reconstruction_loss(self, x, target=None):
+        """F.l1_loss(self(x)[0], target) (train_funcs.py:501; target defaults to x) as ONE fused path for a training step: the
+        latent code stays in the compute dtype between the two FC layers (bf16 -> fp32 -> bf16 is the identity, so the result
+        equals forward()'s) and the loss is taken from the last SpiralConv's slab output (slab.l1_loss), so neither the
+        row-major reconstruction nor its gradient is materialised.  Same loss and gradients as the unfused calls up to
+        summation order."""
+        if self.VAE_flag:
+            return fn.l1_loss(self(x)[0], x if target is None else target)
+        bsize = x.size(0)
+        h = self._encode_trunk(x)
+        z = self._linear(self.fc_latent_enc, h.reshape(bsize, -1))
+        h = self._linear(self.fc_latent_dec, z)
+        s = self._decode_slab(h.view(bsize, self.sizes[-1] + 1, -1))
+        return slab.l1_loss(s, x if target is None else target, self._perm_dev)
 
 
 class SpiralAutoencoder_multiz_partkps(_SpiralTrunk):

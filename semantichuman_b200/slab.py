@@ -153,6 +153,52 @@ def to_rows(s, perm=None, dtype=torch.float32):
     return ToRowsFn.apply(s.t, perm, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked), dtype)
 
 
+class SlabL1LossFn(torch.autograd.Function):
+    """mean |rec - target| with rec still a slab tensor (the last decoder SpiralConv's output) and target the caller's row-major
+    (B, rows, C) tensor: stands in for to_rows + F.l1_loss (train_funcs.py:501) and, on the way back, for the L1 backward +
+    from_rows -- the row-major reconstruction and its gradient are never written.  The gradient it returns is already in the
+    trunk's convention (times act' of the producer, producer's dummy-row mask applied)."""
+
+    @staticmethod
+    def forward(ctx, t, target, perm, meta):
+        rows, B, C, Cp, planes, act, masked = meta
+        _cuda(target)
+        if Cp != 8:
+            raise NotImplementedError("slab l1_loss: the reconstruction must be an 8-channel (<= 8 real channels) slab tensor")
+        if tuple(target.shape) != (B, rows, C):
+            raise ValueError(f"slab l1_loss: target must be ({B}, {rows}, {C}), got {tuple(target.shape)}")
+        target = target.contiguous()
+        ctx.perm, ctx.meta = perm, meta
+        ctx.save_for_backward(t, target)
+        nbytes = lib.shb_slab_l1_workspace()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=t.device)
+        loss = torch.empty((), dtype=torch.float32, device=t.device)
+        _call(f"slab_l1_fwd[{rows}x{C}]", {"bytes": float(B) * rows * (C * target.element_size() + Cp * 2 * planes)},
+              lib.shb_slab_l1_fwd, _p(t), _p(target), _dt(target), _p(inverse_perm(perm)), _p(ws), nbytes, _p(loss), B, rows, C,
+              planes, _stream())
+        _count(2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        t, target = ctx.saved_tensors
+        rows, B, C, Cp, planes, act, masked = ctx.meta
+        gs = g.to(torch.float32).contiguous()
+        gt = torch.empty_like(t)
+        _call(f"slab_l1_bwd[{rows}x{C}]", {"bytes": float(B) * rows * (C * target.element_size() + 2 * Cp * 2 * planes)},
+              lib.shb_slab_l1_bwd, _p(t), _p(target), _dt(target), _p(inverse_perm(ctx.perm)), _p(gs), _p(gt), B, rows, C, int(act),
+              int(bool(masked)), planes, _stream())
+        _count()
+        return gt, None, None, None
+
+
+def l1_loss(s, target, perm=None):
+    """F.l1_loss(to_rows(s, perm), target) without the row-major reconstruction (target: (B, rows, C), no gradient)."""
+    if target.requires_grad:
+        raise NotImplementedError("slab l1_loss: the target takes no gradient; use to_rows + functions.l1_loss")
+    return SlabL1LossFn.apply(s.t, target, perm, (s.rows, s.B, s.C, s.Cp, s.planes, s.act, s.masked))
+
+
 class SlabPoolFn(torch.autograd.Function):
     """y[r] = sum_k P[r,k] x[k] over whole slabs (models.py:127,148); backward = P^T, times act' of x's producer."""
 

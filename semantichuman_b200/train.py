@@ -17,11 +17,15 @@ from .optim import Adam
 
 
 class TrainStep:
-    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False, comm_sms=0, grad_comm_dtype="auto"):
-        """`grad_comm_dtype`: dtype of the gradient sinks of the two FC weights (dp.GradSync) --
+    def __init__(self, model, lr=1e-3, weight_decay=5e-5, optimizer=True, graph=False, comm_sms=0, grad_comm_dtype="auto",
+                 fused_loss=True):
+        """`fused_loss`: take the L1 loss through model.reconstruction_loss (slab-side loss, no row-major reconstruction) when
+        the model offers it; False runs model(x) + functions.l1_loss, the reference loop's two calls.
+        `grad_comm_dtype`: dtype of the gradient sinks of the two FC weights (dp.GradSync) --
         "auto": bfloat16 when the model computes in bf16 (the compute dtype must be set before this constructor), none in
         fp32 mode (every gradient travels in fp32 through p.grad); or torch.float32 / torch.bfloat16 / None explicitly."""
         self.model = model
+        self.fused_loss = bool(fused_loss) and hasattr(model, "reconstruction_loss")
         if grad_comm_dtype == "auto":
             grad_comm_dtype = torch.bfloat16 if getattr(model, "compute_dtype", None) == torch.bfloat16 else None
         if not optimizer and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -77,8 +81,11 @@ class TrainStep:
         split = self._opt_stream is not None
         if split:
             self.optim.tick()   # before anything of this step: every optimizer launch below reads the advanced count
-        xh, _z = self.model(x)
-        loss = fn.l1_loss(x, xh)  # train_funcs.py:501  loss_fn(tx, tx_hat)
+        if self.fused_loss:
+            loss = self.model.reconstruction_loss(x)   # == the two lines below, without the row-major reconstruction
+        else:
+            xh, _z = self.model(x)
+            loss = fn.l1_loss(x, xh)  # train_funcs.py:501  loss_fn(tx, tx_hat)
         loss.backward()
         self.sync.finish()
         if self.optim is not None:

@@ -271,3 +271,39 @@ def test_slab_backward_is_bit_reproducible(sl):
     for o in outs[1:]:
         for a, c in zip(outs[0], o):
             assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("B,R,C", [(1, 5, 3), (3, 37, 3), (130, 70, 3), (256, 101, 8), (200, 64, 1)])
+@pytest.mark.parametrize("act,masked", [("identity", True), ("elu", False), ("tanh", True)])
+@pytest.mark.parametrize("use_perm", [True, False])
+def test_slab_l1_loss_matches_rows_path(sl, planes, B, R, C, act, masked, use_perm):
+    """slab.l1_loss (shb_slab_l1_fwd / _bwd) against the path it replaces -- to_rows, F.l1_loss on the rows, and back through
+    from_rows with act' and the dummy-row mask -- and against torch on the CPU: same loss (summation order aside) and the
+    IDENTICAL gradient slab (both round gscale / n * sign to bf16 hi (+ lo) the same way).  Ragged batches, row counts that
+    are not multiples of the 32-row tile, 1 / 3 / 8 channels, a non-unit upstream gradient."""
+    from semantichuman_b200._capi import ACT_ENUM
+    from semantichuman_b200 import functions as fn
+
+    g = torch.Generator().manual_seed(B * 131 + R * 7 + C)
+    rec = torch.randn(B, R, C, generator=g)
+    target = (rec + 0.3 * torch.randn(B, R, C, generator=g)).to(DEV)
+    perm = torch.randperm(R, generator=g).to(torch.int32).to(DEV) if use_perm else None
+    base = sl.from_rows(rec.to(DEV), perm, planes)
+    # exact ties (sign(0) = 0): the target takes the value the slab holds for a few elements
+    held = sl.to_rows(base, perm, torch.float32)
+    target[:, 0, :] = held[:, 0, :]
+    res = {}
+    for fused in (True, False):
+        t = base.t.detach().clone().requires_grad_(True)
+        s = sl.Slab(t, R, B, C, base.Cp, planes, ACT_ENUM[act], masked)
+        loss = sl.l1_loss(s, target, perm) if fused else fn.l1_loss(sl.to_rows(s, perm, torch.float32), target)
+        (loss * 1.7).backward()
+        res[fused] = (loss.item(), t.grad.float().cpu())
+    assert abs(res[True][0] - res[False][0]) <= 2e-6 * abs(res[False][0]) + 1e-8
+    assert torch.equal(res[True][1], res[False][1])
+    # and against plain torch on what the slab actually holds
+    rows = sl.to_rows(base, perm, torch.float32).cpu()
+    want = (rows - target.cpu()).abs().mean().item()
+    assert abs(res[True][0] - want) <= 2e-6 * want + 1e-8
+    assert res[True][1].abs().max() > 0
