@@ -268,16 +268,18 @@ __global__ void __launch_bounds__(SW_THREADS, DUAL ? 2 : 1) slab_wgrad_kernel(co
 }
 
 // gw[o][s*Cin + c] = sum over CTAs of partial[cta][row(s,c)][o];  gb likewise.  Fixed order, hence bit-reproducible: a block
-// owns 32 consecutive outputs (o fastest: the 32 loads of a warp are one or two contiguous runs); warp w of its 8 warps adds the
-// partials q = w, w + 8, ... in ascending order, eight loads in flight, and warp 0 adds the eight sums in warp order.
+// owns 32 consecutive outputs (o fastest: the 32 loads of a warp are one or two contiguous runs); warp w of its NW warps adds the
+// partials q = w, w + NW, ... in ascending order, eight loads in flight, and warp 0 adds the NW sums in warp order.
 // (First version: one thread per output walking all 148-296 partials -- 28 blocks for the level-0 layer, 18 us per launch,
 // 8 % of the step for 0.2 % of its bytes.)
-constexpr int SWR_WARPS = 8;
-__global__ void __launch_bounds__(SWR_WARPS * 32) slab_wgrad_reduce_kernel(const float* __restrict__ partial,
-                                                                             const float* __restrict__ bias_partial, int nparts, int G,
-                                                                             int NPt, int S, int Cin, int Cin_p, int Cout, int PC, int PPS,
-                                                                             int PPG, float* __restrict__ gw, float* __restrict__ gb) {
-  __shared__ float part_s[SWR_WARPS][32];
+// Layers with few outputs (level 0-1: 700-13 000) give few blocks, and each of their warps then walks 37 partials in five
+// dependent rounds: those run with 32 warps per block (one or two rounds) -- NW is the number of warps sharing a block's partials.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) slab_wgrad_reduce_kernel(const float* __restrict__ partial,
+                                                                    const float* __restrict__ bias_partial, int nparts, int G,
+                                                                    int NPt, int S, int Cin, int Cin_p, int Cout, int PC, int PPS,
+                                                                    int PPG, float* __restrict__ gw, float* __restrict__ gb) {
+  __shared__ float part_s[NW][32];
   const int K = S * Cin;
   const int total = K * Cout;
   const size_t pstride = (size_t)G * 128 * NPt;
@@ -306,14 +308,22 @@ __global__ void __launch_bounds__(SWR_WARPS * 32) slab_wgrad_reduce_kernel(const
     float acc = 0.f;
     if (src != nullptr) {
       int q = w;
-      for (; q + 7 * SWR_WARPS < nparts; q += 8 * SWR_WARPS) {
+      for (; q + 7 * NW < nparts; q += 8 * NW) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)(q + j * SWR_WARPS) * stride);
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)(q + j * NW) * stride);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc += v[j];
       }
-      for (; q < nparts; q += SWR_WARPS) acc += __ldg(src + (size_t)q * stride);
+      if (q + 3 * NW < nparts) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(src + (size_t)(q + j * NW) * stride);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += v[j];
+        q += 4 * NW;
+      }
+      for (; q < nparts; q += NW) acc += __ldg(src + (size_t)q * stride);
     }
     __syncthreads();   // previous round's readers are done with part_s
     part_s[w][lane] = acc;
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(SWR_WARPS * 32) slab_wgrad_reduce_kernel(const
     if (w == 0 && out != nullptr) {
       float r = 0.f;
 #pragma unroll
-      for (int j = 0; j < SWR_WARPS; ++j) r += part_s[j][lane];
+      for (int j = 0; j < NW; ++j) r += part_s[j][lane];
       *out = r;
     }
   }
@@ -454,8 +464,12 @@ int shb_slab_wgrad(const void* x, const int32_t* table, const void* gz, float* g
   const int total = S * Cin * Cout + Cout;
   int rgrid = ceil_div(total, 32);
   if (rgrid > 8 * kNumSMs) rgrid = 8 * kNumSMs;
-  slab_wgrad_reduce_kernel<<<rgrid, SWR_WARPS * 32, 0, st>>>(partial, gb ? bias_partial : nullptr, grid, plan.G, NPt, S, Cin, Cin_p, Cout,
-                                                 plan.PC, plan.PPS, plan.PPG, gw, gb);
+  if (rgrid < 2 * kNumSMs)
+    slab_wgrad_reduce_kernel<32><<<rgrid, 32 * 32, 0, st>>>(partial, gb ? bias_partial : nullptr, grid, plan.G, NPt, S, Cin, Cin_p, Cout,
+                                                            plan.PC, plan.PPS, plan.PPG, gw, gb);
+  else
+    slab_wgrad_reduce_kernel<8><<<rgrid, 8 * 32, 0, st>>>(partial, gb ? bias_partial : nullptr, grid, plan.G, NPt, S, Cin, Cin_p, Cout,
+                                                          plan.PC, plan.PPS, plan.PPG, gw, gb);
   SHB_LAUNCH_CHECK();
   return 0;
 }
