@@ -43,30 +43,32 @@ __global__ void __launch_bounds__(256) l1_bwd_kernel(const T* __restrict__ a, co
 
 // ------------------------------------------------------------------------------------------------ column sums
 // out[c] = sum_b x[b][c] (the bias gradient of an nn.Linear: models.py:129,142), x row-major (B, N), fp32 result.
-// A CTA owns 256 columns: thread (v = tid & 31, rg = tid >> 5) adds rows rg, rg + 8, ... of the 8-column vector v (16-byte
-// loads for bf16, coalesced across the warp, eight in flight), the eight row groups are added in index order through shared
-// memory.  Fixed order, no atomics.  (ATen's reduce kernel ran this with 2 CTAs for N = 256: 15 us of latency.)
+// A CTA owns VPC 8-column vectors: thread (v, rg) adds rows rg, rg + RG, ... of vector v (16-byte loads for bf16, coalesced
+// across the vectors, eight in flight), the RG row groups are added in index order through shared memory.  Fixed order, no
+// atomics.  (ATen's reduce kernel ran this with 2 CTAs for N = 256: 15 us of latency.)
 constexpr int CS_ROWGROUPS = 8;
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int B, int N, float* __restrict__ out) {
-  __shared__ float part[CS_ROWGROUPS][32][9];
-  const int v = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int c0 = (blockIdx.x * 32 + v) * 8;
+// VPC = 8-column vectors per CTA, RG = row groups: (16, 16) for long rows (N / 128 CTAs, all resident at once), (32, 32) for
+// short ones (a single CTA for N = 256 -- its 1024 threads then need one round of eight loads each instead of four)
+template <typename T, int VPC, int RG>
+__global__ void __launch_bounds__(VPC * RG, 1024 / (VPC * RG)) colsum_kernel(const T* __restrict__ x, int B, int N, float* __restrict__ out) {
+  __shared__ float part[RG][VPC][9];
+  const int v = threadIdx.x % VPC, rg = threadIdx.x / VPC;
+  const int c0 = (blockIdx.x * VPC + v) * 8;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (c0 < N) {
     int b = rg;
-    for (; b + 7 * CS_ROWGROUPS < B; b += 8 * CS_ROWGROUPS) {
+    for (; b + 7 * RG < B; b += 8 * RG) {
       float r[8][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) Io<T>::ld8(x + (size_t)(b + k * CS_ROWGROUPS) * N + c0, r[k]);
+      for (int k = 0; k < 8; ++k) Io<T>::ld8(x + (size_t)(b + k * RG) * N + c0, r[k]);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += r[k][e];
     }
-    for (; b < B; b += CS_ROWGROUPS) {
+    for (; b < B; b += RG) {
       float r[8];
       Io<T>::ld8(x + (size_t)b * N + c0, r);
 #pragma unroll
@@ -76,13 +78,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
 #pragma unroll
   for (int e = 0; e < 8; ++e) part[rg][v][e] = acc[e];
   __syncthreads();
-  const int col = threadIdx.x, cv = col >> 3, ce = col & 7;
-  const int c = blockIdx.x * 256 + col;
-  if (c < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < CS_ROWGROUPS; ++k) s += part[k][cv][ce];
-    out[c] = s;
+  const int col = threadIdx.x;
+  if (col < VPC * 8) {
+    const int c = blockIdx.x * VPC * 8 + col;
+    if (c < N) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < RG; ++k) s += part[k][col >> 3][col & 7];
+      out[c] = s;
+    }
   }
 }
 
@@ -191,9 +195,15 @@ int shb_colsum(const void* x, int dtype, int B, int N, float* out, void* stream)
     SHB_LAUNCH_CHECK();
     return 0;
   }
-  const int grid = (N + 255) / 256;
-  if (dtype == SHB_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, N, out);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, N, out);
+  if ((long long)N >= 128LL * kNumSMs) {
+    const int grid = (N + 127) / 128;
+    if (dtype == SHB_F32) colsum_kernel<float, 16, 16><<<grid, 256, 0, st>>>((const float*)x, B, N, out);
+    else colsum_kernel<__nv_bfloat16, 16, 16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, N, out);
+  } else {
+    const int grid = (N + 255) / 256;
+    if (dtype == SHB_F32) colsum_kernel<float, 32, 32><<<grid, 1024, 0, st>>>((const float*)x, B, N, out);
+    else colsum_kernel<__nv_bfloat16, 32, 32><<<grid, 1024, 0, st>>>((const __nv_bfloat16*)x, B, N, out);
+  }
   SHB_LAUNCH_CHECK();
   return 0;
 }

@@ -599,12 +599,13 @@ __global__ void __launch_bounds__(CV_THREADS) slab_to_rows_narrow_kernel(const u
 // ascending order, block_sum; slab_l1_final_kernel adds the CTA partials in index order).  MODE 1: the gradient slab
 // gscale / n * sign(d), times act'(rec) of the producer, dummy row zeroed when the producer masks it.
 template <typename T, int P, int MODE>
-__global__ void __launch_bounds__(CV_THREADS) slab_l1_kernel(const uint8_t* __restrict__ rec, const T* __restrict__ target,
+__global__ void __launch_bounds__(CV_THREADS, 3) slab_l1_kernel(const uint8_t* __restrict__ rec, const T* __restrict__ target,
                                                              const int32_t* __restrict__ pos, float* __restrict__ partials,
                                                              const float* __restrict__ gscale, uint8_t* __restrict__ gdst, int B,
                                                              int R, int Cs, float n_elems, int act, int zero_last) {
   extern __shared__ __align__(16) uint8_t cv_smem[];
   __shared__ float red[CV_THREADS / 32];
+  __shared__ int pos_s[CV_ROWS];   // internal row of each of the tile's rows: read once per tile, not once per item
   float* t = reinterpret_cast<float*>(cv_smem);
   const int NB = num_chunks(B), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = (CV_ROWS * Cs) | 1;
@@ -615,6 +616,7 @@ __global__ void __launch_bounds__(CV_THREADS) slab_l1_kernel(const uint8_t* __re
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int q = tile / rblocks, c0 = (tile - q * rblocks) * CV_ROWS;
     const int nrows = R - c0 < CV_ROWS ? R - c0 : CV_ROWS, len = nrows * Cs;
+    if (tid < nrows) pos_s[tid] = pos != nullptr ? __ldg(pos + c0 + tid) : c0 + tid;
     for (int e = lane; e < len; e += 32) {
       float tmp[CHUNK / (CV_THREADS / 32)];
 #pragma unroll
@@ -626,14 +628,42 @@ __global__ void __launch_bounds__(CV_THREADS) slab_l1_kernel(const uint8_t* __re
       for (int k = 0; k < CHUNK / (CV_THREADS / 32); ++k) t[(warp + k * (CV_THREADS / 32)) * stride + e] = tmp[k];
     }
     __syncthreads();
-#pragma unroll 2
-    for (int it = tid; it < nrows * CHUNK; it += CV_THREADS) {
+    // four items of a thread at a time: their slab vectors are requested together (unrolled by hand -- left to the
+    // compiler the loads end up interleaved with the arithmetic that waits for them)
+    constexpr int NBATCH = 4;
+    for (int it0 = tid; it0 < nrows * CHUNK; it0 += NBATCH * CV_THREADS) {
+      uint4 raw[NBATCH][P];
+      size_t offs[NBATCH];
+      int ris[NBATCH];
+#pragma unroll
+      for (int u = 0; u < NBATCH; ++u) {
+        const int it = it0 + u * CV_THREADS;
+        ris[u] = -1;
+        offs[u] = 0;
+        if (it < nrows * CHUNK) {
+          const int j = it >> 7;
+          ris[u] = pos_s[j];
+          offs[u] = ((size_t)ris[u] * NB + q) * slab_b + (size_t)(it & (CHUNK - 1)) * 16;
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) raw[u][pl] = __ldg(reinterpret_cast<const uint4*>(rec + offs[u] + pl * plane_b));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NBATCH; ++u) {
+      if (ris[u] < 0) continue;
+      const int it = it0 + u * CV_THREADS;
       const int j = it >> 7, bl = it & (CHUNK - 1);
-      const int ri = pos != nullptr ? __ldg(pos + c0 + j) : c0 + j;
-      const size_t off = ((size_t)ri * NB + q) * slab_b + (size_t)bl * 16;
+      const int ri = ris[u];
+      const size_t off = offs[u];
       const bool live = q * CHUNK + bl < B;
       float y[8];
-      cv_load_slab8<P>(rec + off, plane_b, y);
+      unpack8(raw[u][0], y);
+      if (P == 2) {
+        float l[8];
+        unpack8(raw[u][P - 1], l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] += l[e];
+      }
       if (MODE == 0) {
         if (live) {
 #pragma unroll
@@ -654,6 +684,7 @@ __global__ void __launch_bounds__(CV_THREADS) slab_l1_kernel(const uint8_t* __re
           if (act != SHB_ACT_IDENTITY) act_bwd8(v, y, act);
         }
         cv_store_slab8<P>(gdst + off, plane_b, v);
+      }
       }
     }
     __syncthreads();
