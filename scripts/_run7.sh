@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s7_tests.log 2>&1; tail -3 gpurun_out/s7_tests.log
 timeout 300 python bench.py --no-cpu-baseline --no-other-mode > gpurun_out/s7_bench.json 2> gpurun_out/s7_bench.err
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"slab_l1|colsum|reduce" --csv --log-file gpurun_out/s7_small_kernels.csv python bench.py --steps 3 --warmup 3 --no-graph --no-other-mode --no-cpu-baseline > gpurun_out/s7_ncu.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"slab_l1|colsum|rows" --csv --log-file gpurun_out/s7_small_kernels.csv python bench.py --steps 3 --warmup 3 --no-graph --no-other-mode --no-cpu-baseline > gpurun_out/s7_ncu.log 2>&1
 python - <<'P'
 import json,csv,collections
 d=json.loads(open('gpurun_out/s7_bench.json').read().strip().splitlines()[-1]); print(round(d['ms_per_step'],4), round(d['value']), round(d['e2e']['value']))

@@ -402,7 +402,7 @@ template <int P> __device__ __forceinline__ void cv_store_slab8(uint8_t* p, size
 
 // LG = log2(channel groups per tile) (1..4); tiles = R * NB * nsl, nsl = Cp / (8 << LG)
 template <typename T, int P, int LG>
-__global__ void __launch_bounds__(CV_THREADS) slab_from_rows_wide_kernel(const T* __restrict__ src, const int32_t* __restrict__ perm,
+__global__ void __launch_bounds__(CV_THREADS, 3) slab_from_rows_wide_kernel(const T* __restrict__ src, const int32_t* __restrict__ perm,
                                                                          uint8_t* __restrict__ dst,
                                                                          const uint8_t* __restrict__ ymul, int B, int R, int Cp,
                                                                          int act_mul, int zero_last, int nsl) {
@@ -417,7 +417,25 @@ __global__ void __launch_bounds__(CV_THREADS) slab_from_rows_wide_kernel(const T
     const bool zero = zero_last && r == R - 1;
     const int rs = perm != nullptr ? __ldg(perm + r) : r;
     // phase 1: row-major side, channel group fastest (a sample's channels are contiguous)
-    {
+    if constexpr (sizeof(T) == 2) {   // bf16 rows: the eight loads stay raw (4 registers each) until they are staged
+      const int cc = tid & (G - 1);
+      uint4 raw[ITEMS];
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int bl = (tid >> LG) + k * (CV_THREADS >> LG), b = q * CHUNK + bl;
+        raw[k] = (b < B && !zero) ? __ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * R + rs) * Cp + (size_t)(sl * G + cc) * 8))
+                                  : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int bl = (tid >> LG) + k * (CV_THREADS >> LG);
+        float v[8];
+        unpack8(raw[k], v);
+        float4* d = reinterpret_cast<float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
+        d[0] = make_float4(v[0], v[1], v[2], v[3]);
+        d[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
       const int cc = tid & (G - 1);
       float v[ITEMS][8];
 #pragma unroll
@@ -439,27 +457,49 @@ __global__ void __launch_bounds__(CV_THREADS) slab_from_rows_wide_kernel(const T
       }
     }
     __syncthreads();
-    // phase 2: slab side, sample fastest
+    // phase 2: slab side, sample fastest; the producer's outputs for act' are requested four items ahead (all eight would
+    // cost a third resident CTA: measured 21 -> 30 us)
+    const bool with_y = ymul != nullptr && !zero;
+    constexpr int HB = ITEMS < 4 ? ITEMS : 4;
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      const int it = tid + k * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
-      const float4* t4 = reinterpret_cast<const float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
-      const float4 a = t4[0], c = t4[1];
-      float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-      const size_t doff = ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16;
-      if (ymul != nullptr && !zero && q * CHUNK + bl < B) {
-        float y[8];
-        cv_load_slab8<P>(ymul + doff, plane_b, y);
-        act_bwd8(v, y, act_mul);
+    for (int k0 = 0; k0 < ITEMS; k0 += HB) {
+      uint4 yraw[HB][P];
+      if (with_y) {
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+          const int it = tid + (k0 + u) * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
+          const uint8_t* a = ymul + ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16;
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) yraw[u][pl] = __ldg(reinterpret_cast<const uint4*>(a + pl * plane_b));
+        }
       }
-      cv_store_slab8<P>(dst + doff, plane_b, v);
+#pragma unroll
+      for (int u = 0; u < HB; ++u) {
+        const int it = tid + (k0 + u) * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
+        const float4* t4 = reinterpret_cast<const float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
+        const float4 a = t4[0], c = t4[1];
+        float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        const size_t doff = ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16;
+        if (with_y && q * CHUNK + bl < B) {
+          float y[8];
+          unpack8(yraw[u][0], y);
+          if (P == 2) {
+            float l[8];
+            unpack8(yraw[u][P - 1], l);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] += l[e];
+          }
+          act_bwd8(v, y, act_mul);
+        }
+        cv_store_slab8<P>(dst + doff, plane_b, v);
+      }
     }
     __syncthreads();
   }
 }
 
 template <typename T, int P, int LG>
-__global__ void __launch_bounds__(CV_THREADS) slab_to_rows_wide_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ perm,
+__global__ void __launch_bounds__(CV_THREADS, 3) slab_to_rows_wide_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ perm,
                                                                        T* __restrict__ dst, int B, int R, int Cp, int nsl) {
   extern __shared__ __align__(16) uint8_t cv_smem[];
   constexpr int G = 1 << LG;
@@ -471,18 +511,30 @@ __global__ void __launch_bounds__(CV_THREADS) slab_to_rows_wide_kernel(const uin
     const int sl = tile % nsl, rq = tile / nsl, q = rq % NB, r = rq / NB;
     const int rd = perm != nullptr ? __ldg(perm + r) : r;
     {
-      float v[ITEMS][8];
+      // all of a thread's slab vectors are requested before the first is unpacked (kept as raw 16-byte words: unpacked at
+      // load they cost 8 registers each and the compiler then interleaves loads and shared-memory stores, two in flight)
+      uint4 raw[ITEMS][P];
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         const int it = tid + k * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
-        cv_load_slab8<P>(src + ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16, plane_b, v[k]);
+        const uint8_t* a = src + ((size_t)r * NB + q) * slab_b + (size_t)(sl * G + cc) * PLANE_STRIDE + (size_t)bl * 16;
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) raw[k][pl] = __ldg(reinterpret_cast<const uint4*>(a + pl * plane_b));
       }
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         const int it = tid + k * CV_THREADS, bl = it & (CHUNK - 1), cc = it >> 7;
+        float v[8];
+        unpack8(raw[k][0], v);
+        if (P == 2) {
+          float l[8];
+          unpack8(raw[k][P - 1], l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += l[e];
+        }
         float4* d = reinterpret_cast<float4*>(cv_smem + (size_t)cc * CV_GROUP_STRIDE + (size_t)bl * 32);
-        d[0] = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
-        d[1] = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
+        d[0] = make_float4(v[0], v[1], v[2], v[3]);
+        d[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
     __syncthreads();
@@ -507,7 +559,7 @@ constexpr int CV_ROWS = 32;   // rows (caller's numbering) per narrow tile
 
 // pos[c] = internal row of the caller's row c (the inverse of perm; null: identity).  Cs <= 8 channels, Cp == 8.
 template <typename T, int P>
-__global__ void __launch_bounds__(CV_THREADS) slab_from_rows_narrow_kernel(const T* __restrict__ src, const int32_t* __restrict__ pos,
+__global__ void __launch_bounds__(CV_THREADS, 3) slab_from_rows_narrow_kernel(const T* __restrict__ src, const int32_t* __restrict__ pos,
                                                                            uint8_t* __restrict__ dst,
                                                                            const uint8_t* __restrict__ ymul, int B, int R, int Cs,
                                                                            int act_mul, int zero_last) {
@@ -558,9 +610,10 @@ __global__ void __launch_bounds__(CV_THREADS) slab_from_rows_narrow_kernel(const
 }
 
 template <typename T, int P>
-__global__ void __launch_bounds__(CV_THREADS) slab_to_rows_narrow_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ pos,
+__global__ void __launch_bounds__(CV_THREADS, 3) slab_to_rows_narrow_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ pos,
                                                                          T* __restrict__ dst, int B, int R, int Cd) {
   extern __shared__ __align__(16) uint8_t cv_smem[];
+  __shared__ int pos_s[CV_ROWS];
   float* t = reinterpret_cast<float*>(cv_smem);
   const int NB = num_chunks(B), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = (CV_ROWS * Cd) | 1;
@@ -569,15 +622,39 @@ __global__ void __launch_bounds__(CV_THREADS) slab_to_rows_narrow_kernel(const u
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int q = tile / rblocks, c0 = (tile - q * rblocks) * CV_ROWS;
     const int nrows = R - c0 < CV_ROWS ? R - c0 : CV_ROWS, len = nrows * Cd;
-#pragma unroll 4
-    for (int it = tid; it < nrows * CHUNK; it += CV_THREADS) {
-      const int j = it >> 7, bl = it & (CHUNK - 1);
-      const int ri = pos != nullptr ? __ldg(pos + c0 + j) : c0 + j;
-      float v[8];
-      cv_load_slab8<P>(src + ((size_t)ri * NB + q) * slab_b + (size_t)bl * 16, plane_b, v);
+    if (tid < nrows) pos_s[tid] = pos != nullptr ? __ldg(pos + c0 + tid) : c0 + tid;
+    __syncthreads();
+    // four items of a thread at a time, their slab vectors requested together (row positions from shared memory: fetched
+    // per item from global memory they put a dependent load in front of every slab load)
+    for (int it0 = tid; it0 < nrows * CHUNK; it0 += 4 * CV_THREADS) {
+      uint4 raw[4][P];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (e < Cd) t[bl * stride + j * Cd + e] = v[e];
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * CV_THREADS;
+        if (it < nrows * CHUNK) {
+          const uint8_t* a = src + ((size_t)pos_s[it >> 7] * NB + q) * slab_b + (size_t)(it & (CHUNK - 1)) * 16;
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) raw[u][pl] = __ldg(reinterpret_cast<const uint4*>(a + pl * plane_b));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * CV_THREADS;
+        if (it < nrows * CHUNK) {
+          const int j = it >> 7, bl = it & (CHUNK - 1);
+          float v[8];
+          unpack8(raw[u][0], v);
+          if (P == 2) {
+            float l[8];
+            unpack8(raw[u][P - 1], l);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += l[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < Cd) t[bl * stride + j * Cd + e] = v[e];
+        }
+      }
     }
     __syncthreads();
     for (int bl = warp; bl < CHUNK; bl += CV_THREADS / 32) {
