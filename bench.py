@@ -420,7 +420,11 @@ def run_own(args):
             "other_mode": other, "loss": last_loss, "loss_e2e_mean": seen / args.steps,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in kernels[:12]},
             "kernel_families_ms_per_step": families,
-            "algorithmic_per_step": {"gflop_convs_pools": step_flops / 1e9, "gbytes": step_bytes / 1e9}}
+            # whole-step rates of the same algorithmic counts (per GPU; graph-replayed step time, not the instrumented pass)
+            "algorithmic_per_step": {"gflop_convs_pools": step_flops / 1e9, "gbytes": step_bytes / 1e9,
+                                     "gbytes_per_s": step_bytes / 1e9 / (ms / args.steps * 1e-3),
+                                     "tflop_per_s": step_flops / 1e12 / (ms / args.steps * 1e-3),
+                                     "frac_of_hbm_peak": step_bytes / 1e9 / (ms / args.steps * 1e-3) / peaks["hbm_gbs"]}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
