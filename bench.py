@@ -233,7 +233,10 @@ def run_own(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     from semantichuman_b200.dp import bind_host_to_device, init_data_parallel
 
-    args.host_cpus = None if args.no_numa_bind else bind_host_to_device(local)  # before any pinned allocation
+    # Pin the process to the GPU's NUMA node before any pinned allocation -- except in the process that also times the CPU
+    # baseline on "all host cores" (N = 1, rank 0): its worker threads would inherit the narrowed mask.
+    runs_cpu_leg = world == 1 and not args.no_cpu_baseline
+    args.host_cpus = None if (args.no_numa_bind or runs_cpu_leg) else bind_host_to_device(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
